@@ -1,0 +1,188 @@
+/*
+ * wgg.h - C ABI of libwgg_sm100.so: the B200 (sm_100a) implementation of the WordGesture-GAN
+ * training-step hot path.
+ *
+ * The reference (edwarddgao/WordGesture-GAN) is pure Python/PyTorch and has NO FFI of its own
+ * (SURVEY.md 2.2); each entry point below therefore cites the reference *Python* interface whose
+ * arithmetic it replaces (file:line relative to the reference root).  The Python host layer in
+ * wordgesture-gan_b200/ binds these with ctypes from torch.autograd.Function.forward/backward
+ * (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor is fp32, contiguous, device memory owned by the caller;
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (void*), never synchronises the
+ *     host and never allocates device memory: scratch comes from the caller (`ws`, sized by the
+ *     *_workspace_floats() queries) - so a whole training step is CUDA-graph capturable;
+ *   - return value: 0 = WGG_OK, negative = error; wgg_last_error(ctx) gives the message;
+ *   - one wgg_ctx per process/GPU; not thread-safe;
+ *   - parameter vectors are FLAT: the module's tensors concatenated in `named_parameters()` order
+ *     (the order torch.optim.Adam indexes them in, src/gan/trainer.py:60-79,208-211);
+ *     spectral-norm buffers are flat in state_dict order (weight_u, weight_v per layer);
+ *   - gradients w.r.t. parameters are ACCUMULATED (+=) into `dparams` (autograd `.grad` semantics).
+ */
+#ifndef WGG_H_
+#define WGG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WGG_API __attribute__((visibility("default")))
+#else
+#define WGG_API
+#endif
+
+enum {
+  WGG_OK = 0,
+  WGG_EINVAL = -1,       /* bad argument / shape */
+  WGG_ECUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  WGG_EUNSUPPORTED = -3, /* configuration not covered by a compiled kernel */
+  WGG_EWORKSPACE = -4    /* workspace too small */
+};
+
+#define WGG_MAX_HIDDEN_LAYERS 8
+
+/* Mirror of ModelConfig (src/shared/config.py:11-33). */
+typedef struct wgg_model_cfg {
+  int32_t seq_length;         /* T, 128 */
+  int32_t input_dim;          /* 3 */
+  int32_t latent_dim;         /* Z, 32 */
+  int32_t gen_hidden_dim;     /* H, 48 */
+  int32_t gen_num_layers;     /* L, 4 */
+  int32_t prototype_has_time; /* 0 -> generator sees (x,y) only */
+  int32_t use_temporal_disc;  /* 1 -> TemporalDiscriminator (Conv1D), 0 -> MLP Discriminator */
+  int32_t n_enc_hidden;
+  int32_t enc_hidden_dims[WGG_MAX_HIDDEN_LAYERS];
+  int32_t n_disc_hidden;
+  int32_t disc_hidden_dims[WGG_MAX_HIDDEN_LAYERS];
+} wgg_model_cfg;
+
+typedef struct wgg_ctx wgg_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+WGG_API int wgg_abi_version(void);
+WGG_API int wgg_create(wgg_ctx** out, int device);
+WGG_API void wgg_destroy(wgg_ctx* ctx);
+WGG_API const char* wgg_last_error(wgg_ctx* ctx);
+/* number of kernels launched through this ctx since creation (bench.py's gpu_launches) */
+WGG_API int64_t wgg_launch_count(wgg_ctx* ctx);
+/* Per-kernel-class device timing for roofline reporting: every launch whose kernel name contains
+ * `kernel_substr` ("gemm_kernel", "lstm_rec_fwd", ...) is bracketed by a CUDA event pair on its stream.
+ * NULL disables.  wgg_profile_read synchronises on the recorded events and returns the summed duration,
+ * the launch count and the algorithmic FLOPs / bytes those launches accounted for.  (max 16384 launches) */
+WGG_API int wgg_profile_enable(wgg_ctx* ctx, const char* kernel_substr);
+WGG_API int wgg_profile_read(wgg_ctx* ctx, double* total_ms, int64_t* launches, double* flops, double* bytes);
+/* math mode: 0 = fp32 FMA everywhere (default), 1 = TF32 tensor-core contractions where available */
+WGG_API int wgg_set_math_mode(wgg_ctx* ctx, int mode);
+
+/* ---- Generator: replaces Generator.forward, src/gan/models.py:125-165 (+ its autograd) --------
+ * params layout: nn.LSTM order - per layer, per direction: weight_ih (4H,I), weight_hh (4H,H),
+ * bias_ih (4H), bias_hh (4H); then output_layer.weight (3,2H), output_layer.bias (3).
+ * proto (B,T,3), z (B,Z) -> out (B,T,3).  stash == NULL: inference / no-grad (eval_gan.py:131-135). */
+WGG_API int64_t wgg_generator_param_floats(const wgg_model_cfg* cfg);
+WGG_API int64_t wgg_generator_stash_floats(const wgg_model_cfg* cfg, int64_t B);
+WGG_API int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int64_t B, int backward);
+WGG_API int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
+                          const float* z, int64_t B, float* out, float* stash, float* ws, int64_t ws_floats,
+                          void* stream);
+/* dout (B,T,3) -> dparams (+=), dz (B,Z) (overwritten; may be NULL).  `stash` is consumed (overwritten). */
+WGG_API int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, int64_t B, float* stash,
+                           const float* out, const float* dout, float* dparams, float* dz, float* ws,
+                           int64_t ws_floats, void* stream);
+
+/* ---- VariationalEncoder: replaces forward + reparameterize, src/gan/models.py:52-86 -----------
+ * params: encoder.{0,2,..}.weight/bias, fc_mu.weight/bias, fc_log_var.weight/bias.
+ * eps (B,Z) is the caller-drawn normal noise (torch.randn_like at models.py:85 - RNG stays in torch). */
+WGG_API int64_t wgg_encoder_param_floats(const wgg_model_cfg* cfg);
+WGG_API int64_t wgg_encoder_stash_floats(const wgg_model_cfg* cfg, int64_t B);
+WGG_API int64_t wgg_encoder_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
+WGG_API int wgg_encoder_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                        const float* eps, int64_t B, float* z, float* mu, float* log_var, float* stash,
+                        void* stream); /* stash (wgg_encoder_stash_floats) is required: it is also the activation scratch */
+/* dz, dmu, dlog_var (B,Z) (any may be NULL = zero) -> dparams (+=), dx (B,T,3) (overwritten; may be NULL). */
+WGG_API int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                         const float* eps, const float* log_var, int64_t B, const float* stash, const float* dz,
+                         const float* dmu, const float* dlog_var, float* dparams, float* dx, float* ws,
+                         int64_t ws_floats, void* stream);
+
+/* ---- Discriminators: replace [Temporal]Discriminator.forward / get_all_features,
+ * src/gan/models.py:202-243,293-353, including the spectral_norm pre-forward hook
+ * (torch/nn/utils/spectral_norm.py:62-114).
+ * params: per layer bias then weight_orig (named_parameters order).  uv: per layer weight_u, weight_v.
+ * wgg_disc_spectral runs ONE power iteration per layer in place on uv when `training` (skipping the
+ * output layer when with_output_layer == 0, as get_all_features does), and fills `sn` with the
+ * effective weights W_orig/sigma (kernel-ready layouts) + the (u, v, sigma) snapshot backward needs. */
+WGG_API int64_t wgg_disc_param_floats(const wgg_model_cfg* cfg);
+WGG_API int64_t wgg_disc_uv_floats(const wgg_model_cfg* cfg);
+WGG_API int64_t wgg_disc_sn_floats(const wgg_model_cfg* cfg);
+WGG_API int64_t wgg_disc_stash_floats(const wgg_model_cfg* cfg, int64_t B);
+WGG_API int64_t wgg_disc_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
+WGG_API int32_t wgg_disc_num_features(const wgg_model_cfg* cfg);
+/* offset (floats) and per-sample width of feature k inside the stash (stash holds [B, width] blocks;
+ * conv features are channel-last (B,T,C)). */
+WGG_API int64_t wgg_disc_feature_offset(const wgg_model_cfg* cfg, int64_t B, int32_t k);
+WGG_API int32_t wgg_disc_feature_width(const wgg_model_cfg* cfg, int32_t k);
+WGG_API int wgg_disc_spectral(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* uv, int training,
+                      int with_output_layer, float* sn, void* stream);
+/* x (B,T,3) -> score (B,1) (NULL = features only), stash (features + pooled activations). */
+WGG_API int wgg_disc_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* sn, const float* x,
+                     int64_t B, float* score, float* stash, void* stream);
+/* dscore (B,1) and/or dfeat (stash layout; only feature blocks are read) may be NULL.
+ * dparams (+=) may be NULL (generator step: discriminator weight grads are discarded, utils.py:75,96);
+ * dx (B,T,3) may be NULL (critic step). */
+WGG_API int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* sn, const float* x,
+                      int64_t B, const float* stash, const float* dscore, const float* dfeat, float* dparams,
+                      float* dx, float* ws, int64_t ws_floats, void* stream);
+/* (B, T, C) channel-last feature block -> (B, C*T) as get_all_features returns it (models.py:339). */
+WGG_API int wgg_transpose_tc(wgg_ctx* ctx, const float* in, float* out, int64_t B, int32_t T, int32_t C, void* stream);
+
+/* ---- Losses: replace src/gan/losses.py ------------------------------------------------------
+ * All scalar results are written to DEVICE floats (no host sync); backward entry points take the
+ * upstream scalar gradient as a device float pointer `g` (NULL = 1.0). */
+/* out[0] = scale * mean(x[0..n)) (+ out[0] if accumulate)            losses.py:43,58 */
+WGG_API int wgg_mean(wgg_ctx* ctx, const float* x, int64_t n, float scale, int accumulate, float* out, void* stream);
+/* dx[i] = g * scale / n                                                 */
+WGG_API int wgg_mean_backward(wgg_ctx* ctx, const float* g, float scale, int64_t n, float* dx, void* stream);
+/* out[0] = scale * mean|a-b|                                          losses.py:120,147 */
+WGG_API int wgg_l1_mean(wgg_ctx* ctx, const float* a, const float* b, int64_t n, float scale, int accumulate, float* out,
+                void* stream);
+/* da[i] (+)= g * scale * sign(a-b) / n                                  */
+WGG_API int wgg_l1_mean_backward(wgg_ctx* ctx, const float* a, const float* b, const float* g, float scale, int64_t n,
+                         int accumulate, float* da, void* stream);
+/* FeatureMatchingLoss over discriminator stashes (layout-invariant)    losses.py:86-93 */
+WGG_API int wgg_feature_matching(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* real_stash, const float* fake_stash,
+                         int64_t B, float scale, int accumulate, float* out, void* stream);
+WGG_API int wgg_feature_matching_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* real_stash,
+                                  const float* fake_stash, const float* g, float scale, int64_t B, float* dfeat,
+                                  void* stream);
+/* KLDivergenceLoss                                                     losses.py:174-175 */
+WGG_API int wgg_kl(wgg_ctx* ctx, const float* mu, const float* log_var, int64_t B, int32_t Z, float scale, int accumulate,
+           float* out, void* stream);
+WGG_API int wgg_kl_backward(wgg_ctx* ctx, const float* mu, const float* log_var, const float* g, float scale, int64_t B,
+                    int32_t Z, float* dmu, float* dlog_var, void* stream);
+
+/* ---- Optimiser step: replaces clip_grad_norm_ + Adam.step, src/shared/utils.py:87-88,108-109,132-135
+ * One fused pass over the module's flat buffers: total L2 norm -> clip coefficient
+ * min(1, max_norm/(norm+1e-6)) -> bias-corrected Adam (torch.optim.Adam, no weight decay/amsgrad).
+ * `step` is the 1-based step count AFTER increment.  max_norm <= 0 disables clipping.
+ * grad_norm_out: optional device float receiving the pre-clip norm.  g is scaled in place like
+ * clip_grad_norm_ does.  ws needs wgg_clip_adam_workspace_floats() floats. */
+WGG_API int64_t wgg_clip_adam_workspace_floats(void);
+WGG_API int wgg_clip_adam(wgg_ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, float max_norm, float* grad_norm_out, float* ws,
+                  void* stream);
+
+/* ---- generic building block exposed for tests/bench: C[M,N] = act(A[M,K] * W[N,K]^T + bias) ---- */
+WGG_API int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
+               int32_t K, int act /*0 none, 1 leaky(0.2), 2 tanh*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGG_H_ */

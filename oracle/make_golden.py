@@ -252,9 +252,25 @@ def pack(name, r, full: bool):
     return path
 
 
+def write_init_fixture(ref):
+    """Summaries of the reference's seed-42 fp32 initial state (default config), for the init-parity test."""
+    ref.utils.seed_everything(42)
+    trainer = ref.trainer.WordGestureGANTrainer(device="cpu")
+    out = {}
+    for n, m in (("G", "generator"), ("E", "encoder"), ("D1", "discriminator_1"), ("D2", "discriminator_2")):
+        sd = getattr(trainer, m).state_dict()
+        out[f"order/{n}"] = np.array(list(sd.keys()))
+        for k, v in sd.items():
+            out[f"{n}/{k}"] = summarise(v.numpy())
+    path = os.path.join(GOLDEN_DIR, "init_seed42.npz")
+    np.savez_compressed(path, **out)
+    print(f"[golden] wrote {path}")
+
+
 def main():
     ref = load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    write_init_fixture(ref)
     for name, (kw, B, seed) in CASES.items():
         r = run_reference_step(ref, kw, B, seed)
         full = name != "default"

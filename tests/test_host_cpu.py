@@ -1,0 +1,158 @@
+"""CPU-only checks of the host layer: the C-ABI library loads and exports every symbol include/wgg.h declares,
+flat-parameter layouts agree between Python and C, construction reproduces the reference's state-dict contract,
+and compute entry points refuse to run without a CUDA device (no silent fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import wgg_b200 as wgg
+from golden_util import Golden, summarise
+from wgg_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "wgg.h")).read()
+    return sorted(set(re.findall(r"WGG_API\s+[\w\s\*]+?\b(wgg_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 39
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/wgg.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms, "ctypes signature table and header disagree"
+    assert _lib.lib().wgg_abi_version() == 1
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_temporal_disc=False), dict(prototype_has_time=True, gen_hidden_dim=32),
+                                dict(seq_length=16, latent_dim=4, gen_hidden_dim=8, gen_num_layers=2,
+                                     enc_hidden_dims=(24, 12, 8, 6), disc_hidden_dims=(20, 12, 8, 6))])
+def test_flat_layout_sizes_agree_with_c(kw):
+    mc = wgg.ModelConfig(**kw)
+    lib = _lib.lib()
+    cfg = _lib.c_cfg(mc)
+    G, E = wgg.Generator(mc), wgg.VariationalEncoder(mc)
+    D = (wgg.TemporalDiscriminator if mc.use_temporal_disc else wgg.Discriminator)(mc)
+    assert lib.wgg_generator_param_floats(cfg) == G.flat_params().numel()
+    assert lib.wgg_encoder_param_floats(cfg) == E.flat_params().numel()
+    assert lib.wgg_disc_param_floats(cfg) == D.flat_params().numel()
+    assert lib.wgg_disc_uv_floats(cfg) == D.flat_buffers().numel()
+    # parameters are views of the flat buffer, in named_parameters order
+    off = 0
+    flat = G.flat_params()
+    for p in G.parameters():
+        assert p.data_ptr() == flat.data_ptr() + 4 * off
+        off += p.numel()
+    B = 7
+    nf = lib.wgg_disc_num_features(cfg)
+    widths = [lib.wgg_disc_feature_width(cfg, k) for k in range(nf)]
+    if mc.use_temporal_disc:
+        assert widths == [mc.seq_length * 64, mc.seq_length * 64, mc.seq_length * 32, 128, 64]
+    else:
+        assert widths == list(mc.disc_hidden_dims)
+    assert lib.wgg_disc_stash_floats(cfg, B) >= B * sum(widths)
+    assert lib.wgg_generator_stash_floats(cfg, B) == mc.seq_length * B * (
+        (3 if mc.prototype_has_time else 2) + mc.latent_dim + 12 * mc.gen_hidden_dim * mc.gen_num_layers)
+
+
+def test_state_dict_contract_default():
+    """Keys / shapes / order listed in SURVEY.md section 8b (measured on the reference)."""
+    G = wgg.Generator()
+    keys = list(G.state_dict())
+    assert keys[:4] == ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0"]
+    assert keys[4] == "lstm.weight_ih_l0_reverse" and keys[-2:] == ["output_layer.weight", "output_layer.bias"]
+    assert tuple(G.state_dict()["lstm.weight_ih_l0"].shape) == (192, 34)
+    assert tuple(G.state_dict()["lstm.weight_ih_l1"].shape) == (192, 96)
+    E = wgg.VariationalEncoder()
+    assert list(E.state_dict()) == ["encoder.0.weight", "encoder.0.bias", "encoder.2.weight", "encoder.2.bias",
+                                    "encoder.4.weight", "encoder.4.bias", "encoder.6.weight", "encoder.6.bias",
+                                    "fc_mu.weight", "fc_mu.bias", "fc_log_var.weight", "fc_log_var.bias"]
+    D = wgg.TemporalDiscriminator()
+    assert list(D.state_dict())[:4] == ["temporal_conv.0.bias", "temporal_conv.0.weight_orig",
+                                        "temporal_conv.0.weight_u", "temporal_conv.0.weight_v"]
+    assert [k for k, _ in D.named_parameters()][-2:] == ["output_layer.bias", "output_layer.weight_orig"]
+    assert tuple(D.state_dict()["temporal_conv.2.weight_v"].shape) == (320,)
+    M = wgg.Discriminator()
+    assert list(M.state_dict())[:4] == ["layers.0.bias", "layers.0.weight_orig", "layers.0.weight_u", "layers.0.weight_v"]
+    assert sum(p.numel() for p in G.parameters()) == 200739
+    assert sum(p.numel() for p in E.parameters()) == 100784
+    assert sum(p.numel() for p in D.parameters()) == 68961
+    assert sum(p.numel() for p in M.parameters()) == 98305
+
+
+def test_seed42_init_matches_reference_fixture():
+    """seed_everything(42) + trainer construction reproduces the reference's initial weights bit for bit
+    (fixture written by oracle/make_golden.py from the reference's own constructor)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "init_seed42.npz"))
+    wgg.seed_everything(42)
+    tr = wgg.WordGestureGANTrainer(device="cpu")
+    for n, attr in (("G", "generator"), ("E", "encoder"), ("D1", "discriminator_1"), ("D2", "discriminator_2")):
+        sd = getattr(tr, attr).state_dict()
+        assert list(sd) == [str(k) for k in z[f"order/{n}"]]
+        for k, v in sd.items():
+            assert np.array_equal(summarise(v.numpy()), z[f"{n}/{k}"]), (n, k)
+
+
+def test_load_state_dict_keeps_flat_aliasing_and_deepcopy():
+    import copy
+    G = wgg.Generator()
+    sd = {k: torch.randn_like(v) for k, v in G.state_dict().items()}
+    G.load_state_dict(sd)
+    assert G._is_flat()
+    assert torch.equal(G.flat_params()[:192 * 34].view(192, 34), sd["lstm.weight_ih_l0"])
+    G2 = copy.deepcopy(G)
+    assert G2._is_flat() and G2.flat_params().data_ptr() != G.flat_params().data_ptr()
+    assert torch.equal(G2.flat_params(), G.flat_params())
+
+
+def test_no_cpu_fallback():
+    G = wgg.Generator()
+    with pytest.raises(_lib.WggError):
+        G(torch.zeros(2, 128, 3), torch.zeros(2, 32))
+    with pytest.raises(_lib.WggError):
+        wgg.VariationalEncoder()(torch.zeros(2, 128, 3))
+    with pytest.raises(_lib.WggError):
+        wgg.TemporalDiscriminator()(torch.zeros(2, 128, 3))
+
+
+def test_dropin_import_paths():
+    from wgg_b200 import dropin
+    dropin.install_as_src(force=True)
+    import importlib
+    m = importlib.import_module("src.gan.models")
+    assert m.Generator is wgg.Generator and m.TemporalDiscriminator is wgg.TemporalDiscriminator
+    t = importlib.import_module("src.gan.trainer")
+    assert t.WordGestureGANTrainer is wgg.WordGestureGANTrainer
+    u = importlib.import_module("src.shared.utils")
+    assert u.train_epoch_with_grad_clip is wgg.train_epoch_with_grad_clip and u.seed_everything is wgg.seed_everything
+    c = importlib.import_module("src.shared.config")
+    assert c.ModelConfig().gen_hidden_dim == 48 and c.TrainingConfig().n_critic == 5
+    from src.gan.losses import WassersteinLoss  # noqa
+    for k in [k for k in list(__import__("sys").modules) if k == "src" or k.startswith("src.")]:
+        del __import__("sys").modules[k]
+
+
+def test_optimizer_is_torch_optimizer_and_scheduler_compatible():
+    E = wgg.VariationalEncoder()
+    opt = wgg.FusedClipAdam(E, lr=2e-4, betas=(0.5, 0.999))
+    assert isinstance(opt, torch.optim.Optimizer)
+    sd = opt.state_dict()
+    assert sd["state"] == {} and sd["param_groups"][0]["params"] == list(range(12))
+    assert sd["param_groups"][0]["betas"] == (0.5, 0.999)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=200, eta_min=1e-5)
+    assert sched.get_last_lr()[0] == pytest.approx(2e-4)
+    # a reference-format Adam state dict (torch.optim.Adam) loads
+    ref_opt = torch.optim.Adam(wgg.VariationalEncoder().parameters(), lr=2e-4, betas=(0.5, 0.999))
+    for p in ref_opt.param_groups[0]["params"]:
+        p.grad = torch.ones_like(p)
+    ref_opt.step()
+    opt.load_state_dict(ref_opt.state_dict())
+    assert opt._step == 1
+    assert torch.allclose(opt._m, torch.full_like(opt._m, 0.5))

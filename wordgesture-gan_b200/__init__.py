@@ -1,0 +1,20 @@
+"""wordgesture-gan_b200: B200-native (sm_100a) implementation of the WordGesture-GAN training step.
+
+Python host layer over libwgg_sm100.so (C ABI in include/wgg.h).  Import as ``wgg_b200`` (the directory
+name contains a hyphen; the repo-root ``wgg_b200.py`` shim registers it).
+"""
+from .configs import DEFAULT_MODEL_CONFIG, DEFAULT_TRAINING_CONFIG, ModelConfig, TrainingConfig
+from .gan_losses import (FeatureMatchingLoss, KLDivergenceLoss, LatentEncodingLoss, ReconstructionLoss,
+                         WassersteinLoss, feature_matching_from_stash)
+from .gan_modules import Discriminator, Generator, TemporalDiscriminator, VariationalEncoder
+from .gan_trainer import WordGestureGANTrainer
+from .optim import FusedClipAdam
+from .train_step import log, seed_everything, train_batch, train_epoch_with_grad_clip
+
+__all__ = [
+    "ModelConfig", "TrainingConfig", "DEFAULT_MODEL_CONFIG", "DEFAULT_TRAINING_CONFIG",
+    "Generator", "VariationalEncoder", "Discriminator", "TemporalDiscriminator",
+    "WassersteinLoss", "FeatureMatchingLoss", "ReconstructionLoss", "LatentEncodingLoss", "KLDivergenceLoss",
+    "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam",
+    "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
+]

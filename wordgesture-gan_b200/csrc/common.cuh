@@ -1,0 +1,190 @@
+// Shared host/device helpers for libwgg_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "wgg.h"
+
+struct wgg_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int math_mode = 0;
+  int64_t launches = 0;
+  // device scratch for reduction partials (allocated once in wgg_create): a ring of slots so that
+  // consecutive reductions queued on one stream never share a slot with a finalize still in flight.
+  float* red_scratch = nullptr;
+  int red_slot = 0;
+  // optional per-kernel-class CUDA-event timing (bench.py's roofline): see wgg_profile_enable
+  bool prof_on = false;
+  char prof_filter[64] = {0};
+  static constexpr int kProfMax = 16384;
+  cudaEvent_t* prof_ev = nullptr;  // 2*kProfMax events, created lazily
+  int prof_n = 0;
+  double prof_flops = 0.0, prof_bytes = 0.0;
+  char err[512] = {0};
+};
+
+// RAII bracket: records a CUDA event pair around one launch of a profiled kernel class.
+struct ProfScope {
+  wgg_ctx* c;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(wgg_ctx* ctx, const char* name, cudaStream_t s, double flops, double bytes) : c(ctx), st(s) {
+    if (!c->prof_on || !strstr(name, c->prof_filter) || c->prof_n >= wgg_ctx::kProfMax) return;
+    idx = c->prof_n++;
+    c->prof_flops += flops;
+    c->prof_bytes += bytes;
+    cudaEventRecord(c->prof_ev[2 * idx], st);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->prof_ev[2 * idx + 1], st);
+  }
+};
+constexpr int kRedBlocks = 296;  // 2 x 148 SMs
+constexpr int kRedSlots = 64;
+inline float* wgg_next_partial(wgg_ctx* ctx) {
+  float* p = ctx->red_scratch + (size_t)ctx->red_slot * kRedBlocks;
+  ctx->red_slot = (ctx->red_slot + 1) % kRedSlots;
+  return p;
+}
+
+inline int wgg_fail(wgg_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b, c);
+  return code;
+}
+
+inline int wgg_check_launch(wgg_ctx* ctx, const char* name) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s: %s", name, cudaGetErrorString(e));
+    return WGG_ECUDA;
+  }
+  return WGG_OK;
+}
+
+#define WGG_CHECK_LAUNCH(ctx, name)             \
+  do {                                          \
+    int rc__ = wgg_check_launch((ctx), (name)); \
+    if (rc__ != WGG_OK) return rc__;            \
+  } while (0)
+
+#define WGG_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != WGG_OK) return rc__; \
+  } while (0)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr float kLeak = 0.2f;  // nn.LeakyReLU(0.2): src/gan/models.py:43,200,272
+
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_TANH = 2 };
+
+// ----------------------------------------------------------------------------------------------
+// generic contraction engine (gemm.cu)
+// C(m,n) = act( sum_k A(m,k) * B(k,n) + bias[n] + bias2[n] ),  fully strided operands, optional
+// batching, optional deterministic split-K, optional conv1d "sliding window" view of one operand.
+// ----------------------------------------------------------------------------------------------
+struct GemmP {
+  const float* A = nullptr;
+  const float* B = nullptr;
+  float* C = nullptr;
+  int64_t M = 0;
+  int64_t N = 0;
+  int64_t K = 0;
+  int64_t sam = 0, sak = 0;  // A(m,k) = A[m*sam + k*sak]
+  int64_t sbk = 0, sbn = 0;  // B(k,n) = B[k*sbk + n*sbn]
+  int64_t scm = 0, scn = 1;  // C(m,n) = C[m*scm + n*scn]
+  int nbatch = 1;
+  int64_t bsA = 0, bsB = 0, bsC = 0, bsBias = 0;
+  const float* bias = nullptr;
+  const float* bias2 = nullptr;
+  int act = ACT_NONE;
+  int accumulate = 0;  // C += result
+  // conv window: operand X (A if conv_mode==1 with (row,col)=(m,k); B if conv_mode==2 with (row,col)=(k,n))
+  // is a (rows = B*T, cols = ksize*Cin) sliding-window view of a channel-last (B,T,Cin) tensor:
+  // X(r,c) = base[(r - pad)*Cin + c] if 0 <= (r % T) + c / Cin - pad < T else 0.
+  int conv_mode = 0;
+  int conv_T = 0, conv_Cin = 0, conv_pad = 0;
+  // split-K: partial sums go to `partial` ([nbatch][splitk][M][N] dense) and are reduced deterministically.
+  int splitk = 1;
+  float* partial = nullptr;
+};
+
+int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
+// workspace (floats) a split-K GEMM of this shape may need
+int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch);
+int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch);
+
+// out[b][i] (+)= sum_s P[b][s][i]   (and the same into out2 if given)
+int reduce_partials_launch(wgg_ctx* ctx, const float* P, int S, int64_t n, int nbatch, int64_t bsP, float* out,
+                           float* out2, int64_t bsOut, int accumulate, cudaStream_t st);
+// out[n] (+)= sum_m X[m*ldx + n]  (two-stage, deterministic); ws >= colsum_ws_floats(N)
+int64_t colsum_ws_floats(int64_t N, int nbatch);
+int colsum_launch(wgg_ctx* ctx, const float* X, int64_t M, int64_t N, int64_t ldx, int nbatch, int64_t bsX,
+                  float* out, float* out2, int64_t bsOut, int accumulate, float* ws, cudaStream_t st);
+
+// ----------------------------------------------------------------------------------------------
+// small device helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in every thread. blockDim.x must be a multiple of 32 and <= 1024.
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nw ? sh[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__device__ __forceinline__ float leaky_f(float x) { return x > 0.f ? x : kLeak * x; }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ----------------------------------------------------------------------------------------------
+// shared elementwise launchers (ew.cu)
+// ----------------------------------------------------------------------------------------------
+// d[i] = (d[i] + (add ? add[i] : 0)) * (y[i] > 0 ? 1 : 0.2)      LeakyReLU backward (+ feature-grad injection)
+int leaky_bwd_launch(wgg_ctx* ctx, const float* y, float* d, const float* add, int64_t n, cudaStream_t st);
+int fill_launch(wgg_ctx* ctx, float* x, float v, int64_t n, cudaStream_t st);
+inline int ew_blocks(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ----------------------------------------------------------------------------------------------
+// dense-layer helpers (encoder.cu) shared with disc.cu
+// ----------------------------------------------------------------------------------------------
+int wgg_linear_fwd(wgg_ctx* ctx, const float* A, int64_t lda, const float* W, const float* bias, float* C,
+                   int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t st);
+int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A, int64_t lda, float* dW, int64_t M,
+                     int N, int K, int accumulate, float* part, cudaStream_t st);
+int wgg_linear_dgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* W, float* dA, int64_t lda, int64_t M,
+                     int N, int K, int accumulate, cudaStream_t st);
+
+// ----------------------------------------------------------------------------------------------
+// discriminator feature table (disc.cu) used by the feature-matching loss (loss.cu)
+// ----------------------------------------------------------------------------------------------
+struct FeatTable {
+  int n = 0;
+  int64_t off[WGG_MAX_HIDDEN_LAYERS + 2];    // float offset of the [B, width] block in the stash
+  int64_t count[WGG_MAX_HIDDEN_LAYERS + 2];  // B * width
+  int width[WGG_MAX_HIDDEN_LAYERS + 2];
+};
+int disc_feature_table(const wgg_model_cfg* cfg, int64_t B, FeatTable* ft);

@@ -1,0 +1,517 @@
+// Generator = word-prototype-conditioned 4-layer BiLSTM + tanh(Linear) head, forward and backward.
+// Replaces Generator.forward (src/gan/models.py:125-165: slice/repeat/cat :147-157, nn.LSTM :160,
+// tanh(Linear) :163) and its autograd.  LSTM cell equations: nn.LSTM, gate order i,f,g,o, two biases,
+// h0 = c0 = 0; reverse direction scans t = T-1..0; layer l>=1 input = concat(h_fwd, h_bwd).
+//
+// Data layout in HBM (ours, time-major so that one timestep of a sample tile is one contiguous block):
+//   x0    [T][B][I0]        layer-0 input  (prototype[:, :, :pd] ++ z)
+//   hseq  [T][B][2H]        per layer output (fwd dir in [0,H), reverse dir in [H,2H))
+//   gates [2][T][B][4H]     per layer: input projection + biases, overwritten in place by the
+//                           post-activation gates (forward) and then by d(pre-activation) (backward)
+//   cseq  [2][T][B][H]      per layer cell state
+//
+// Structure: the time-parallel part of every layer (x_t W_ih^T for all t, both directions) is one batched
+// GEMM; only h_{t-1} W_hh^T runs inside the persistent recurrent kernel, which keeps W_hh resident in
+// shared memory for all T steps and the cell state in registers (one lane = one sample, one warp = H/8
+// hidden units x 4 gates, so the gate epilogue needs no cross-thread traffic).
+#include "common.cuh"
+
+namespace {
+
+struct GenLayout {
+  int T, H, L, Z, pd, I0, C;
+  int64_t layer_off[WGG_MAX_HIDDEN_LAYERS + 1];  // start of layer l's block in the flat params
+  int64_t dir_stride[WGG_MAX_HIDDEN_LAYERS];     // floats between direction 0 and 1 of layer l
+  int64_t off_whh[WGG_MAX_HIDDEN_LAYERS], off_bih[WGG_MAX_HIDDEN_LAYERS], off_bhh[WGG_MAX_HIDDEN_LAYERS];
+  int64_t off_wo, off_bo, total;
+  int in_dim(int l) const { return l == 0 ? I0 : 2 * H; }
+};
+
+int gen_layout(const wgg_model_cfg* c, GenLayout* g) {
+  if (!c || c->gen_num_layers < 1 || c->gen_num_layers > WGG_MAX_HIDDEN_LAYERS) return WGG_EINVAL;
+  g->T = c->seq_length; g->H = c->gen_hidden_dim; g->L = c->gen_num_layers; g->Z = c->latent_dim;
+  g->C = c->input_dim;
+  g->pd = c->prototype_has_time ? c->input_dim : 2;
+  g->I0 = g->pd + g->Z;
+  int64_t off = 0;
+  for (int l = 0; l < g->L; ++l) {
+    const int64_t I = g->in_dim(l), H4 = 4 * g->H;
+    g->layer_off[l] = off;
+    g->off_whh[l] = H4 * I;
+    g->off_bih[l] = g->off_whh[l] + H4 * g->H;
+    g->off_bhh[l] = g->off_bih[l] + H4;
+    g->dir_stride[l] = g->off_bhh[l] + H4;
+    off += 2 * g->dir_stride[l];
+  }
+  g->layer_off[g->L] = off;
+  g->off_wo = off;
+  off += (int64_t)g->C * 2 * g->H;
+  g->off_bo = off;
+  off += g->C;
+  g->total = off;
+  return WGG_OK;
+}
+
+// x0[t][b][j] = j < pd ? proto[b][t][j] : z[b][j-pd]              (models.py:147-157)
+__global__ void build_x0_kernel(const float* __restrict__ proto, const float* __restrict__ z, float* __restrict__ x0,
+                                int T, int64_t B, int C, int pd, int Z) {
+  const int I0 = pd + Z;
+  const int64_t n = (int64_t)T * B * I0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % I0);
+    const int64_t tb = i / I0;
+    const int64_t b = tb % B;
+    const int t = (int)(tb / B);
+    x0[i] = j < pd ? __ldg(proto + (b * T + t) * C + j) : __ldg(z + b * Z + (j - pd));
+  }
+}
+
+// dpre[t][b][c] = dy[b][t][c] * (1 - y[b][t][c]^2)                (backward of tanh, models.py:163)
+__global__ void head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dpre,
+                                int T, int64_t B, int C) {
+  const int64_t n = (int64_t)T * B * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t tb = i / C;
+    const int64_t b = tb % B;
+    const int t = (int)(tb / B);
+    const int64_t src = (b * T + t) * C + c;
+    const float yy = __ldg(y + src);
+    dpre[i] = __ldg(dy + src) * (1.f - yy * yy);
+  }
+}
+
+// dz[b][j] = sum_t dx0[t][b][pd+j]                                  (backward of repeat+cat)
+__global__ void dz_kernel(const float* __restrict__ dx0, float* __restrict__ dz, int T, int64_t B, int I0, int pd,
+                          int Z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Z) return;
+  const int64_t b = i / Z;
+  const int j = (int)(i % Z);
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __ldg(dx0 + ((int64_t)t * B + b) * I0 + pd + j);
+  dz[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent recurrent forward: grid (ceil(B/32), 2 directions), 256 threads.
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) lstm_rec_fwd_kernel(float* __restrict__ gates, const float* __restrict__ lp,
+                                                           int64_t dir_stride, int64_t off_whh,
+                                                           float* __restrict__ hseq, float* __restrict__ cseq,
+                                                           int T, int64_t B, int store) {
+  constexpr int UPT = H / 8;
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;              // [H(k)][H(u)][4(g)]
+  float* hs = smem + H * H * 4;  // [2][H][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dir = blockIdx.y;
+  const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  const bool valid = b < B;
+  const float* __restrict__ whh = lp + dir * dir_stride + off_whh;
+  for (int idx = tid; idx < 4 * H * H; idx += 256) {
+    const int row = idx / H, k = idx % H;
+    const int g = row / H, u = row % H;
+    Ws[(k * H + u) * 4 + g] = __ldg(whh + idx);
+  }
+  for (int idx = tid; idx < 2 * H * 32; idx += 256) hs[idx] = 0.f;
+  __syncthreads();
+
+  const int u0 = warp * UPT;
+  float c[UPT];
+#pragma unroll
+  for (int uu = 0; uu < UPT; ++uu) c[uu] = 0.f;
+  const int64_t TB = (int64_t)T * B;
+  float* gbase = gates + (int64_t)dir * TB * 4 * H;
+  float* cbase = cseq ? cseq + (int64_t)dir * TB * H : nullptr;
+
+  float nxt[UPT][4];
+  {
+    const int t0 = dir ? T - 1 : 0;
+    const float* gp = gbase + ((int64_t)t0 * B + b) * 4 * H;
+#pragma unroll
+    for (int uu = 0; uu < UPT; ++uu)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) nxt[uu][g] = valid ? gp[g * H + u0 + uu] : 0.f;
+  }
+  for (int step = 0; step < T; ++step) {
+    const int t = dir ? T - 1 - step : step;
+    float acc[UPT][4];
+#pragma unroll
+    for (int uu = 0; uu < UPT; ++uu)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[uu][g] = nxt[uu][g];
+    if (step + 1 < T) {  // prefetch the next step's input projection while this step computes
+      const int tn = dir ? t - 1 : t + 1;
+      const float* gp = gbase + ((int64_t)tn * B + b) * 4 * H;
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) nxt[uu][g] = valid ? gp[g * H + u0 + uu] : 0.f;
+    }
+    const float* hcur = hs + (step & 1) * H * 32;
+    float* hnext = hs + ((step + 1) & 1) * H * 32;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+      const float hk = hcur[k * 32 + lane];
+      const float4* w4 = reinterpret_cast<const float4*>(Ws + (k * H + u0) * 4);
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu) {
+        const float4 w = w4[uu];
+        acc[uu][0] = fmaf(hk, w.x, acc[uu][0]);
+        acc[uu][1] = fmaf(hk, w.y, acc[uu][1]);
+        acc[uu][2] = fmaf(hk, w.z, acc[uu][2]);
+        acc[uu][3] = fmaf(hk, w.w, acc[uu][3]);
+      }
+    }
+    float* gp = gbase + ((int64_t)t * B + b) * 4 * H;
+    float* hp = hseq + ((int64_t)t * B + b) * 2 * H + dir * H;
+#pragma unroll
+    for (int uu = 0; uu < UPT; ++uu) {
+      const float ig = sigmoid_f(acc[uu][0]);
+      const float fg = sigmoid_f(acc[uu][1]);
+      const float gg = tanhf(acc[uu][2]);
+      const float og = sigmoid_f(acc[uu][3]);
+      c[uu] = fg * c[uu] + ig * gg;
+      const float h = og * tanhf(c[uu]);
+      hnext[(u0 + uu) * 32 + lane] = h;
+      if (valid) {
+        hp[u0 + uu] = h;
+        if (store) {
+          gp[0 * H + u0 + uu] = ig;
+          gp[1 * H + u0 + uu] = fg;
+          gp[2 * H + u0 + uu] = gg;
+          gp[3 * H + u0 + uu] = og;
+          cbase[((int64_t)t * B + b) * H + u0 + uu] = c[uu];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent recurrent backward (BPTT): same decomposition; writes d(pre-activation) over `gates`.
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) lstm_rec_bwd_kernel(float* __restrict__ gates, const float* __restrict__ cseq,
+                                                           const float* __restrict__ lp, int64_t dir_stride,
+                                                           int64_t off_whh, const float* __restrict__ dh_out, int T,
+                                                           int64_t B) {
+  constexpr int UPT = H / 8;
+  extern __shared__ __align__(16) float smem[];
+  float* Wb = smem;                   // [4H][H]
+  float* das = Wb + 4 * H * H;        // [4H][32]
+  float* dhs = das + 4 * H * 32;      // [H][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dir = blockIdx.y;
+  const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  const bool valid = b < B;
+  const float* __restrict__ whh = lp + dir * dir_stride + off_whh;
+  for (int idx = tid; idx < 4 * H * H; idx += 256) Wb[idx] = __ldg(whh + idx);
+  for (int idx = tid; idx < H * 32; idx += 256) dhs[idx] = 0.f;
+  __syncthreads();
+  const int u0 = warp * UPT;
+  const int64_t TB = (int64_t)T * B;
+  float* gbase = gates + (int64_t)dir * TB * 4 * H;
+  const float* cbase = cseq + (int64_t)dir * TB * H;
+  float dc[UPT];
+#pragma unroll
+  for (int uu = 0; uu < UPT; ++uu) dc[uu] = 0.f;
+
+  for (int step = T - 1; step >= 0; --step) {
+    const int t = dir ? T - 1 - step : step;
+    const int tp = dir ? t + 1 : t - 1;  // the timestep processed before t in the forward scan
+    float* gp = gbase + ((int64_t)t * B + b) * 4 * H;
+    const float* cp = cbase + ((int64_t)t * B + b) * H;
+    const float* cpp = cbase + ((int64_t)tp * B + b) * H;
+    const float* dhp = dh_out + ((int64_t)t * B + b) * 2 * H + dir * H;
+#pragma unroll
+    for (int uu = 0; uu < UPT; ++uu) {
+      const int u = u0 + uu;
+      float da_i = 0.f, da_f = 0.f, da_g = 0.f, da_o = 0.f;
+      if (valid) {
+        const float ig = gp[0 * H + u], fg = gp[1 * H + u], gg = gp[2 * H + u], og = gp[3 * H + u];
+        const float cc = cp[u];
+        const float cprev = step > 0 ? cpp[u] : 0.f;
+        const float tc = tanhf(cc);
+        const float dh = dhp[u] + dhs[u * 32 + lane];
+        const float d_o = dh * tc;
+        const float dct = dc[uu] + dh * og * (1.f - tc * tc);
+        da_i = dct * gg * ig * (1.f - ig);
+        da_f = dct * cprev * fg * (1.f - fg);
+        da_g = dct * ig * (1.f - gg * gg);
+        da_o = d_o * og * (1.f - og);
+        dc[uu] = dct * fg;
+        gp[0 * H + u] = da_i;
+        gp[1 * H + u] = da_f;
+        gp[2 * H + u] = da_g;
+        gp[3 * H + u] = da_o;
+      }
+      das[(0 * H + u) * 32 + lane] = da_i;
+      das[(1 * H + u) * 32 + lane] = da_f;
+      das[(2 * H + u) * 32 + lane] = da_g;
+      das[(3 * H + u) * 32 + lane] = da_o;
+    }
+    __syncthreads();
+    if (step > 0) {
+      float acc[UPT];
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu) acc[uu] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < 4 * H; ++j) {
+        const float d = das[j * 32 + lane];
+        const float* w = Wb + j * H + u0;
+#pragma unroll
+        for (int uu = 0; uu < UPT; ++uu) acc[uu] = fmaf(d, w[uu], acc[uu]);
+      }
+#pragma unroll
+      for (int uu = 0; uu < UPT; ++uu) dhs[(u0 + uu) * 32 + lane] = acc[uu];
+    }
+    __syncthreads();
+  }
+}
+
+template <int H>
+int rec_fwd_launch_t(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                     float* cseq, int T, int64_t B, int store, cudaStream_t st) {
+  const size_t smem = (size_t)(H * H * 4 + 2 * H * 32) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(lstm_rec_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid((unsigned)cdiv64(B, 32), 2);
+  // algorithmic work: 2 dirs x T steps x B x (8 H^2 MAC-flops + gate math); bytes: xproj in, gates/c/h out
+  ProfScope prof(ctx, "lstm_rec_fwd_kernel", st, 2.0 * T * (double)B * 8.0 * H * H,
+                 2.0 * T * (double)B * 4.0 * (4 * H + (store ? 5 * H : 0) + H));
+  lstm_rec_fwd_kernel<H><<<grid, 256, smem, st>>>(gates, lp, dir_stride, off_whh, hseq, cseq, T, B, store);
+  WGG_CHECK_LAUNCH(ctx, "lstm_rec_fwd_kernel");
+  return WGG_OK;
+}
+
+template <int H>
+int rec_bwd_launch_t(wgg_ctx* ctx, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
+                     int64_t off_whh, const float* dh_out, int T, int64_t B, cudaStream_t st) {
+  const size_t smem = (size_t)(4 * H * H + 4 * H * 32 + H * 32) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(lstm_rec_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid((unsigned)cdiv64(B, 32), 2);
+  ProfScope prof(ctx, "lstm_rec_bwd_kernel", st, 2.0 * T * (double)B * 8.0 * H * H,
+                 2.0 * T * (double)B * 4.0 * (4 * H + 4 * H + 2 * H + H));
+  lstm_rec_bwd_kernel<H><<<grid, 256, smem, st>>>(gates, cseq, lp, dir_stride, off_whh, dh_out, T, B);
+  WGG_CHECK_LAUNCH(ctx, "lstm_rec_bwd_kernel");
+  return WGG_OK;
+}
+
+#define WGG_DISPATCH_H(H, CALL)                                                                         \
+  switch (H) {                                                                                          \
+    case 8: { constexpr int HH = 8; return CALL; }                                                      \
+    case 16: { constexpr int HH = 16; return CALL; }                                                    \
+    case 32: { constexpr int HH = 32; return CALL; }                                                    \
+    case 48: { constexpr int HH = 48; return CALL; }                                                    \
+    case 64: { constexpr int HH = 64; return CALL; }                                                    \
+    default:                                                                                            \
+      return wgg_fail(ctx, WGG_EUNSUPPORTED, "gen_hidden_dim=%s%lld has no compiled recurrent kernel (8,16,32,48,64)", \
+                      "", (long long)(H));                                                              \
+  }
+
+int rec_fwd_launch(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh,
+                   float* hseq, float* cseq, int T, int64_t B, int store, cudaStream_t st) {
+  WGG_DISPATCH_H(H, (rec_fwd_launch_t<HH>(ctx, gates, lp, dir_stride, off_whh, hseq, cseq, T, B, store, st)));
+}
+
+int rec_bwd_launch(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
+                   int64_t off_whh, const float* dh_out, int T, int64_t B, cudaStream_t st) {
+  WGG_DISPATCH_H(H, (rec_bwd_launch_t<HH>(ctx, gates, cseq, lp, dir_stride, off_whh, dh_out, T, B, st)));
+}
+
+inline int ew_grid(int64_t n) {
+  int64_t g = cdiv64(n, 256);
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+struct StashView {
+  float* x0;
+  float* hseq[WGG_MAX_HIDDEN_LAYERS];
+  float* gates[WGG_MAX_HIDDEN_LAYERS];
+  float* cseq[WGG_MAX_HIDDEN_LAYERS];
+};
+
+int64_t stash_floats(const GenLayout& g, int64_t B) {
+  const int64_t TB = (int64_t)g.T * B;
+  return TB * (g.I0 + (int64_t)g.L * 12 * g.H);
+}
+
+void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
+  const int64_t TB = (int64_t)g.T * B;
+  v->x0 = s;
+  s += TB * g.I0;
+  for (int l = 0; l < g.L; ++l) { v->hseq[l] = s; s += TB * 2 * g.H; }
+  for (int l = 0; l < g.L; ++l) { v->gates[l] = s; s += TB * 8 * g.H; }
+  for (int l = 0; l < g.L; ++l) { v->cseq[l] = s; s += TB * 2 * g.H; }
+}
+
+}  // namespace
+
+extern "C" int64_t wgg_generator_param_floats(const wgg_model_cfg* cfg) {
+  GenLayout g;
+  if (gen_layout(cfg, &g) != WGG_OK) return -1;
+  return g.total;
+}
+
+extern "C" int64_t wgg_generator_stash_floats(const wgg_model_cfg* cfg, int64_t B) {
+  GenLayout g;
+  if (gen_layout(cfg, &g) != WGG_OK) return -1;
+  return stash_floats(g, B);
+}
+
+extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int64_t B, int backward) {
+  GenLayout g;
+  if (gen_layout(cfg, &g) != WGG_OK) return -1;
+  const int64_t TB = (int64_t)g.T * B;
+  if (!backward) return TB * (g.I0 + 4 * g.H + 8 * g.H);  // x0 + two hseq + gates (no-grad forward)
+  const int64_t maxI = g.I0 > 2 * g.H ? g.I0 : 2 * g.H;
+  return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2);
+}
+
+extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
+                                     const float* z, int64_t B, float* out, float* stash, float* ws,
+                                     int64_t ws_floats, void* stream) {
+  GenLayout g;
+  if (!ctx) return WGG_EINVAL;
+  if (gen_layout(cfg, &g) != WGG_OK) return wgg_fail(ctx, WGG_EINVAL, "generator: bad config%s");
+  if (B <= 0) return WGG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t TB = (int64_t)g.T * B;
+  StashView sv;
+  float* hbuf[2] = {nullptr, nullptr};
+  float* gates_ws = nullptr;
+  if (stash) {
+    stash_view(g, B, stash, &sv);
+  } else {
+    if (!ws || ws_floats < wgg_generator_workspace_floats(cfg, B, 0))
+      return wgg_fail(ctx, WGG_EWORKSPACE, "generator_forward: workspace too small%s");
+    sv.x0 = ws;
+    hbuf[0] = ws + TB * g.I0;
+    hbuf[1] = hbuf[0] + TB * 2 * g.H;
+    gates_ws = hbuf[1] + TB * 2 * g.H;
+  }
+  build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sv.x0, g.T, B, g.C, g.pd, g.Z);
+  WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
+  const float* in = sv.x0;
+  float* hout = nullptr;
+  for (int l = 0; l < g.L; ++l) {
+    const int I = g.in_dim(l);
+    const float* lp = params + g.layer_off[l];
+    float* gates = stash ? sv.gates[l] : gates_ws;
+    float* cseq = stash ? sv.cseq[l] : nullptr;
+    hout = stash ? sv.hseq[l] : hbuf[l & 1];
+    GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
+    p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
+    p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
+    p.C = gates; p.scm = 4 * g.H; p.scn = 1;
+    p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
+    p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
+    WGG_TRY(gemm_launch(ctx, p, st));
+    WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, g.T, B, stash ? 1 : 0, st));
+    in = hout;
+  }
+  GemmP p;  // out[b][t][:] = tanh(h[t][b][:] * Wo^T + bo), batched over t to transpose (t,b)->(b,t)
+  p.A = hout; p.M = B; p.K = 2 * g.H; p.sam = 2 * g.H; p.sak = 1;
+  p.B = params + g.off_wo; p.N = g.C; p.sbk = 1; p.sbn = 2 * g.H;
+  p.C = out; p.scm = (int64_t)g.T * g.C; p.scn = 1;
+  p.nbatch = g.T; p.bsA = B * 2 * g.H; p.bsB = 0; p.bsC = g.C; p.bsBias = 0;
+  p.bias = params + g.off_bo; p.act = ACT_TANH;
+  return gemm_launch(ctx, p, st);
+}
+
+extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, int64_t B,
+                                      float* stash, const float* out, const float* dout, float* dparams, float* dz,
+                                      float* ws, int64_t ws_floats, void* stream) {
+  GenLayout g;
+  if (!ctx) return WGG_EINVAL;
+  if (gen_layout(cfg, &g) != WGG_OK) return wgg_fail(ctx, WGG_EINVAL, "generator: bad config%s");
+  if (B <= 0) return WGG_OK;
+  if (!stash || !ws || ws_floats < wgg_generator_workspace_floats(cfg, B, 1))
+    return wgg_fail(ctx, WGG_EWORKSPACE, "generator_backward: stash/workspace missing or too small%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t TB = (int64_t)g.T * B;
+  const int H = g.H, H4 = 4 * g.H;
+  const int64_t maxI = g.I0 > 2 * H ? g.I0 : 2 * H;
+  StashView sv;
+  stash_view(g, B, stash, &sv);
+  float* dpre = ws;
+  float* dh = dpre + TB * g.C;
+  float* dx = dh + TB * maxI;
+  float* part = dx + TB * maxI;
+  float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
+
+  head_bwd_kernel<<<ew_grid(TB * g.C), 256, 0, st>>>(out, dout, dpre, g.T, B, g.C);
+  WGG_CHECK_LAUNCH(ctx, "head_bwd_kernel");
+  const float* hL = sv.hseq[g.L - 1];
+  {
+    GemmP p;  // dWo (C x 2H) += dpre^T * hL
+    p.A = dpre; p.M = g.C; p.K = TB; p.sam = 1; p.sak = g.C;
+    p.B = hL; p.N = 2 * H; p.sbk = 2 * H; p.sbn = 1;
+    p.C = dparams + g.off_wo; p.scm = 2 * H; p.scn = 1; p.accumulate = 1;
+    p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 1); p.partial = part;
+    WGG_TRY(gemm_launch(ctx, p, st));
+    WGG_TRY(colsum_launch(ctx, dpre, TB, g.C, g.C, 1, 0, dparams + g.off_bo, nullptr, 0, 1, csws, st));
+    GemmP q;  // dh (TB x 2H) = dpre * Wo
+    q.A = dpre; q.M = TB; q.K = g.C; q.sam = g.C; q.sak = 1;
+    q.B = params + g.off_wo; q.N = 2 * H; q.sbk = 2 * H; q.sbn = 1;
+    q.C = dh; q.scm = 2 * H; q.scn = 1;
+    WGG_TRY(gemm_launch(ctx, q, st));
+  }
+  for (int l = g.L - 1; l >= 0; --l) {
+    const int I = g.in_dim(l);
+    const float* lp = params + g.layer_off[l];
+    float* dlp = dparams + g.layer_off[l];
+    float* da = sv.gates[l];
+    const float* in = l == 0 ? sv.x0 : sv.hseq[l - 1];
+    WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, g.T, B, st));
+    {
+      GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
+      p.A = da; p.M = H4; p.K = TB; p.sam = 1; p.sak = H4;
+      p.B = in; p.N = I; p.sbk = I; p.sbn = 1;
+      p.C = dlp; p.scm = I; p.scn = 1; p.accumulate = 1;
+      p.nbatch = 2; p.bsA = TB * H4; p.bsB = 0; p.bsC = g.dir_stride[l];
+      p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 2); p.partial = part;
+      WGG_TRY(gemm_launch(ctx, p, st));
+    }
+    if (g.T > 1) {
+      GemmP p;  // dW_hh[d] (4H x H) += da[d][t]^T * h[d][t_prev]; time shift = pointer offset
+      p.A = da + B * H4; p.M = H4; p.K = (int64_t)(g.T - 1) * B; p.sam = 1; p.sak = H4;
+      p.B = sv.hseq[l]; p.N = H; p.sbk = 2 * H; p.sbn = 1;
+      p.C = dlp + g.off_whh[l]; p.scm = H; p.scn = 1; p.accumulate = 1;
+      p.nbatch = 2; p.bsA = TB * H4 - B * H4; p.bsB = B * 2 * H + H; p.bsC = g.dir_stride[l];
+      p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 2); p.partial = part;
+      WGG_TRY(gemm_launch(ctx, p, st));
+    }
+    // db_ih[d] = db_hh[d] += column sums of da[d]
+    WGG_TRY(colsum_launch(ctx, da, TB, H4, H4, 2, TB * H4, dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1,
+                          csws, st));
+    if (l > 0 || dz) {
+      for (int d = 0; d < 2; ++d) {
+        GemmP p;  // dx (TB x I) (+)= da[d] * W_ih[d]
+        p.A = da + (int64_t)d * TB * H4; p.M = TB; p.K = H4; p.sam = H4; p.sak = 1;
+        p.B = lp + d * g.dir_stride[l]; p.N = I; p.sbk = I; p.sbn = 1;
+        p.C = dx; p.scm = I; p.scn = 1; p.accumulate = d;
+        WGG_TRY(gemm_launch(ctx, p, st));
+      }
+      float* t = dh; dh = dx; dx = t;  // dh now holds d(input of layer l) = d(output of layer l-1)
+    }
+  }
+  if (dz) {
+    dz_kernel<<<(unsigned)cdiv64(B * g.Z, 256), 256, 0, st>>>(dh, dz, g.T, B, g.I0, g.pd, g.Z);
+    WGG_CHECK_LAUNCH(ctx, "dz_kernel");
+  }
+  return WGG_OK;
+}

@@ -1,0 +1,115 @@
+"""WordGestureGANTrainer drop-in: owns the four networks, the loss objects and the four optimisers.
+
+Interface contract = src/gan/trainer.py:24-230 of the reference: same constructor, attribute names
+(.generator .encoder .discriminator_1 .discriminator_2 .optimizer_G/E/D1/D2 .current_epoch ...), the two
+generator-side cycle builders returning ``(fake_gesture, total_loss, loss_dict)`` and the checkpoint dict
+format of get_modal_checkpoint_dict / load_modal_checkpoint.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .configs import DEFAULT_MODEL_CONFIG, DEFAULT_TRAINING_CONFIG, ModelConfig, TrainingConfig
+from .gan_losses import (FeatureMatchingLoss, KLDivergenceLoss, LatentEncodingLoss, ReconstructionLoss,
+                         WassersteinLoss, feature_matching_from_stash)
+from .gan_modules import Discriminator, Generator, TemporalDiscriminator, VariationalEncoder
+from .optim import FusedClipAdam
+
+_MODULES = (("generator", "optimizer_G"), ("discriminator_1", "optimizer_D1"),
+            ("discriminator_2", "optimizer_D2"), ("encoder", "optimizer_E"))
+
+
+class WordGestureGANTrainer:
+    def __init__(self, model_config: ModelConfig = DEFAULT_MODEL_CONFIG,
+                 training_config: TrainingConfig = DEFAULT_TRAINING_CONFIG,
+                 device: str = "cuda" if torch.cuda.is_available() else "cpu"):
+        self.model_config = model_config
+        self.training_config = training_config
+        self.device = torch.device(device)
+        # construction order fixes the RNG stream of the initial weights: G, E, D1, D2 (trainer.py:44-51)
+        self.generator = Generator(model_config).to(self.device)
+        self.encoder = VariationalEncoder(model_config).to(self.device)
+        disc_cls = TemporalDiscriminator if model_config.use_temporal_disc else Discriminator
+        self.discriminator_1 = disc_cls(model_config).to(self.device)
+        self.discriminator_2 = disc_cls(model_config).to(self.device)
+
+        self.feature_matching_loss = FeatureMatchingLoss()
+        self.reconstruction_loss = ReconstructionLoss()
+        self.latent_encoding_loss = LatentEncodingLoss()
+        self.kl_divergence_loss = KLDivergenceLoss()
+
+        lr = training_config.learning_rate
+        self.optimizer_G = FusedClipAdam(self.generator, lr=lr, betas=(0.5, 0.999))
+        self.optimizer_E = FusedClipAdam(self.encoder, lr=lr, betas=(0.5, 0.999))
+        self.optimizer_D1 = FusedClipAdam(self.discriminator_1, lr=lr, betas=(0.5, 0.999))
+        self.optimizer_D2 = FusedClipAdam(self.discriminator_2, lr=lr, betas=(0.5, 0.999))
+        self.current_epoch = 0
+
+    # ---- generator-side cycles ------------------------------------------------------------------
+    def _adversarial_terms(self, disc, fake, real):
+        """-mean D(fake) and the feature-matching term; three discriminator calls in the reference's order
+        (score(fake), features(fake), features(real)) because each advances the spectral-norm power iteration
+        (trainer.py:111-113 / :167-169)."""
+        fake_scores = disc(fake)
+        fake_stash = disc.features_stash(fake)
+        real_stash = disc.features_stash(real)
+        wgan = WassersteinLoss.generator_loss(fake_scores)
+        feat = feature_matching_from_stash(real_stash, fake_stash, self.model_config, fake.shape[0])
+        return wgan, feat
+
+    def cycle1_tensors(self, prototype, real_gesture, z: Optional[torch.Tensor] = None,
+                       eps_recover: Optional[torch.Tensor] = None):
+        """Cycle 1 (z -> X' -> z').  Returns (fake, total, dict of 0-dim device tensors) without host syncs.
+        ``z`` / ``eps_recover`` inject the two normal draws (default: torch.randn, in the reference's order)."""
+        tc = self.training_config
+        B = prototype.size(0)
+        if z is None:
+            z = torch.randn(B, self.model_config.latent_dim, device=self.device)
+        fake = self.generator(prototype, z)
+        wgan, feat = self._adversarial_terms(self.discriminator_1, fake, real_gesture)
+        with torch.no_grad():  # latent recovery carries no gradient in the reference either (trainer.py:116-119)
+            z_rec, _, _ = self.encoder(fake, eps_recover)
+        lat = self.latent_encoding_loss(z, z_rec)
+        total = wgan + tc.lambda_feat * feat + tc.lambda_lat * lat
+        return fake, total, {"cycle1_wgan": wgan, "cycle1_feat": feat, "cycle1_lat": lat, "cycle1_total": total}
+
+    def cycle2_tensors(self, prototype, real_gesture, eps: Optional[torch.Tensor] = None):
+        """Cycle 2 (X -> z -> X')."""
+        tc = self.training_config
+        z_enc, mu, log_var = self.encoder(real_gesture, eps)
+        fake = self.generator(prototype, z_enc)
+        wgan, feat = self._adversarial_terms(self.discriminator_2, fake, real_gesture)
+        rec = self.reconstruction_loss(real_gesture, fake)
+        kld = self.kl_divergence_loss(mu, log_var)
+        total = wgan + tc.lambda_feat * feat + tc.lambda_rec * rec + tc.lambda_kld * kld
+        return fake, total, {"cycle2_wgan": wgan, "cycle2_feat": feat, "cycle2_rec": rec, "cycle2_kld": kld,
+                             "cycle2_total": total}
+
+    def train_generator_step_cycle1(self, prototype: torch.Tensor, real_gesture: torch.Tensor
+                                    ) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, float]]:
+        fake, total, d = self.cycle1_tensors(prototype, real_gesture)
+        return fake, total, {k: v.item() for k, v in d.items()}
+
+    def train_generator_step_cycle2(self, prototype: torch.Tensor, real_gesture: torch.Tensor
+                                    ) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, float]]:
+        fake, total, d = self.cycle2_tensors(prototype, real_gesture)
+        return fake, total, {k: v.item() for k, v in d.items()}
+
+    # ---- checkpoints ------------------------------------------------------------------------------
+    def get_modal_checkpoint_dict(self) -> dict:
+        ckpt = {"epoch": self.current_epoch}
+        for mod, opt in _MODULES:
+            ckpt[mod] = getattr(self, mod).state_dict()
+        for mod, opt in _MODULES:
+            ckpt[opt] = getattr(self, opt).state_dict()
+        return ckpt
+
+    def load_modal_checkpoint(self, checkpoint: dict):
+        self.current_epoch = checkpoint["epoch"] + 1
+        for mod, opt in _MODULES:
+            getattr(self, mod).load_state_dict(checkpoint[mod])
+        for mod, opt in _MODULES:
+            getattr(self, opt).load_state_dict(checkpoint[opt])
+        print(f"Loaded modal checkpoint from epoch {checkpoint['epoch'] + 1}")

@@ -1,0 +1,79 @@
+"""Data-parallel plumbing: one process per GPU, shard the gesture minibatch, all-reduce flat gradients.
+
+The reference is single-GPU; this is the new data-parallel wrapper the north star asks for
+(SURVEY.md section 8e).  Every loss of the step is a batch mean and no layer mixes samples, so averaging the
+per-rank flat gradients of equal shards reproduces the global-batch gradient; spectral-norm power iterations
+depend on weights only, so replicas stay identical with no further communication.  The collective is NCCL
+(over NVLink 5 / NVSwitch) on the flat gradient buffer, issued BEFORE clipping (the clip is on the global
+gradient).  Noise is drawn for the GLOBAL batch with the shared seed on every rank and sliced, so an N-rank
+run consumes the same random numbers as a 1-rank run on the same global batch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, equal shards: rank r owns [r*n/W, (r+1)*n/W).  n must divide evenly (batch means!)."""
+    if n % world_size != 0:
+        raise ValueError(f"global batch {n} is not divisible by world size {world_size}: unequal shards would "
+                         "bias the averaged gradient")
+    per = n // world_size
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(t: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    lo, hi = shard_bounds(t.shape[0], rank, world_size)
+    return t[lo:hi]
+
+
+def draw_global_noise(n_draws: int, global_batch: int, latent_dim: int, device, generator=None) -> List[torch.Tensor]:
+    """The step's (B, Z) normal draws for the GLOBAL batch, as individual torch.randn calls in the
+    reference's consumption order; identical on every rank when the seeds agree."""
+    return [torch.randn(global_batch, latent_dim, device=device, generator=generator) for _ in range(n_draws)]
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None, world_size: Optional[int] = None) -> torch.Tensor:
+    """In-place mean all-reduce of a flat gradient bucket."""
+    if world_size is None:
+        world_size = dist.get_world_size(group)
+    if world_size == 1:
+        return flat
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo (CPU tests) has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world_size)
+    return flat
+
+
+class DataParallelGAN:
+    """Attaches a process group to a trainer's four fused optimisers: each ``step`` first mean-all-reduces the
+    module's flat gradient bucket.  Also broadcasts rank 0's state so replicas start identical."""
+
+    def __init__(self, trainer, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.trainer = trainer
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        for opt in (trainer.optimizer_G, trainer.optimizer_E, trainer.optimizer_D1, trainer.optimizer_D2):
+            opt.process_group = group if group is not None else dist.group.WORLD
+            opt.world_size = self.world_size
+        self.sync_state()
+
+    def sync_state(self):
+        for mod in (self.trainer.generator, self.trainer.encoder, self.trainer.discriminator_1,
+                    self.trainer.discriminator_2):
+            dist.broadcast(mod.flat_params(), src=0, group=self.group)
+            fb = mod.flat_buffers()
+            if fb is not None:
+                dist.broadcast(fb, src=0, group=self.group)
+
+    def shard(self, t: torch.Tensor) -> torch.Tensor:
+        return shard_batch(t, self.rank, self.world_size)

@@ -1,0 +1,108 @@
+"""The training step: ``train_epoch_with_grad_clip`` and the seed / log helpers.
+
+Interface contract = src/shared/utils.py:12-148 of the reference.  Per DataLoader batch:
+n_critic x { D1 step on G(proto, randn) ; D2 step on G(proto, E(real)) } then one joint G/E step on
+cycle-1 + cycle-2 losses; every optimiser step is clip_grad_norm_(max_norm) + Adam, here one fused kernel.
+Loss scalars are accumulated on the device and read back once per epoch (the reference syncs 11 times per
+batch; its return contract is only the epoch means, utils.py:138-148).
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .gan_losses import WassersteinLoss
+
+
+def seed_everything(seed: int) -> None:
+    """python, numpy, torch CPU and current-CUDA-device generators (utils.py:12-20)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+
+
+def log(msg: str) -> None:
+    print(msg, flush=True)
+
+
+def n_noise_draws(training_config) -> int:
+    return 2 * training_config.n_critic + 3
+
+
+def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, max_norm: float,
+                noise: Optional[List[torch.Tensor]] = None, on_step=None) -> Dict[str, torch.Tensor]:
+    """One batch of the step.  ``noise`` optionally injects the 2*n_critic+3 (B, Z) normal draws in consumption
+    order (z_rand, eps) x n_critic, z, eps_recover, eps; by default each is a torch.randn call made at the point
+    where the reference makes it, so the global RNG stream is consumed identically.
+    ``on_step(tag, optimizer)`` (optional) is called right before each of the 12 optimiser steps (tests use it
+    to read the un-clipped gradients).  Returns 0-dim device tensors for all 11 logged scalars."""
+    tc, mc = trainer.training_config, trainer.model_config
+    dev = real_gesture.device
+    B = real_gesture.size(0)
+    it = iter(noise) if noise is not None else None
+
+    def draw():
+        return next(it) if it is not None else torch.randn(B, mc.latent_dim, device=dev)
+
+    out: Dict[str, torch.Tensor] = {}
+    for critic_it in range(tc.n_critic):
+        for name, disc, opt in (("d1_loss", trainer.discriminator_1, trainer.optimizer_D1),
+                                ("d2_loss", trainer.discriminator_2, trainer.optimizer_D2)):
+            with torch.no_grad():
+                if name == "d1_loss":
+                    z = draw()
+                else:
+                    z, _, _ = trainer.encoder(real_gesture, draw())
+                fake = trainer.generator(prototype, z)
+            opt.zero_grad()
+            real_scores = disc(real_gesture)
+            fake_scores = disc(fake)
+            loss = WassersteinLoss.discriminator_loss(real_scores, fake_scores)
+            loss.backward()
+            if on_step is not None:
+                on_step(f"{name[:2].upper()}_grads_{critic_it}", opt)
+            opt.step(max_norm=max_norm)
+            out[name] = loss.detach()
+
+    trainer.optimizer_G.zero_grad()
+    trainer.optimizer_E.zero_grad()
+    _, loss1, d1 = trainer.cycle1_tensors(prototype, real_gesture, z=draw(), eps_recover=draw())
+    _, loss2, d2 = trainer.cycle2_tensors(prototype, real_gesture, eps=draw())
+    (loss1 + loss2).backward()
+    if on_step is not None:
+        on_step("G_grads", trainer.optimizer_G)
+        on_step("E_grads", trainer.optimizer_E)
+    trainer.optimizer_G.step(max_norm=max_norm)
+    trainer.optimizer_E.step(max_norm=max_norm)
+    for d in (d1, d2):
+        for k, v in d.items():
+            out[k] = v.detach()
+    return out
+
+
+def train_epoch_with_grad_clip(trainer, dataloader, max_norm, model_config, training_config, device, scaler=None):
+    """Drop-in for src/shared/utils.py:28.  ``scaler`` must be None: the reference hard-wires it to None
+    (train_gan.py:90-92) and the fp32 path is the only one implemented."""
+    if scaler is not None:
+        raise NotImplementedError("mixed precision is a dead branch in the reference (scaler is always None)")
+    for m in (trainer.generator, trainer.encoder, trainer.discriminator_1, trainer.discriminator_2):
+        m.train()
+    keys = ("d1_loss", "d2_loss", "cycle1_total", "cycle2_total")
+    sums = None
+    num_batches = 0
+    for batch in dataloader:
+        real = batch["gesture"].to(device, non_blocking=True)
+        proto = batch["prototype"].to(device, non_blocking=True)
+        out = train_batch(trainer, real, proto, max_norm)
+        vals = torch.stack([out[k] for k in keys])
+        sums = vals if sums is None else sums + vals
+        num_batches += 1
+    if num_batches == 0:
+        raise ZeroDivisionError("empty dataloader")
+    means = (sums / num_batches).tolist()  # the only host sync of the epoch
+    return dict(zip(keys, means))
