@@ -156,3 +156,28 @@ def test_optimizer_is_torch_optimizer_and_scheduler_compatible():
     opt.load_state_dict(ref_opt.state_dict())
     assert opt._step == 1
     assert torch.allclose(opt._m, torch.full_like(opt._m, 0.5))
+
+
+def test_ctypes_signatures_match_header_arity_and_types():
+    """Every ctypes signature has the header's parameter count and pointer/integer/float kinds."""
+    from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+    text = open(os.path.join(ROOT, "include", "wgg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"WGG_API\s+([\w\s\*]+?)\b(wgg_\w+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_lib.EXPORTED_SYMBOLS)
+    for ret, name, params in protos:
+        params = params.strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        res, args = _lib._SIG[name]
+        assert len(args) == len(plist), f"{name}: header has {len(plist)} parameters, ctypes table has {len(args)}"
+        for decl, a in zip(plist, args):
+            if "*" in decl:
+                assert a not in (c_int, c_int32, c_int64, c_float), (name, decl, a)
+            elif decl.startswith("int64_t"):
+                assert a is c_int64, (name, decl, a)
+            elif decl.startswith("float"):
+                assert a is c_float, (name, decl, a)
+            elif decl.startswith(("int32_t", "int ")):
+                assert a in (c_int, c_int32), (name, decl, a)
+            else:
+                raise AssertionError(f"{name}: unhandled parameter declaration {decl!r}")
