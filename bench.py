@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); fp32: FMA only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -171,6 +173,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    wgg.set_math_mode(args.math)
     mc, tc = wgg.ModelConfig(), wgg.TrainingConfig(batch_size=B)
     wgg.seed_everything(42)
     tr = wgg.WordGestureGANTrainer(mc, tc, dev)
@@ -285,7 +288,8 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex!r}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if args.math == "tf32" else "f32",
         "data": "synthetic",
         "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
                                "T=128), BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,

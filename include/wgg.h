@@ -78,6 +78,9 @@ WGG_API int64_t wgg_launch_count(wgg_ctx* ctx);
  * the launch count and the algorithmic FLOPs / bytes those launches accounted for.  (max 16384 launches) */
 WGG_API int wgg_profile_enable(wgg_ctx* ctx, const char* kernel_substr);
 WGG_API int wgg_profile_read(wgg_ctx* ctx, double* total_ms, int64_t* launches, double* flops, double* bytes);
+/* SYNCHRONISING debug query: reads (and clears) the device-side error word that the persistent tcgen05
+ * kernels set when one of their bounded mbarrier waits times out (code = which wait).  0 = healthy. */
+WGG_API int wgg_async_error(wgg_ctx* ctx, int* code);
 /* math mode: 0 = fp32 FMA everywhere (default), 1 = TF32 tensor-core contractions where available */
 WGG_API int wgg_set_math_mode(wgg_ctx* ctx, int mode);
 

@@ -3,6 +3,7 @@
 Python host layer over libwgg_sm100.so (C ABI in include/wgg.h).  Import as ``wgg_b200`` (the directory
 name contains a hyphen; the repo-root ``wgg_b200.py`` shim registers it).
 """
+from ._lib import get_math_mode, set_math_mode
 from .configs import DEFAULT_MODEL_CONFIG, DEFAULT_TRAINING_CONFIG, ModelConfig, TrainingConfig
 from .gan_losses import (FeatureMatchingLoss, KLDivergenceLoss, LatentEncodingLoss, ReconstructionLoss,
                          WassersteinLoss, feature_matching_from_stash)
@@ -16,5 +17,5 @@ __all__ = [
     "Generator", "VariationalEncoder", "Discriminator", "TemporalDiscriminator",
     "WassersteinLoss", "FeatureMatchingLoss", "ReconstructionLoss", "LatentEncodingLoss", "KLDivergenceLoss",
     "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam",
-    "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
+    "set_math_mode", "get_math_mode", "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
 ]

@@ -39,6 +39,7 @@ _SIG = {
     "wgg_last_error": (c_char_p, [_P]),
     "wgg_launch_count": (c_int64, [_P]),
     "wgg_set_math_mode": (c_int, [_P, c_int]),
+    "wgg_async_error": (c_int, [_P, POINTER(c_int)]),
     "wgg_profile_enable": (c_int, [_P, c_char_p]),
     "wgg_profile_read": (c_int, [_P, POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double),
                                  POINTER(ctypes.c_double)]),
@@ -117,6 +118,8 @@ def ctx(device: torch.device):
         if rc != 0:
             raise WggError(f"wgg_create(device={idx}) failed with code {rc} (needs an sm_100 GPU)")
         c = _ctx[idx] = out
+        if _math_mode:
+            check(lib().wgg_set_math_mode(c, _math_mode), c)
     return c
 
 
@@ -187,3 +190,31 @@ def profile_read(device):
     ms, n, fl, by = ctypes.c_double(), c_int64(), ctypes.c_double(), ctypes.c_double()
     check(lib().wgg_profile_read(c, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl), ctypes.byref(by)), c)
     return dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+
+
+_math_mode = 0
+
+
+def set_math_mode(mode, device=None) -> None:
+    """"fp32" / 0: every contraction in fp32 FMA (bit-for-bit the most faithful, used by the tight parity tests).
+    "tf32" / 1: LSTM and conv contractions on TF32 tensor cores with fp32 accumulation - the numerics of the
+    reference's own CUDA path (cuDNN allows TF32 by default); nn.Linear layers stay fp32."""
+    global _math_mode
+    m = {"fp32": 0, "tf32": 1}.get(mode, mode)
+    if m not in (0, 1):
+        raise ValueError(f"unknown math mode {mode!r}")
+    _math_mode = m
+    for idx, c in _ctx.items():
+        check(lib().wgg_set_math_mode(c, m), c)
+
+
+def get_math_mode() -> str:
+    return "tf32" if _math_mode else "fp32"
+
+
+def async_error(device) -> int:
+    """Synchronising debug query of the persistent kernels' pipeline-timeout word (0 = healthy)."""
+    c = ctx(device)
+    code = c_int(0)
+    check(lib().wgg_async_error(c, ctypes.byref(code)), c)
+    return code.value

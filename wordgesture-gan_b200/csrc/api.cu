@@ -19,6 +19,11 @@ extern "C" int wgg_create(wgg_ctx** out, int device) {
     delete ctx;
     return WGG_ECUDA;
   }
+  if (cudaMalloc(&ctx->async_err, sizeof(int)) != cudaSuccess || cudaMemset(ctx->async_err, 0, sizeof(int)) != cudaSuccess) {
+    cudaFree(ctx->red_scratch);
+    delete ctx;
+    return WGG_ECUDA;
+  }
   *out = ctx;
   return WGG_OK;
 }
@@ -26,6 +31,7 @@ extern "C" int wgg_create(wgg_ctx** out, int device) {
 extern "C" void wgg_destroy(wgg_ctx* ctx) {
   if (!ctx) return;
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+  if (ctx->async_err) cudaFree(ctx->async_err);
   if (ctx->prof_ev) {
     for (int i = 0; i < 2 * wgg_ctx::kProfMax; ++i) cudaEventDestroy(ctx->prof_ev[i]);
     delete[] ctx->prof_ev;
@@ -74,5 +80,13 @@ extern "C" int wgg_profile_read(wgg_ctx* ctx, double* total_ms, int64_t* launche
   if (launches) *launches = ctx->prof_n;
   if (flops) *flops = ctx->prof_flops;
   if (bytes) *bytes = ctx->prof_bytes;
+  return WGG_OK;
+}
+
+extern "C" int wgg_async_error(wgg_ctx* ctx, int* code) {
+  if (!ctx || !code) return WGG_EINVAL;
+  if (cudaMemcpy(code, ctx->async_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return wgg_fail(ctx, WGG_ECUDA, "async_error: %s", cudaGetErrorString(cudaGetLastError()));
+  if (*code != 0) cudaMemset(ctx->async_err, 0, sizeof(int));
   return WGG_OK;
 }

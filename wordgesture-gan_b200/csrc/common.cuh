@@ -16,6 +16,8 @@ struct wgg_ctx {
   // consecutive reductions queued on one stream never share a slot with a finalize still in flight.
   float* red_scratch = nullptr;
   int red_slot = 0;
+  // device word set by a persistent kernel whose pipeline wedged (bounded mbarrier waits); see wgg_async_error
+  int* async_err = nullptr;
   // optional per-kernel-class CUDA-event timing (bench.py's roofline): see wgg_profile_enable
   bool prof_on = false;
   char prof_filter[64] = {0};
@@ -112,6 +114,11 @@ struct GemmP {
   // split-K: partial sums go to `partial` ([nbatch][splitk][M][N] dense) and are reduced deterministically.
   int splitk = 1;
   float* partial = nullptr;
+  // numerics: 0 = follow the context's math mode (TF32 tensor cores when wgg_set_math_mode(ctx, 1));
+  //           1 = always fp32 FMA (nn.Linear layers: the reference keeps cuBLAS matmuls in true fp32,
+  //               only cuDNN LSTM / conv run TF32 - SURVEY.md 2.4 K1/K4/K7)
+  int force_fp32 = 0;
+  int x3 = 0;  // tensor-core mode: error-compensated 3xTF32 (always on for conv windows)
 };
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
@@ -188,3 +195,14 @@ struct FeatTable {
   int width[WGG_MAX_HIDDEN_LAYERS + 2];
 };
 int disc_feature_table(const wgg_model_cfg* cfg, int64_t B, FeatTable* ft);
+
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05 persistent BiLSTM forward (lstm_tc.cu)
+// ----------------------------------------------------------------------------------------------
+bool generator_tc_supported(const wgg_model_cfg* cfg);
+int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
+int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
+                         const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
+                         const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
+                         int64_t B, float* out, float* ws, int64_t ws_floats, cudaStream_t st);

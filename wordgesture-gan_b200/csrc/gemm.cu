@@ -11,10 +11,110 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;     // fp32 FMA kernel tile
+constexpr int TBM = 128, TBN = 64, TBK = 16, TPAD = 8;  // tensor-core kernel tile
 
+__device__ __forceinline__ int fast_div(int x, int d, float inv) {
+  int q = (int)(((float)x + 0.5f) * inv);
+  const int r = x - q * d;  // one correction step: exact for 0 <= x < 2^23
+  q += (r >= d) - (r < 0);
+  return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Operand tile loaders.  Every division / modulo is hoisted out of the K loop: per thread the (m | n)
+// coordinate of each element is fixed and only k advances by the tile depth, so global offsets are advanced
+// incrementally and the conv-window test costs one add + one compare per element.
+// ---------------------------------------------------------------------------------------------
+// Element e of a thread sits at tile coordinates (c0 + e*dc) in the fixed (m | n) direction and (k0 + e*dk) in
+// k, an affine pattern, so only the bases live in registers.
+template <int NE, int TILE_MN, int TILE_K, int CONV>
+struct ALoader {
+  int64_t off0, doff, kstep;
+  int mm0, kk0, dmm, dkk;
+  int mt[CONV == 1 ? NE : 1];
+  float inv_cin;
+  __device__ __forceinline__ int mm(int e) const { return mm0 + e * dmm; }
+  __device__ __forceinline__ int kk(int e) const { return kk0 + e * dkk; }
+  __device__ __forceinline__ void init(const GemmP& p, int64_t m0, int64_t k_begin, int tid) {
+    if (p.sak == 1) { kk0 = tid % TILE_K; mm0 = tid / TILE_K; dkk = 0; dmm = 256 / TILE_K; }
+    else { mm0 = tid % TILE_MN; kk0 = tid / TILE_MN; dmm = 0; dkk = 256 / TILE_MN; }
+    kstep = (int64_t)TILE_K * p.sak;
+    off0 = (m0 + mm0) * p.sam + (k_begin + kk0) * p.sak;
+    doff = (int64_t)dmm * p.sam + (int64_t)dkk * p.sak;
+    inv_cin = CONV == 1 ? 1.f / (float)p.conv_Cin : 0.f;
+    if (CONV == 1) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) mt[e] = (int)((m0 + mm(e)) % p.conv_T) - p.conv_pad;
+    }
+  }
+  __device__ __forceinline__ void load(const GemmP& p, const float* __restrict__ A, int64_t m0, int64_t k0,
+                                       float (&r)[NE]) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int64_t k = k0 + kk(e);
+      bool v = (m0 + mm(e) < p.M) && k < p.K;
+      if (CONV == 1 && v) v = (unsigned)(mt[e] + fast_div((int)k, p.conv_Cin, inv_cin)) < (unsigned)p.conv_T;
+      r[e] = v ? __ldg(A + off0 + e * doff) : 0.f;
+    }
+    off0 += kstep;
+  }
+};
+
+template <int NE, int TILE_MN, int TILE_K, int CONV>
+struct BLoader {
+  int64_t off0, doff, kstep;
+  int nn0, kk0, dnn, dkk;
+  int nc[CONV == 2 ? NE : 1], kmod[CONV == 2 ? NE : 1];
+  __device__ __forceinline__ int nn(int e) const { return nn0 + e * dnn; }
+  __device__ __forceinline__ int kk(int e) const { return kk0 + e * dkk; }
+  __device__ __forceinline__ void init(const GemmP& p, int64_t n0, int64_t k_begin, int tid) {
+    if ((p.sbn == 1) || (p.sbk != 1)) { nn0 = tid % TILE_MN; kk0 = tid / TILE_MN; dnn = 0; dkk = 256 / TILE_MN; }
+    else { kk0 = tid % TILE_K; nn0 = tid / TILE_K; dkk = 0; dnn = 256 / TILE_K; }
+    kstep = (int64_t)TILE_K * p.sbk;
+    off0 = (k_begin + kk0) * p.sbk + (n0 + nn0) * p.sbn;
+    doff = (int64_t)dkk * p.sbk + (int64_t)dnn * p.sbn;
+    if (CONV == 2) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        nc[e] = (int)((n0 + nn(e)) / p.conv_Cin) - p.conv_pad;
+        kmod[e] = (int)((k_begin + kk(e)) % p.conv_T);
+      }
+    }
+  }
+  __device__ __forceinline__ void load(const GemmP& p, const float* __restrict__ B, int64_t n0, int64_t k0,
+                                       float (&r)[NE]) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int64_t k = k0 + kk(e);
+      bool v = (n0 + nn(e) < p.N) && k < p.K;
+      if (CONV == 2) {
+        v = v && (unsigned)(kmod[e] + nc[e]) < (unsigned)p.conv_T;
+        kmod[e] += TILE_K;
+        while (kmod[e] >= p.conv_T) kmod[e] -= p.conv_T;
+      }
+      r[e] = v ? __ldg(B + off0 + e * doff) : 0.f;
+    }
+    off0 += kstep;
+  }
+};
+
+__device__ __forceinline__ void store_out(const GemmP& p, float* C, const float* bias, const float* bias2, int64_t m,
+                                          int64_t n, float v) {
+  if (bias) v += __ldg(bias + n);
+  if (bias2) v += __ldg(bias2 + n);
+  if (p.act == ACT_LEAKY) v = leaky_f(v);
+  else if (p.act == ACT_TANH) v = tanhf(v);
+  float* dst = C + m * p.scm + n * p.scn;
+  if (p.accumulate) v += *dst;
+  *dst = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 FMA kernel: 64x64x16 tile, 256 threads, 4x4 register tile
+// ---------------------------------------------------------------------------------------------
 template <int CONV>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
+__global__ void __launch_bounds__(256, 2) gemm_kernel(GemmP p) {
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -28,49 +128,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   const int64_t kt_begin = (int64_t)split * per;
   const int64_t kt_end = min(ktiles, kt_begin + per);
 
-  // thread -> tile element maps chosen so that global reads run along the unit-stride dimension
-  const bool a_kfast = (p.sak == 1);
-  const bool b_nfast = (p.sbn == 1) || (p.sbk != 1);
-  int a_mm[4], a_kk[4], b_kk[4], b_nn[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = tid + i * 256;
-    if (a_kfast) { a_kk[i] = idx % BK; a_mm[i] = idx / BK; } else { a_mm[i] = idx % BM; a_kk[i] = idx / BM; }
-    if (b_nfast) { b_nn[i] = idx % BN; b_kk[i] = idx / BN; } else { b_kk[i] = idx % BK; b_nn[i] = idx / BK; }
-  }
-
-  auto load_a = [&](int64_t k0, float (&r)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + a_mm[i], k = k0 + a_kk[i];
-      float v = 0.f;
-      if (m < p.M && k < p.K) {
-        bool ok = true;
-        if (CONV == 1) {
-          const int tt = (int)(m % p.conv_T) + (int)(k / p.conv_Cin) - p.conv_pad;
-          ok = (unsigned)tt < (unsigned)p.conv_T;
-        }
-        if (ok) v = __ldg(A + m * p.sam + k * p.sak);
-      }
-      r[i] = v;
-    }
-  };
-  auto load_b = [&](int64_t k0, float (&r)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t k = k0 + b_kk[i], n = n0 + b_nn[i];
-      float v = 0.f;
-      if (k < p.K && n < p.N) {
-        bool ok = true;
-        if (CONV == 2) {
-          const int tt = (int)(k % p.conv_T) + (int)(n / p.conv_Cin) - p.conv_pad;
-          ok = (unsigned)tt < (unsigned)p.conv_T;
-        }
-        if (ok) v = __ldg(B + k * p.sbk + n * p.sbn);
-      }
-      r[i] = v;
-    }
-  };
+  ALoader<4, BM, BK, CONV> la;
+  BLoader<4, BN, BK, CONV> lb;
+  la.init(p, m0, kt_begin * BK, tid);
+  lb.init(p, n0, kt_begin * BK, tid);
 
   float acc[4][4];
 #pragma unroll
@@ -81,19 +142,19 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   const int tx = tid % 16, ty = tid / 16;
   float ra[4], rb[4];
   if (kt_begin < kt_end) {
-    load_a(kt_begin * BK, ra);
-    load_b(kt_begin * BK, rb);
+    la.load(p, A, m0, kt_begin * BK, ra);
+    lb.load(p, B, n0, kt_begin * BK, rb);
   }
   for (int64_t kt = kt_begin; kt < kt_end; ++kt) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      As[a_kk[i]][a_mm[i]] = ra[i];
-      Bs[b_kk[i]][b_nn[i]] = rb[i];
+      As[la.kk(i)][la.mm(i)] = ra[i];
+      Bs[lb.kk(i)][lb.nn(i)] = rb[i];
     }
     __syncthreads();
     if (kt + 1 < kt_end) {
-      load_a((kt + 1) * BK, ra);
-      load_b((kt + 1) * BK, rb);
+      la.load(p, A, m0, (kt + 1) * BK, ra);
+      lb.load(p, B, n0, (kt + 1) * BK, rb);
     }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
@@ -109,40 +170,157 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     __syncthreads();
   }
 
-  if (p.splitk > 1) {
-    float* P = p.partial + (int64_t)blockIdx.z * p.M * p.N;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + ty * 4 + i;
-      if (m >= p.M) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t n = n0 + tx * 4 + j;
-        if (n < p.N) P[m * p.N + n] = acc[i][j];
-      }
-    }
-    return;
-  }
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
   float* C = p.C + (int64_t)batch * p.bsC;
   const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
   const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int64_t n = n0 + tx * 4 + j;
-    if (n >= p.N) continue;
-    float bsum = 0.f;
-    if (bias) bsum += __ldg(bias + n);
-    if (bias2) bsum += __ldg(bias2 + n);
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + ty * 4 + i;
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      if (P) P[m * p.N + n] = acc[i][j];
+      else store_out(p, C, bias, bias2, m, n, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core kernel (mma.sync.m16n8k8 TF32, fp32 accumulate): 128x64x16 block tile, 8 warps as 4(m) x 2(n),
+// warp tile 32x32.  X3 = error-compensated "3xTF32" (a_hi b_hi + a_hi b_lo + a_lo b_hi), fp32-grade accuracy
+// for the conv stack whose gradients do not tolerate plain TF32 (measured 6e-3 rel-L2 vs the 1e-3 budget).
+// These contractions are HBM-bound (K <= 320), which is why the warp-level MMA path suffices here; the
+// on-chip-resident recurrent kernel uses tcgen05 + TMEM (lstm_tc.cu).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int CONV, int X3>
+__global__ void __launch_bounds__(256, 2) gemm_mma_kernel(GemmP p) {
+  __shared__ __align__(16) float As[TBK][TBM + TPAD];
+  __shared__ __align__(16) float Bs[TBK][TBN + TPAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+  const float* __restrict__ A = p.A + (int64_t)batch * p.bsA;
+  const float* __restrict__ B = p.B + (int64_t)batch * p.bsB;
+  const int64_t m0 = (int64_t)blockIdx.x * TBM;
+  const int64_t n0 = (int64_t)blockIdx.y * TBN;
+  const int64_t ktiles = (p.K + TBK - 1) / TBK;
+  const int64_t per = (ktiles + p.splitk - 1) / p.splitk;
+  const int64_t kt_begin = (int64_t)split * per;
+  const int64_t kt_end = min(ktiles, kt_begin + per);
+
+  ALoader<8, TBM, TBK, CONV> la;
+  BLoader<4, TBN, TBK, CONV> lb;
+  la.init(p, m0, kt_begin * TBK, tid);
+  lb.init(p, n0, kt_begin * TBK, tid);
+
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int g = lane >> 2, q = lane & 3;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  float ra[8], rb[4];
+  if (kt_begin < kt_end) {
+    la.load(p, A, m0, kt_begin * TBK, ra);
+    lb.load(p, B, n0, kt_begin * TBK, rb);
+  }
+  for (int64_t kt = kt_begin; kt < kt_end; ++kt) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) As[la.kk(e)][la.mm(e)] = ra[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Bs[lb.kk(e)][lb.nn(e)] = rb[e];
+    __syncthreads();
+    if (kt + 1 < kt_end) {
+      la.load(p, A, m0, (kt + 1) * TBK, ra);
+      lb.load(p, B, n0, (kt + 1) * TBK, rb);
+    }
+#pragma unroll
+    for (int ks = 0; ks < TBK; ks += 8) {
+      float af[2][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int mb = wm + i * 16;
+        af[i][0] = As[ks + q][mb + g];
+        af[i][1] = As[ks + q][mb + g + 8];
+        af[i][2] = As[ks + q + 4][mb + g];
+        af[i][3] = As[ks + q + 4][mb + g + 8];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nb = wn + j * 8;
+        bf[j][0] = Bs[ks + q][nb + g];
+        bf[j][1] = Bs[ks + q + 4][nb + g];
+      }
+      uint32_t ah[2][4], bh[4][2], al[2][4], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ah[i][c] = to_tf32(af[i][c]);
+          if (X3) al[i][c] = to_tf32(af[i][c] - __uint_as_float(ah[i][c]));
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          bh[j][c] = to_tf32(bf[j][c]);
+          if (X3) bl[j][c] = to_tf32(bf[j][c] - __uint_as_float(bh[j][c]));
+        }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (X3) {
+            mma_tf32(acc[i][j], al[i], bh[j]);
+            mma_tf32(acc[i][j], ah[i], bl[j]);
+          }
+          mma_tf32(acc[i][j], ah[i], bh[j]);
+        }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: thread holds C[(g | g+8)][2q, 2q+1] of each 16x8 tile
+  float* C = p.C + (int64_t)batch * p.bsC;
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
+  const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
+  const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int64_t m = m0 + wm + i * 16 + g + rr * 8;
       if (m >= p.M) continue;
-      float v = acc[i][j] + bsum;
-      if (p.act == ACT_LEAKY) v = leaky_f(v);
-      else if (p.act == ACT_TANH) v = tanhf(v);
-      float* dst = C + m * p.scm + n * p.scn;
-      if (p.accumulate) v += *dst;
-      *dst = v;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int64_t n = n0 + wn + j * 8 + 2 * q + cc;
+          if (n >= p.N) continue;
+          const float v = acc[i][j][rr * 2 + cc];
+          if (P) P[m * p.N + n] = v;
+          else store_out(p, C, bias, bias2, m, n, v);
+        }
+      }
     }
   }
 }
@@ -193,7 +371,8 @@ constexpr int kMaxSplit = 128;
 }  // namespace
 
 int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch) {
-  const int64_t tiles = cdiv64(M, BM) * cdiv64(N, BN) * nbatch;
+  const bool tf32 = ctx->math_mode == 1;
+  const int64_t tiles = cdiv64(M, tf32 ? TBM : BM) * cdiv64(N, tf32 ? TBN : BN) * nbatch;
   const int64_t ktiles = cdiv64(K, BK);
   int64_t want = cdiv64(2 * (int64_t)ctx->sm_count, tiles);
   int64_t maxs = ktiles / 8;  // at least 8 k-tiles per split
@@ -210,11 +389,19 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.M >= (1ll << 31) || p.K >= (1ll << 31)) return wgg_fail(ctx, WGG_EINVAL, "gemm: dimension too large%s");
   if (p.splitk > 1 && (!p.partial || p.act != ACT_NONE || p.bias || p.bias2))
     return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K needs a partial buffer and a plain epilogue%s");
-  dim3 grid((unsigned)cdiv64(p.M, BM), (unsigned)cdiv64(p.N, BN), (unsigned)(p.nbatch * p.splitk));
+  const bool tf32 = ctx->math_mode == 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
+  const int bm = tf32 ? TBM : BM, bn = tf32 ? TBN : BN;
+  dim3 grid((unsigned)cdiv64(p.M, bm), (unsigned)cdiv64(p.N, bn), (unsigned)(p.nbatch * p.splitk));
   if (grid.y > 65535 || grid.z > 65535) return wgg_fail(ctx, WGG_EINVAL, "gemm: grid too large%s");
   ProfScope prof(ctx, "gemm_kernel", st, 2.0 * (double)p.M * (double)p.N * (double)p.K * p.nbatch,
                  4.0 * ((double)p.M * p.K + (double)p.K * p.N + (double)p.M * p.N) * p.nbatch);
-  if (p.conv_mode == 1) gemm_kernel<1><<<grid, 256, 0, st>>>(p);
+  if (tf32) {
+    const bool x3 = p.conv_mode != 0 || p.x3;
+    if (p.conv_mode == 1) gemm_mma_kernel<1, 1><<<grid, 256, 0, st>>>(p);
+    else if (p.conv_mode == 2) gemm_mma_kernel<2, 1><<<grid, 256, 0, st>>>(p);
+    else if (x3) gemm_mma_kernel<0, 1><<<grid, 256, 0, st>>>(p);
+    else gemm_mma_kernel<0, 0><<<grid, 256, 0, st>>>(p);
+  } else if (p.conv_mode == 1) gemm_kernel<1><<<grid, 256, 0, st>>>(p);
   else if (p.conv_mode == 2) gemm_kernel<2><<<grid, 256, 0, st>>>(p);
   else gemm_kernel<0><<<grid, 256, 0, st>>>(p);
   WGG_CHECK_LAUNCH(ctx, "gemm_kernel");

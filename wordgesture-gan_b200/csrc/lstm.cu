@@ -376,7 +376,11 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   GenLayout g;
   if (gen_layout(cfg, &g) != WGG_OK) return -1;
   const int64_t TB = (int64_t)g.T * B;
-  if (!backward) return TB * (g.I0 + 4 * g.H + 8 * g.H);  // x0 + two hseq + gates (no-grad forward)
+  if (!backward) {  // no-grad forward: x0 + two hseq + gates (FMA path) or the tcgen05 path's buffers
+    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H);
+    const int64_t tcw = generator_tc_workspace_floats(cfg, B);
+    return simt > tcw ? simt : tcw;
+  }
   const int64_t maxI = g.I0 > 2 * g.H ? g.I0 : 2 * g.H;
   return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2);
 }
@@ -390,6 +394,11 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   if (B <= 0) return WGG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t TB = (int64_t)g.T * B;
+  if (!stash && ctx->math_mode == 1 && generator_tc_supported(cfg)) {
+    // no-grad calls (sampling, and the 10 critic-loop generations per batch) run on the tcgen05 path
+    return generator_forward_tc(ctx, cfg, params, g.layer_off, g.dir_stride, g.off_whh, g.off_bih, g.off_bhh, g.off_wo,
+                                g.off_bo, proto, z, B, out, ws, ws_floats, st);
+  }
   StashView sv;
   float* hbuf[2] = {nullptr, nullptr};
   float* gates_ws = nullptr;
@@ -428,7 +437,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   p.B = params + g.off_wo; p.N = g.C; p.sbk = 1; p.sbn = 2 * g.H;
   p.C = out; p.scm = (int64_t)g.T * g.C; p.scn = 1;
   p.nbatch = g.T; p.bsA = B * 2 * g.H; p.bsB = 0; p.bsC = g.C; p.bsBias = 0;
-  p.bias = params + g.off_bo; p.act = ACT_TANH;
+  p.bias = params + g.off_bo; p.act = ACT_TANH; p.force_fp32 = 1;  // nn.Linear head stays fp32
   return gemm_launch(ctx, p, st);
 }
 
@@ -460,14 +469,14 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     GemmP p;  // dWo (C x 2H) += dpre^T * hL
     p.A = dpre; p.M = g.C; p.K = TB; p.sam = 1; p.sak = g.C;
     p.B = hL; p.N = 2 * H; p.sbk = 2 * H; p.sbn = 1;
-    p.C = dparams + g.off_wo; p.scm = 2 * H; p.scn = 1; p.accumulate = 1;
+    p.C = dparams + g.off_wo; p.scm = 2 * H; p.scn = 1; p.accumulate = 1; p.force_fp32 = 1;
     p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 1); p.partial = part;
     WGG_TRY(gemm_launch(ctx, p, st));
     WGG_TRY(colsum_launch(ctx, dpre, TB, g.C, g.C, 1, 0, dparams + g.off_bo, nullptr, 0, 1, csws, st));
     GemmP q;  // dh (TB x 2H) = dpre * Wo
     q.A = dpre; q.M = TB; q.K = g.C; q.sam = g.C; q.sak = 1;
     q.B = params + g.off_wo; q.N = 2 * H; q.sbk = 2 * H; q.sbn = 1;
-    q.C = dh; q.scm = 2 * H; q.scn = 1;
+    q.C = dh; q.scm = 2 * H; q.scn = 1; q.force_fp32 = 1;
     WGG_TRY(gemm_launch(ctx, q, st));
   }
   for (int l = g.L - 1; l >= 0; --l) {

@@ -1,0 +1,521 @@
+// Persistent BiLSTM-layer forward on 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces, for the no-grad generator calls (10 of the 12 per training batch: src/shared/utils.py:70-73,91-94;
+// and all of sampling: eval_gan.py:131-135), nn.LSTM's per-layer work of src/gan/models.py:160:
+//     gates_t = x_t W_ih^T + h_{t-1} W_hh^T + b ;  c_t = f c_{t-1} + i g ;  h_t = o tanh(c_t)
+// One CTA owns a tile of 128 samples of one direction for all T timesteps:
+//   * W_ih, W_hh (TF32) stay resident in shared memory for the whole sequence;
+//   * x_t tiles stream in through a 5-stage ring of bulk asynchronous copies (cp.async.bulk -> mbarrier tx);
+//   * one elected thread issues tcgen05.mma kind::tf32 (M=128 samples, N=192 gates, K=8 per instruction), the
+//     accumulator lives in TMEM (two 192-column buffers: the x-projection of step t+1 is issued while the
+//     epilogue of step t still runs; only h_{t-1} W_hh^T sits on the recurrent critical path);
+//   * 8 epilogue warps read the accumulator with tcgen05.ld (one thread = one sample row, gates of a hidden
+//     unit are adjacent columns because the weight rows are permuted unit-major), apply the gate
+//     non-linearities, keep c in registers, and write h_t both to shared memory (the next step's A operand)
+//     and to HBM (the next layer's input).
+//
+// Operand layout ("tc layout", no swizzle, K-major core matrices): a [rows x K] fp32 matrix is stored as
+//   [K/4 chunks][rows/8 groups][8 rows][4 floats]   i.e. 128-byte core matrices (8 rows x 16 B);
+// UMMA descriptors use LBO = stride between consecutive 16-byte K chunks, SBO = 128 B between 8-row groups.
+// Layer activations live in HBM in exactly this layout per 128-row tile and timestep, so a timestep's tile is
+// ONE contiguous block: it is fetched with plain bulk copies (no tensor map) and written by the epilogue with
+// fully coalesced 16-byte stores (lane = row).
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int TM = 128;   // samples per CTA tile (UMMA M)
+constexpr int HID = 48;   // hidden units (this kernel is specialised for the default model)
+constexpr int N4 = 192;   // gate columns (UMMA N)
+constexpr int KH_CHUNKS = HID / 4;
+constexpr int CHUNK_BYTES_A = (TM / 8) * 128;  // 2048: one 16-byte K chunk of a 128-row tile
+constexpr int CHUNK_BYTES_W = (N4 / 8) * 128;  // 3072: one 16-byte K chunk of the 192-row weight image
+constexpr int SB_CHUNKS = 8;                   // K chunks per ring stage (32 floats)
+constexpr int SB_BYTES = SB_CHUNKS * CHUNK_BYTES_A;  // 16384
+constexpr int NSTAGE = 5;
+constexpr int NTHREADS = 320;                  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int ACC_COLS = N4;                   // TMEM columns per accumulator buffer
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: returns false if the kernel is being aborted (a peer timed out) or this wait timed out
+// (~2 s), in which case *abort_flag and the global error word are set.  A wedged pipeline therefore ends
+// the kernel instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code) {
+  if (mbar_try(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try(bar, parity)) return true;
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 4000000000ll) {
+      *abort_flag = 1;
+      atomicCAS(gerr, 0, code);
+      return false;
+    }
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major, no swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N=192, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N4 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// element (row, k) of a tc-layout tile with `rows` rows: float index
+__host__ __device__ __forceinline__ int64_t tc_index(int rows, int row, int k) {
+  return ((int64_t)(k >> 2) * (rows >> 3) + (row >> 3)) * 32 + (row & 7) * 4 + (k & 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight image: per (layer, dir): Wx [KXC chunks][24][8][4], Wh [12][24][8][4], bias[192]; rows permuted
+// unit-major (n' = 4u + gate  <->  PyTorch row gate*H + u), values rounded to TF32 (bias stays fp32).
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_weights_kernel(const float* __restrict__ lp, int64_t dir_stride, int64_t off_whh, int64_t off_bih,
+                                    int64_t off_bhh, int I, int KX, float* __restrict__ img, int64_t img_stride) {
+  const int dir = blockIdx.y;
+  const float* w = lp + dir * dir_stride;
+  float* o = img + dir * img_stride;
+  const int nx = N4 * KX, nh = N4 * HID;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nx + nh + N4; idx += gridDim.x * blockDim.x) {
+    if (idx < nx) {
+      const int np = idx / KX, k = idx % KX;
+      const int u = np >> 2, g = np & 3;
+      const float v = k < I ? w[(int64_t)(g * HID + u) * I + k] : 0.f;
+      o[tc_index(N4, np, k)] = rna_tf32(v);
+    } else if (idx < nx + nh) {
+      const int j = idx - nx;
+      const int np = j / HID, k = j % HID;
+      const int u = np >> 2, g = np & 3;
+      o[nx + tc_index(N4, np, k)] = rna_tf32(w[off_whh + (int64_t)(g * HID + u) * HID + k]);
+    } else {
+      const int np = idx - nx - nh;
+      const int u = np >> 2, g = np & 3;
+      o[nx + nh + np] = w[off_bih + g * HID + u] + w[off_bhh + g * HID + u];
+    }
+  }
+}
+
+// layer-0 input in tc layout, K padded to KX0 (zero fill), rows padded to the tile: (models.py:147-157)
+__global__ void build_x0_tc_kernel(const float* __restrict__ proto, const float* __restrict__ z, float* __restrict__ x0,
+                                   int T, int64_t B, int ntiles, int C, int pd, int Z, int KX0) {
+  const int64_t per_t = (int64_t)ntiles * TM * KX0;
+  const int64_t n = (int64_t)T * per_t;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // enumerate in storage order so that writes are coalesced
+    const int t = (int)(i / per_t);
+    int64_t r = i % per_t;
+    const int tile = (int)(r / ((int64_t)TM * KX0));
+    r %= (int64_t)TM * KX0;
+    const int chunk = (int)(r / (TM * 4));
+    const int row = (int)((r % (TM * 4)) / 4);
+    const int k = chunk * 4 + (int)(r & 3);
+    const int64_t b = (int64_t)tile * TM + row;
+    float v = 0.f;
+    if (b < B) {
+      if (k < pd) v = __ldg(proto + (b * T + t) * C + k);
+      else if (k < pd + Z) v = __ldg(z + b * Z + (k - pd));
+    }
+    x0[i] = rna_tf32(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent layer kernel.  grid (ntiles, 2 directions), 320 threads, 1 CTA / SM.
+// xin : [T][ntiles][KXC][16][8][4]   hout : [T][ntiles][24][16][8][4] (this direction fills chunks dir*12..+12)
+// ---------------------------------------------------------------------------------------------
+template <int KXC>
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
+                                                                  const float* __restrict__ wimg, int64_t img_stride,
+                                                                  float* __restrict__ hout, int T, int ntiles,
+                                                                  int* __restrict__ gerr) {
+  constexpr int NSB = (KXC + SB_CHUNKS - 1) / SB_CHUNKS;
+  constexpr int WX_BYTES = KXC * CHUNK_BYTES_W;
+  constexpr int WH_BYTES = KH_CHUNKS * CHUNK_BYTES_W;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_wx = smem;
+  uint8_t* s_wh = s_wx + WX_BYTES;
+  uint8_t* s_x = s_wh + WH_BYTES;
+  uint8_t* s_h = s_x + NSTAGE * SB_BYTES;
+  float* s_bias = reinterpret_cast<float*>(s_h + KH_CHUNKS * CHUNK_BYTES_A);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + N4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto BAR_ACC_FULL = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
+  auto BAR_ACC_EMPTY = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
+  const uint32_t BAR_H = bar0 + 8u * (2 * NSTAGE + 4);
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  {
+    const float4* src = reinterpret_cast<const float4*>(wimg + dir * img_stride);
+    float4* dst = reinterpret_cast<float4*>(s_wx);
+    constexpr int n4 = (WX_BYTES + WH_BYTES) / 16;
+    for (int i = tid; i < n4; i += NTHREADS) dst[i] = __ldg(src + i);
+    const float* bsrc = wimg + dir * img_stride + (WX_BYTES + WH_BYTES) / 4;
+    for (int i = tid; i < N4; i += NTHREADS) s_bias[i] = __ldg(bsrc + i);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(BAR_FULL(s), 1);
+      mbar_init(BAR_EMPTY(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR_ACC_FULL(b), 1);
+      mbar_init(BAR_ACC_EMPTY(b), 8);
+    }
+    mbar_init(BAR_H, 8);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();  // weights were written through the generic proxy; the tensor core reads via the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===== producer: stream x_t sub-blocks =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int step = 0; step < T && ok; ++step) {
+        const int t = dir ? T - 1 - step : step;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(xin) + ((int64_t)t * ntiles + tile) * KXC * CHUNK_BYTES_A;
+#pragma unroll 1
+        for (int sb = 0; sb < NSB; ++sb) {
+          if (!mbar_wait(BAR_EMPTY(stage), phase ^ 1, s_abort, gerr, 1)) { ok = false; break; }
+          const int chunks = (KXC - sb * SB_CHUNKS) < SB_CHUNKS ? (KXC - sb * SB_CHUNKS) : SB_CHUNKS;
+          const uint32_t bytes = chunks * CHUNK_BYTES_A;
+          mbar_expect_tx(BAR_FULL(stage), bytes);
+          bulk_g2s(smem_u32(s_x + stage * SB_BYTES), src + (int64_t)sb * SB_BYTES, bytes, BAR_FULL(stage));
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      const uint32_t wx = smem_u32(s_wx), wh = smem_u32(s_wh), hs = smem_u32(s_h);
+      for (int step = 0; step < T && ok; ++step) {
+        const int b = step & 1;
+        const uint32_t use = (uint32_t)(step >> 1);  // how many times this buffer has been used before
+        if (!mbar_wait(BAR_ACC_EMPTY(b), (use & 1) ^ 1, s_abort, gerr, 2)) break;
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(b * ACC_COLS);
+#pragma unroll 1
+        for (int sb = 0; sb < NSB; ++sb) {
+          if (!mbar_wait(BAR_FULL(stage), phase, s_abort, gerr, 3)) { ok = false; break; }
+          tc_fence_after();
+          const int chunks = (KXC - sb * SB_CHUNKS) < SB_CHUNKS ? (KXC - sb * SB_CHUNKS) : SB_CHUNKS;
+          const uint32_t xa = smem_u32(s_x + stage * SB_BYTES);
+          for (int j = 0; j < chunks / 2; ++j) {
+            const uint64_t ad = make_desc(xa + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
+            const uint64_t bd = make_desc(wx + (sb * SB_CHUNKS + 2 * j) * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
+            mma_tf32_ss(tacc, ad, bd, (sb | j) ? 1u : 0u);
+          }
+          mma_commit(BAR_EMPTY(stage));  // frees the ring stage once these MMAs have read it
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        if (step > 0) {
+          if (!mbar_wait(BAR_H, (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) break;
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < KH_CHUNKS / 2; ++j) {
+            const uint64_t ad = make_desc(hs + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
+            const uint64_t bd = make_desc(wh + j * 2 * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
+            mma_tf32_ss(tacc, ad, bd, 1u);
+          }
+        }
+        mma_commit(BAR_ACC_FULL(b));
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    float c[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) c[i] = 0.f;
+    float4* hs4 = reinterpret_cast<float4*>(s_h);
+    for (int step = 0; step < T; ++step) {
+      const int t = dir ? T - 1 - step : step;
+      const int b = step & 1;
+      if (!mbar_wait(BAR_ACC_FULL(b), (uint32_t)((step >> 1) & 1), s_abort, gerr, 5)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + half * 96);
+      float4* hg4 = reinterpret_cast<float4*>(hout) +
+                    (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * (TM) + row;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (ch == 2) {  // accumulator fully read by this warp: hand the buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
+        }
+        float hv[8];
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          const int ul = ch * 8 + uu;                 // unit index inside this thread's 24
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (half * 24 + ul) * 4);
+          const float ig = sigmoid_fast(v[4 * uu + 0] + bb.x);
+          const float fg = sigmoid_fast(v[4 * uu + 1] + bb.y);
+          const float gg = tanh_fast(v[4 * uu + 2] + bb.z);
+          const float og = sigmoid_fast(v[4 * uu + 3] + bb.w);
+          c[ul] = fg * c[ul] + ig * gg;
+          hv[uu] = rna_tf32(og * tanh_fast(c[ul]));
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int chunk = half * 6 + ch * 2 + k2;   // K chunk (4 hidden units) of this direction's h
+          const float4 q = make_float4(hv[4 * k2], hv[4 * k2 + 1], hv[4 * k2 + 2], hv[4 * k2 + 3]);
+          hs4[chunk * TM + row] = q;                  // next step's A operand
+          hg4[(int64_t)chunk * TM] = q;               // next layer's input (coalesced: lane = row)
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_H);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// out[b][t][:] = tanh(W_o [h_fwd, h_bwd] + b_o) from the last layer's tc-layout output   (models.py:163)
+// block: 8 warps = 8 timesteps x 32 rows; results staged in smem so each row writes 8*C contiguous floats.
+__global__ void __launch_bounds__(256) head_tc_kernel(const float* __restrict__ h, const float* __restrict__ wo,
+                                                      const float* __restrict__ bo, float* __restrict__ out, int T,
+                                                      int64_t B, int ntiles, int C) {
+  __shared__ float s_w[3 * 96 + 3];
+  __shared__ float s_o[32][8 * 3 + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < C * 96 + C; i += 256) s_w[i] = i < C * 96 ? wo[i] : bo[i - C * 96];
+  __syncthreads();
+  const int64_t row0 = (int64_t)blockIdx.x * 32;
+  const int t0 = blockIdx.y * 8;
+  const int t = t0 + warp;
+  const int64_t b = row0 + lane;
+  const int tile = (int)(b / TM), r = (int)(b % TM);
+  if (t < T && tile < ntiles) {
+    const float4* hp = reinterpret_cast<const float4*>(h) + ((int64_t)t * ntiles + tile) * 24 * TM + r;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int ck = 0; ck < 24; ++ck) {
+      const float4 v = __ldg(hp + (int64_t)ck * TM);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const float* w = s_w + cc * 96 + ck * 4;
+        acc[cc] = fmaf(v.x, w[0], fmaf(v.y, w[1], fmaf(v.z, w[2], fmaf(v.w, w[3], acc[cc]))));
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) s_o[lane][warp * 3 + cc] = tanhf(acc[cc] + s_w[C * 96 + cc]);
+  }
+  __syncthreads();
+  // 32 rows x (8 timesteps x 3) floats; each row's 24 floats are contiguous in out
+  for (int i = tid; i < 32 * 24; i += 256) {
+    const int rr = i / 24, j = i % 24;
+    const int64_t bb = row0 + rr;
+    const int tt = t0 + j / 3;
+    if (bb < B && tt < T) out[(bb * T + tt) * C + (j % 3)] = s_o[rr][j];
+  }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kKX0 = 40;  // layer-0 K (2 + 32 = 34, or 35 with time) padded to a multiple of 8
+
+struct TcPlan {
+  int T, L, Z, pd, C;
+  int ntiles;
+  int64_t rows;
+  int64_t x0_floats, h_floats, img_floats[WGG_MAX_HIDDEN_LAYERS], img_off[WGG_MAX_HIDDEN_LAYERS], total;
+};
+
+bool tc_plan(const wgg_model_cfg* c, int64_t B, TcPlan* p) {
+  if (c->gen_hidden_dim != tc::HID || c->input_dim != 3) return false;
+  const int pd = c->prototype_has_time ? 3 : 2;
+  if (pd + c->latent_dim > kKX0) return false;
+  p->T = c->seq_length; p->L = c->gen_num_layers; p->Z = c->latent_dim; p->pd = pd; p->C = c->input_dim;
+  p->ntiles = (int)cdiv64(B, tc::TM);
+  p->rows = (int64_t)p->ntiles * tc::TM;
+  p->x0_floats = (int64_t)p->T * p->rows * kKX0;
+  p->h_floats = (int64_t)p->T * p->rows * 96;
+  int64_t off = p->x0_floats + 2 * p->h_floats;
+  for (int l = 0; l < p->L; ++l) {
+    const int KX = l == 0 ? kKX0 : 96;
+    p->img_floats[l] = (int64_t)tc::N4 * (KX + tc::HID) + tc::N4;
+    p->img_off[l] = off;
+    off += 2 * p->img_floats[l];
+  }
+  p->total = off;
+  return true;
+}
+
+template <int KXC>
+int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_stride, float* hout, int T, int ntiles,
+                 int64_t B, cudaStream_t st) {
+  constexpr size_t smem = (size_t)KXC * tc::CHUNK_BYTES_W + tc::KH_CHUNKS * tc::CHUNK_BYTES_W + tc::NSTAGE * tc::SB_BYTES +
+                          tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 16 * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc::lstm_tc_fwd_kernel<KXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_fwd_kernel: cannot reserve shared memory%s");
+    configured = true;
+  }
+  dim3 grid((unsigned)ntiles, 2);
+  // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out
+  ProfScope prof(ctx, "lstm_tc_fwd_kernel", st, 2.0 * T * (double)B * 2.0 * tc::N4 * (KXC * 4 + tc::HID),
+                 (double)T * B * 4.0 * (2.0 * KXC * 4 + 96));
+  tc::lstm_tc_fwd_kernel<KXC><<<grid, tc::NTHREADS, smem, st>>>(xin, img, img_stride, hout, T, ntiles, ctx->async_err);
+  WGG_CHECK_LAUNCH(ctx, "lstm_tc_fwd_kernel");
+  return WGG_OK;
+}
+}  // namespace
+
+int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
+  TcPlan p;
+  return tc_plan(cfg, B, &p) ? p.total : 0;
+}
+
+bool generator_tc_supported(const wgg_model_cfg* cfg) {
+  TcPlan p;
+  return tc_plan(cfg, 1, &p);
+}
+
+// no-grad generator forward on the tcgen05 path.  `layer_off`, `dir_stride`, ... describe the flat parameter layout.
+int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
+                         const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
+                         const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
+                         int64_t B, float* out, float* ws, int64_t ws_floats, cudaStream_t st) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_forward_tc: unsupported configuration%s");
+  if (!ws || ws_floats < p.total) return wgg_fail(ctx, WGG_EWORKSPACE, "generator_forward_tc: workspace too small%s");
+  float* x0 = ws;
+  float* hbuf[2] = {ws + p.x0_floats, ws + p.x0_floats + p.h_floats};
+  for (int l = 0; l < p.L; ++l) {
+    const int I = l == 0 ? p.pd + p.Z : 96;
+    const int KX = l == 0 ? kKX0 : 96;
+    tc::prep_weights_kernel<<<dim3(32, 2), 256, 0, st>>>(params + layer_off[l], dir_stride[l], off_whh[l], off_bih[l],
+                                                         off_bhh[l], I, KX, ws + p.img_off[l], p.img_floats[l]);
+    WGG_CHECK_LAUNCH(ctx, "prep_weights_kernel");
+  }
+  tc::build_x0_tc_kernel<<<ew_blocks(p.x0_floats), 256, 0, st>>>(proto, z, x0, p.T, B, p.ntiles, p.C, p.pd, p.Z, kKX0);
+  WGG_CHECK_LAUNCH(ctx, "build_x0_tc_kernel");
+  const float* in = x0;
+  for (int l = 0; l < p.L; ++l) {
+    float* hout = hbuf[l & 1];
+    if (l == 0) {
+      WGG_TRY(launch_layer<kKX0 / 4>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, st));
+    } else {
+      WGG_TRY(launch_layer<24>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, st));
+    }
+    in = hout;
+  }
+  dim3 grid((unsigned)cdiv64(B, 32), (unsigned)((p.T + 7) / 8));
+  tc::head_tc_kernel<<<grid, 256, 0, st>>>(in, params + off_wo, params + off_bo, out, p.T, B, p.ntiles, p.C);
+  WGG_CHECK_LAUNCH(ctx, "head_tc_kernel");
+  return WGG_OK;
+}
