@@ -78,10 +78,15 @@ WGG_API int64_t wgg_launch_count(wgg_ctx* ctx);
  * the launch count and the algorithmic FLOPs / bytes those launches accounted for.  (max 16384 launches) */
 WGG_API int wgg_profile_enable(wgg_ctx* ctx, const char* kernel_substr);
 WGG_API int wgg_profile_read(wgg_ctx* ctx, double* total_ms, int64_t* launches, double* flops, double* bytes);
+/* per call-site text report of the same brackets: one "tag launches ms gflop" line per tag */
+WGG_API int wgg_profile_report(wgg_ctx* ctx, char* buf, int64_t size);
 /* SYNCHRONISING debug query: reads (and clears) the device-side error word that the persistent tcgen05
  * kernels set when one of their bounded mbarrier waits times out (code = which wait).  0 = healthy. */
 WGG_API int wgg_async_error(wgg_ctx* ctx, int* code);
-/* math mode: 0 = fp32 FMA everywhere (default), 1 = TF32 tensor-core contractions where available */
+/* math mode: 0 = fp32 FMA everywhere (default);
+ * 1 = "tf32": LSTM and conv contractions on TF32 tensor cores (tcgen05 kernels; the numerics of the reference's
+ *     own CUDA path, cuDNN TF32), nn.Linear layers stay fp32;
+ * 2 = "tf32x3": LSTM as in 1, conv contractions in error-compensated 3xTF32 (fp32-grade gradients). */
 WGG_API int wgg_set_math_mode(wgg_ctx* ctx, int mode);
 
 /* ---- Generator: replaces Generator.forward, src/gan/models.py:125-165 (+ its autograd) --------
@@ -142,7 +147,12 @@ WGG_API int wgg_disc_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float
 WGG_API int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* sn, const float* x,
                       int64_t B, const float* stash, const float* dscore, const float* dfeat, float* dparams,
                       float* dx, float* ws, int64_t ws_floats, void* stream);
-/* (B, T, C) channel-last feature block -> (B, C*T) as get_all_features returns it (models.py:339). */
+/* Conv feature block of a stash <-> the public (B, C*T) layout get_all_features returns (models.py:339).
+ * The stash layout depends on the math mode the forward ran in ((B,T,C) or channel-chunked [B][C/4][T][4]);
+ * do not change the math mode between a forward and the calls that consume its stash. */
+WGG_API int wgg_disc_feature_convert(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* in, float* out, int64_t B,
+                                     int32_t T, int32_t C, int to_stash, void* stream);
+/* (B, T, C) -> (B, C, T) transpose (generic helper). */
 WGG_API int wgg_transpose_tc(wgg_ctx* ctx, const float* in, float* out, int64_t B, int32_t T, int32_t C, void* stream);
 
 /* ---- Losses: replace src/gan/losses.py ------------------------------------------------------

@@ -368,14 +368,25 @@ def tf32_mode():
     wgg.set_math_mode("fp32")
 
 
+@pytest.fixture(params=["tf32", "tf32x3"])
+def tc_mode(request):
+    wgg.set_math_mode(request.param)
+    yield request.param
+    wgg.set_math_mode("fp32")
+
+
 TF32_FWD_TOL = 2e-3
-TF32_GRAD_TOL = 1e-2  # per-tensor rel-L2 against the fp64 oracle; measured values are logged to gpurun_out/
+# TF32 tensor-core modes, per-tensor gradient rel-L2 against the fp64 oracle.  The bounds are those of the
+# reference's OWN CUDA path measured on the same B200 (cuDNN TF32 convs / LSTM vs fp64, B=24, default model:
+# profiles/r01_ref_cuda_precision.json): generator 6e-4, discriminator weights up to 6.1e-3, discriminator input
+# gradient 1.6e-2.  "tf32x3" compensates the conv contractions and must meet the fp32 budget on the discriminator.
+TF32_GEN_GRAD_TOL = 2e-3
+TF32_DISC_GRAD_TOL = {"tf32": 2e-2, "tf32x3": 1e-3}
+TF32_DISC_DX_TOL = {"tf32": 4e-2, "tf32x3": 1e-3}
 
 
-def test_tf32_mode_parity(tf32_mode):
-    """TF32 tensor-core mode (LSTM + conv contractions; fp32 accumulate) against the fp64 oracle on the default
-    model.  The reference's own CUDA path runs these ops in TF32 (cuDNN default), whose error against fp64 the
-    survey measured at 7e-4 worst-tensor gradient rel-L2; we log what we measure."""
+def test_tensor_core_modes_parity(tc_mode):
+    """Tensor-core math modes against the fp64 oracle on the default model; measured errors are logged."""
     import json
     import os
     report = {}
@@ -395,21 +406,65 @@ def test_tf32_mode_parity(tf32_mode):
     report["gen_dz_rel_l2"] = rel_l2(to_np(zt.grad), dz_ref)
     D = wgg.TemporalDiscriminator(model_cfg(ocfg)).to(DEV).train()
     pd = state_of(D)
+    # critic-step pattern with feature-matching injection: exercises forward, weight grads, input grads
     rs_ref, _, st_r = O.disc_fwd(pd, ocfg, real, True)
     g_r, dx_ref = O.disc_bwd(pd, ocfg, st_r, np.full((B, 1), 1.0 / B), None)
     xt = to_t(real).requires_grad_(True)
     rs = D(xt)
     report["disc_fwd_max_abs_rel"] = max_abs_rel(to_np(rs), rs_ref)
     wgg.WassersteinLoss.generator_loss(rs).backward()  # = -mean(score): gradients are the negated oracle ones
-    report["disc_grad_worst_rel_l2"] = max(rel_l2(-v, g_r[k]) for k, v in grads_of(D).items())
+    per = {k: rel_l2(-v, g_r[k]) for k, v in grads_of(D).items()}
+    report["disc_grad_per_tensor"] = per
+    report["disc_grad_worst_rel_l2"] = max(per.values())
     report["disc_dx_rel_l2"] = rel_l2(-to_np(xt.grad), dx_ref)
+    # feature path: stash features and their gradient injection
+    fake = rand_inputs(ocfg, B, seed + 1)[0]
+    ff_ref, st_ff = O.disc_fwd(pd, ocfg, fake, True, features_only=True)
+    rf_ref, _ = O.disc_fwd(pd, ocfg, real, True, features_only=True)
+    fm_ref, dff = O.feature_matching(rf_ref, ff_ref)
+    _, dx_fm_ref = O.disc_bwd(pd, ocfg, st_ff, None, dff)
+    ft = to_t(fake).requires_grad_(True)
+    fs = D.features_stash(ft)
+    rstash = D.features_stash(to_t(real))
+    fm = wgg.feature_matching_from_stash(rstash, fs, D.config, B)
+    report["fm_loss_rel"] = abs(fm.item() - fm_ref) / abs(fm_ref)
+    fm.backward()
+    report["fm_dx_rel_l2"] = rel_l2(to_np(ft.grad), dx_fm_ref)
+    # public feature layout in this mode
+    feats = D.get_all_features(to_t(fake))
+    ff_ref2, _ = O.disc_fwd(pd, ocfg, fake, True, features_only=True)
+    report["public_feature_worst"] = max(max_abs_rel(to_np(a), b) for a, b in zip(feats, ff_ref2))
+    from wgg_b200 import _lib
+    torch.cuda.synchronize()
+    assert _lib.async_error(DEV) == 0, "tcgen05 pipeline timed out"
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/tf32_errors.json", "w") as f:
+    with open(f"gpurun_out/{tc_mode}_errors.json", "w") as f:
         json.dump(report, f, indent=1)
-    print(report)
+    print(tc_mode, report)
     assert report["gen_fwd_max_abs_rel"] <= TF32_FWD_TOL and report["disc_fwd_max_abs_rel"] <= TF32_FWD_TOL
-    for k in ("gen_grad_worst_rel_l2", "gen_dz_rel_l2", "disc_grad_worst_rel_l2", "disc_dx_rel_l2"):
-        assert report[k] <= TF32_GRAD_TOL, (k, report[k])
+    assert report["public_feature_worst"] <= TF32_FWD_TOL
+    assert report["gen_grad_worst_rel_l2"] <= TF32_GEN_GRAD_TOL and report["gen_dz_rel_l2"] <= TF32_GEN_GRAD_TOL
+    assert report["disc_grad_worst_rel_l2"] <= TF32_DISC_GRAD_TOL[tc_mode], report["disc_grad_per_tensor"]
+    assert report["disc_dx_rel_l2"] <= TF32_DISC_DX_TOL[tc_mode]
+    assert report["fm_dx_rel_l2"] <= TF32_DISC_DX_TOL[tc_mode] and report["fm_loss_rel"] <= 1e-2
+
+
+@pytest.mark.parametrize("case", ["default"])
+def test_train_batch_golden_tensor_core_modes(tc_mode, case):
+    """Full training batch from the reference's golden state in the tensor-core modes: all 11 losses within the
+    TF32 budget and the pipeline-timeout word clear."""
+    from wgg_b200 import _lib
+    g = Golden(case)
+    tr = trainer_from_golden(g)
+    real, proto, noise = g.inputs()
+    for m in (tr.generator, tr.encoder, tr.discriminator_1, tr.discriminator_2):
+        m.train()
+    out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise])
+    torch.cuda.synchronize()
+    assert _lib.async_error(DEV) == 0
+    for k in LOSS_KEYS:
+        ref = g.loss(k)
+        assert abs(out[k].item() - ref) <= 2e-2 * max(abs(ref), 1e-2), (tc_mode, k, out[k].item(), ref)
 
 
 @pytest.mark.parametrize("B", [1, 7, 130, 300])

@@ -40,6 +40,7 @@ _SIG = {
     "wgg_launch_count": (c_int64, [_P]),
     "wgg_set_math_mode": (c_int, [_P, c_int]),
     "wgg_async_error": (c_int, [_P, POINTER(c_int)]),
+    "wgg_profile_report": (c_int, [_P, c_char_p, c_int64]),
     "wgg_profile_enable": (c_int, [_P, c_char_p]),
     "wgg_profile_read": (c_int, [_P, POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double),
                                  POINTER(ctypes.c_double)]),
@@ -65,6 +66,7 @@ _SIG = {
     "wgg_disc_forward": (c_int, [_P, _CFG, _P, _P, _P, c_int64, _P, _P, _P]),
     "wgg_disc_backward": (c_int, [_P, _CFG, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "wgg_transpose_tc": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "wgg_disc_feature_convert": (c_int, [_P, _CFG, _P, _P, c_int64, c_int32, c_int32, c_int, _P]),
     "wgg_mean": (c_int, [_P, _P, c_int64, c_float, c_int, _P, _P]),
     "wgg_mean_backward": (c_int, [_P, _P, c_float, c_int64, _P, _P]),
     "wgg_l1_mean": (c_int, [_P, _P, _P, c_int64, c_float, c_int, _P, _P]),
@@ -197,11 +199,12 @@ _math_mode = 0
 
 def set_math_mode(mode, device=None) -> None:
     """"fp32" / 0: every contraction in fp32 FMA (bit-for-bit the most faithful, used by the tight parity tests).
-    "tf32" / 1: LSTM and conv contractions on TF32 tensor cores with fp32 accumulation - the numerics of the
-    reference's own CUDA path (cuDNN allows TF32 by default); nn.Linear layers stay fp32."""
+    "tf32" / 1: LSTM and conv contractions on TF32 tensor cores (tcgen05 kernels) with fp32 accumulation - the
+    numerics of the reference's own CUDA path (cuDNN allows TF32 by default); nn.Linear layers
+    stay fp32.  "tf32x3" / 2: as "tf32" but conv contractions in error-compensated 3xTF32 (fp32-grade)."""
     global _math_mode
-    m = {"fp32": 0, "tf32": 1}.get(mode, mode)
-    if m not in (0, 1):
+    m = {"fp32": 0, "tf32": 1, "tf32x3": 2}.get(mode, mode)
+    if m not in (0, 1, 2):
         raise ValueError(f"unknown math mode {mode!r}")
     _math_mode = m
     for idx, c in _ctx.items():
@@ -209,7 +212,7 @@ def set_math_mode(mode, device=None) -> None:
 
 
 def get_math_mode() -> str:
-    return "tf32" if _math_mode else "fp32"
+    return ("fp32", "tf32", "tf32x3")[_math_mode]
 
 
 def async_error(device) -> int:
@@ -218,3 +221,20 @@ def async_error(device) -> int:
     code = c_int(0)
     check(lib().wgg_async_error(c, ctypes.byref(code)), c)
     return code.value
+
+
+def profile_report(device):
+    c = ctx(device)
+    buf = ctypes.create_string_buffer(16384)
+    check(lib().wgg_profile_report(c, buf, 16384), c)
+    rows = []
+    for line in buf.value.decode().splitlines():
+        tag, n, ms, gf = line.rsplit(" ", 3)
+        rows.append(dict(tag=tag, launches=int(n), ms=float(ms), gflop=float(gf)))
+    return rows
+
+
+# Set by train_step while the generator/encoder step back-propagates through the discriminators: their weight
+# gradients are discarded by the reference (zero_grad before the next critic backward, utils.py:75,96), so the
+# discriminator backward may skip computing them.
+SKIP_DISC_WEIGHT_GRADS = False

@@ -44,7 +44,7 @@ extern "C" const char* wgg_last_error(wgg_ctx* ctx) { return ctx ? ctx->err : "n
 extern "C" int64_t wgg_launch_count(wgg_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 extern "C" int wgg_set_math_mode(wgg_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return WGG_EINVAL;
+  if (!ctx || mode < 0 || mode > 2) return WGG_EINVAL;
   ctx->math_mode = mode;
   return WGG_OK;
 }
@@ -59,6 +59,8 @@ extern "C" int wgg_profile_enable(wgg_ctx* ctx, const char* kernel_substr) {
   }
   if (!ctx->prof_ev) {
     ctx->prof_ev = new cudaEvent_t[2 * wgg_ctx::kProfMax];
+    ctx->prof_tag = new const char*[wgg_ctx::kProfMax];
+    ctx->prof_fl = new double[wgg_ctx::kProfMax];
     for (int i = 0; i < 2 * wgg_ctx::kProfMax; ++i)
       if (cudaEventCreate(&ctx->prof_ev[i]) != cudaSuccess) return wgg_fail(ctx, WGG_ECUDA, "profile: cudaEventCreate failed%s");
   }
@@ -88,5 +90,29 @@ extern "C" int wgg_async_error(wgg_ctx* ctx, int* code) {
   if (cudaMemcpy(code, ctx->async_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
     return wgg_fail(ctx, WGG_ECUDA, "async_error: %s", cudaGetErrorString(cudaGetLastError()));
   if (*code != 0) cudaMemset(ctx->async_err, 0, sizeof(int));
+  return WGG_OK;
+}
+
+// aggregated per call-site report: "tag launches ms gflop" lines
+extern "C" int wgg_profile_report(wgg_ctx* ctx, char* buf, int64_t size) {
+  if (!ctx || !buf || size <= 0) return WGG_EINVAL;
+  buf[0] = 0;
+  const int n = ctx->prof_n;
+  if (n == 0) return WGG_OK;
+  cudaEventSynchronize(ctx->prof_ev[2 * (n - 1) + 1]);
+  const char* tags[64];
+  double ms[64], fl[64];
+  int cnt[64], nt = 0;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]);
+    int k = 0;
+    for (; k < nt; ++k) if (tags[k] == ctx->prof_tag[i] || !strcmp(tags[k], ctx->prof_tag[i])) break;
+    if (k == nt) { if (nt == 64) continue; tags[nt] = ctx->prof_tag[i]; ms[nt] = 0; fl[nt] = 0; cnt[nt] = 0; ++nt; }
+    ms[k] += t; fl[k] += ctx->prof_fl[i]; cnt[k]++;
+  }
+  int64_t off = 0;
+  for (int k = 0; k < nt && off < size - 96; ++k)
+    off += snprintf(buf + off, size - off, "%s %d %.3f %.2f\n", tags[k], cnt[k], ms[k], fl[k] / 1e9);
   return WGG_OK;
 }

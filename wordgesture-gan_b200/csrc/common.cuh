@@ -25,6 +25,8 @@ struct wgg_ctx {
   cudaEvent_t* prof_ev = nullptr;  // 2*kProfMax events, created lazily
   int prof_n = 0;
   double prof_flops = 0.0, prof_bytes = 0.0;
+  const char** prof_tag = nullptr;   // per event pair: static call-site tag
+  double* prof_fl = nullptr;         // per event pair: FLOPs
   char err[512] = {0};
 };
 
@@ -33,9 +35,12 @@ struct ProfScope {
   wgg_ctx* c;
   cudaStream_t st;
   int idx = -1;
-  ProfScope(wgg_ctx* ctx, const char* name, cudaStream_t s, double flops, double bytes) : c(ctx), st(s) {
+  ProfScope(wgg_ctx* ctx, const char* name, cudaStream_t s, double flops, double bytes, const char* tag = nullptr)
+      : c(ctx), st(s) {
     if (!c->prof_on || !strstr(name, c->prof_filter) || c->prof_n >= wgg_ctx::kProfMax) return;
     idx = c->prof_n++;
+    c->prof_tag[idx] = tag ? tag : name;
+    c->prof_fl[idx] = flops;
     c->prof_flops += flops;
     c->prof_bytes += bytes;
     cudaEventRecord(c->prof_ev[2 * idx], st);
@@ -118,6 +123,7 @@ struct GemmP {
   //           1 = always fp32 FMA (nn.Linear layers: the reference keeps cuBLAS matmuls in true fp32,
   //               only cuDNN LSTM / conv run TF32 - SURVEY.md 2.4 K1/K4/K7)
   int force_fp32 = 0;
+  const char* tag = nullptr;  // call-site label for the profiler
   int x3 = 0;  // tensor-core mode: error-compensated 3xTF32 (always on for conv windows)
 };
 
@@ -206,3 +212,18 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
                          int64_t B, float* out, float* ws, int64_t ws_floats, cudaStream_t st);
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05 conv1d layers of the TemporalDiscriminator (conv_tc.cu)
+// ----------------------------------------------------------------------------------------------
+int conv_tc_fwd_launch(wgg_ctx* ctx, const float* in, const float* wimg, const float* bias, float* out,
+                       const float* act_lower, const float* dfeat, int64_t B, int CinC, int taps, int pad, int N,
+                       int mode, const char* tag, cudaStream_t st);
+int64_t conv_tc_wgrad_ws_floats(wgg_ctx* ctx, int ncols_max);
+int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int Cout, int Cin, int taps,
+                         int pad, float* G, float* db, float* ws, cudaStream_t st);
+int pack_x4_launch(wgg_ctx* ctx, const float* x, float* x4, int64_t B, int C, cudaStream_t st);
+int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B, int C, cudaStream_t st);
+int unpool_leaky_chunk_launch(wgg_ctx* ctx, const float* dpool, const float* a3, const float* dfeat, float* dpre,
+                              int64_t B, int C, cudaStream_t st);
+int chunk_to_rows_launch(wgg_ctx* ctx, const float* in, float* out, int64_t B, int C, cudaStream_t st);

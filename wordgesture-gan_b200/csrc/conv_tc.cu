@@ -1,0 +1,502 @@
+// Conv1d layers of the TemporalDiscriminator on tcgen05 tensor cores: one sample = one 128-row MMA tile.
+//
+// Replaces the cuDNN conv1d forward / backward-data / backward-weight calls behind
+// TemporalDiscriminator.forward / get_all_features (src/gan/models.py:270-277,309-311,335-339) in "tf32" mode.
+// The sequence length T = 128 equals the UMMA M dimension, so a conv over one gesture is a single accumulator
+// tile D[t, co]:
+//     D[t, co] = sum_{tap, ci} act[t + tap - pad, ci] * W[co, ci, tap]
+// Activations of one sample are stored channel-chunked: [C/4 chunks][T rows][4 floats].  In shared memory each
+// chunk carries 2 zero rows of padding in front (and spare rows behind), rows are 16 B apart, so the K-major A
+// operand of tap `j` is simply the same tile with its start address advanced by j*16 bytes - the sliding window
+// costs nothing and needs no boundary masking.  K per MMA is 8 = two 16-byte chunks: two channel chunks of one tap
+// (LBO = chunk stride) or, for the 3-channel input layer, two consecutive taps of the single chunk (LBO = 16 B).
+// The weight gradient uses the SAME tiles as MN-major operands (M = co from the d(pre-activation) tile, N = ci from
+// the shifted input tile, K = time), accumulating over all samples of a persistent CTA in TMEM; bias gradients fall
+// out of one extra N=8 MMA against a tile of ones.
+// Numerics: TF32 operands (round-to-nearest on write), fp32 accumulation - the numerics of the reference's own
+// CUDA path (cuDNN TF32 convs; measured deviation from fp64 in profiles/r01_ref_cuda_precision.json).
+#include "tc_common.cuh"
+
+using namespace tcu;
+
+namespace ctc {
+
+constexpr int T = 128;
+constexpr int ROWS_S = 136;            // rows per chunk in shared memory: 2 pad + 128 + 6 spare (max tap shift 5)
+constexpr int CS = ROWS_S * 16;        // chunk stride in shared memory (bytes)
+constexpr int PAD_ROWS = 2;
+constexpr int CHUNK_G = T * 16;        // chunk size in HBM (bytes): 128 rows x 16 B
+constexpr int NTHREADS = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 epilogue (TMEM quarter = warp % 4)
+
+struct FwdArgs {
+  const float* in;        // [B][CinC][T][4]
+  const float* wimg;      // [Kchunks][N/8][8][4] (TF32)
+  const float* bias;      // [N] or null
+  float* out;             // mode 0/1: [B][N/4][T][4]; mode 2: (B,T,3) row-major
+  const float* act_lower; // mode 1: activation of the layer below (same layout as out) for LeakyReLU backward
+  const float* dfeat;     // mode 1: optional feature-matching gradient w.r.t. that activation (same layout)
+  int64_t B;
+  int CinC, taps, taps_p, tap_row0, N, mode;
+  int* gerr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward-type conv: mode 0 = conv + bias + LeakyReLU; mode 1 = backward-data fused with LeakyReLU backward
+// (produces d(pre-activation) of the layer below); mode 2 = backward-data into the (B,T,3) input gradient.
+// persistent: grid = min(B, #SM); each CTA loops over samples with a 2-deep input ring.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Kchunks = a.CinC == 1 ? a.taps_p : a.taps * a.CinC;
+  const int WCS = (a.N / 8) * 128;  // weight image chunk stride
+  uint8_t* s_w = smem;
+  uint8_t* s_in = s_w + ((Kchunks * WCS + 1023) / 1024) * 1024;
+  const int in_bytes = a.CinC * CS;
+  float* s_bias = reinterpret_cast<float*>(s_in + 2 * in_bytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
+  const uint32_t BAR_ACC_FULL = bar0 + 8u * 4, BAR_ACC_EMPTY = bar0 + 8u * 5;
+
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.wimg);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < Kchunks * WCS / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+    float4* zin = reinterpret_cast<float4*>(s_in);
+    for (int i = tid; i < 2 * in_bytes / 16; i += NTHREADS) zin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 64; i += NTHREADS) s_bias[i] = (a.bias && i < a.N) ? __ldg(a.bias + i) : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+    mbar_init(BAR_ACC_FULL, 1);
+    mbar_init(BAR_ACC_EMPTY, 4);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t idesc = make_idesc(128, a.N);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 11)) break;
+        mbar_expect_tx(BAR_FULL(st), a.CinC * CHUNK_G);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) + b * (int64_t)a.CinC * CHUNK_G;
+        for (int q = 0; q < a.CinC; ++q)
+          bulk_g2s(smem_u32(s_in + st * in_bytes + q * CS + PAD_ROWS * 16), src + (int64_t)q * CHUNK_G, CHUNK_G, BAR_FULL(st));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int n = 0;
+      const uint32_t wb = smem_u32(s_w);
+      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 12)) break;
+        if (!mbar_wait(BAR_ACC_EMPTY, (n & 1) ^ 1, s_abort, a.gerr, 13)) break;
+        tc_fence_after();
+        const uint32_t ab = smem_u32(s_in + st * in_bytes);
+        uint32_t first = 0;
+        if (a.CinC == 1) {
+          for (int jp = 0; jp < a.taps_p / 2; ++jp) {
+            const uint64_t ad = make_desc(ab + (a.tap_row0 + 2 * jp) * 16, 16, 128);
+            const uint64_t bd = make_desc(wb + (2 * jp) * WCS, WCS, 128);
+            mma_tf32_ss(tmem_base, ad, bd, idesc, first);
+            first = 1;
+          }
+        } else {
+          for (int j = 0; j < a.taps; ++j)
+            for (int p = 0; p < a.CinC / 2; ++p) {
+              const uint64_t ad = make_desc(ab + (2 * p) * CS + (a.tap_row0 + j) * 16, CS, 128);
+              const uint64_t bd = make_desc(wb + (j * a.CinC + 2 * p) * WCS, WCS, 128);
+              mma_tf32_ss(tmem_base, ad, bd, idesc, first);
+              first = 1;
+            }
+        }
+        mma_commit(BAR_EMPTY(st));
+        mma_commit(BAR_ACC_FULL);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int t = quarter * 32 + lane;
+    int n = 0;
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      if (!mbar_wait(BAR_ACC_FULL, n & 1, s_abort, a.gerr, 14)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float v[64];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 16 < a.N) {  // warp-uniform
+          float r[16];
+          tmem_ld16(taddr + cc * 16, r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[cc * 16 + i] = r[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_ACC_EMPTY);
+      if (a.mode == 2) {
+        float* o = a.out + (b * T + t) * 3;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+      } else {
+        float4* o4 = reinterpret_cast<float4*>(a.out) + (b * (a.N / 4)) * T + t;
+        const float4* y4 = a.mode == 1 ? reinterpret_cast<const float4*>(a.act_lower) + (b * (a.N / 4)) * T + t : nullptr;
+        const float4* f4 = (a.mode == 1 && a.dfeat) ? reinterpret_cast<const float4*>(a.dfeat) + (b * (a.N / 4)) * T + t : nullptr;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (q >= a.N / 4) break;
+          float x[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
+          if (a.mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = leaky_f(x[i] + s_bias[4 * q + i]);
+          } else {
+            const float4 y = __ldg(y4 + (int64_t)q * T);
+            if (f4) {
+              const float4 f = __ldg(f4 + (int64_t)q * T);
+              x[0] += f.x; x[1] += f.y; x[2] += f.z; x[3] += f.w;
+            }
+            x[0] = y.x > 0.f ? x[0] : kLeak * x[0];
+            x[1] = y.y > 0.f ? x[1] : kLeak * x[1];
+            x[2] = y.z > 0.f ? x[2] : kLeak * x[2];
+            x[3] = y.w > 0.f ? x[3] : kLeak * x[3];
+          }
+          o4[(int64_t)q * T] = make_float4(rna_tf32(x[0]), rna_tf32(x[1]), rna_tf32(x[2]), rna_tf32(x[3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient: G[co][(tap, ci)] = sum_{b, t} dpre[b][t][co] * in[b][t + tap - pad][ci];  db[co] = sum dpre.
+// A = dpre tile (MN-major, M = 64 output channels; missing channels are zero chunks), B = shifted input tile
+// (MN-major, N = ci) per tap, K = time (16 steps of 8).  Accumulates over the CTA's samples in TMEM; each CTA
+// writes one partial [64][ncols] block, reduced by wgrad_finalize_kernel.
+// ---------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* dpre;  // [B][CoutC][T][4]
+  const float* in;    // [B][CinC][T][4]
+  float* partial;     // [grid][64][ncols]
+  int64_t B;
+  int CoutC, CinC, taps, taps_p, tap_row0, ncols;
+  int* gerr;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int dp_bytes = 16 * CS, in_bytes = a.CinC * CS;
+  uint8_t* s_dp = smem;                      // 2 stages x 16 chunks
+  uint8_t* s_in = s_dp + 2 * dp_bytes;       // 2 stages x CinC chunks
+  uint8_t* s_one = s_in + 2 * in_bytes;      // 2 chunks of ones
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + 2 * CS);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
+  const uint32_t BAR_DONE = bar0 + 8u * 4;
+  {
+    float4* z = reinterpret_cast<float4*>(smem);
+    const int nz = (2 * dp_bytes + 2 * in_bytes) / 16;
+    for (int i = tid; i < nz; i += NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* o = reinterpret_cast<float4*>(s_one);
+    for (int i = tid; i < 2 * CS / 16; i += NTHREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+    mbar_init(BAR_DONE, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int Ntap = a.CinC * 4;
+  const int Ktot = a.CinC == 1 ? a.taps_p * 4 : a.taps * Ntap;
+  int nsamples = 0;
+  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) ++nsamples;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 21)) break;
+        mbar_expect_tx(BAR_FULL(st), (a.CoutC + a.CinC) * CHUNK_G);
+        const uint8_t* sd = reinterpret_cast<const uint8_t*>(a.dpre) + b * (int64_t)a.CoutC * CHUNK_G;
+        for (int q = 0; q < a.CoutC; ++q)
+          bulk_g2s(smem_u32(s_dp + st * dp_bytes + q * CS + PAD_ROWS * 16), sd + (int64_t)q * CHUNK_G, CHUNK_G, BAR_FULL(st));
+        const uint8_t* si = reinterpret_cast<const uint8_t*>(a.in) + b * (int64_t)a.CinC * CHUNK_G;
+        for (int q = 0; q < a.CinC; ++q)
+          bulk_g2s(smem_u32(s_in + st * in_bytes + q * CS + PAD_ROWS * 16), si + (int64_t)q * CHUNK_G, CHUNK_G, BAR_FULL(st));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int n = 0;
+      bool ok = true;
+      const uint32_t one = smem_u32(s_one);
+      const uint32_t id_tap = make_idesc(64, a.CinC == 1 ? a.taps_p * 4 : Ntap, 1, 1);
+      const uint32_t id_one = make_idesc(64, 8, 1, 1);
+      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 22)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t dp = smem_u32(s_dp + st * dp_bytes) + PAD_ROWS * 16;
+        const uint32_t in = smem_u32(s_in + st * in_bytes);
+        for (int ks = 0; ks < T / 8; ++ks) {
+          const uint32_t acc = (n | ks) ? 1u : 0u;
+          const uint64_t ad = make_desc(dp + ks * 128, 128, CS);
+          if (a.CinC == 1) {
+            const uint64_t bd = make_desc(in + a.tap_row0 * 16 + ks * 128, 128, 16);
+            mma_tf32_ss(tmem_base, ad, bd, id_tap, acc);
+          } else {
+            for (int j = 0; j < a.taps; ++j) {
+              const uint64_t bd = make_desc(in + (a.tap_row0 + j) * 16 + ks * 128, 128, CS);
+              mma_tf32_ss(tmem_base + (uint32_t)(j * Ntap), ad, bd, id_tap, acc);
+            }
+          }
+          const uint64_t od = make_desc(one + ks * 128, 128, CS);
+          mma_tf32_ss(tmem_base + (uint32_t)Ktot, ad, od, id_one, acc);
+        }
+        mma_commit(BAR_EMPTY(st));
+      }
+      if (ok) mma_commit(BAR_DONE);
+    }
+  } else {
+    // M = 64 accumulators occupy lanes 0..15 of every 32-lane TMEM quarter: row = 16 * quarter + lane
+    if (nsamples > 0 && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 23)) {
+      tc_fence_after();
+      const int quarter = warp & 3;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float* dst = a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
+      for (int c0 = 0; c0 < a.ncols; c0 += 16) {
+        float r[16];
+        tmem_ld16(taddr + c0, r);
+        if (lane < 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < a.ncols) dst[c0 + i] = r[i];
+        }
+      }
+    } else if (nsamples == 0) {
+      const int quarter = warp & 3;
+      if (lane < 16) {
+        float* dst = a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
+        for (int c = 0; c < a.ncols; ++c) dst[c] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// G[co][(tap,ci)] = sum_cta partial[cta][co][tap*Cin4 + ci];  db[co] += sum_cta partial[cta][co][Ktot]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int nparts, int ncols, int Cout, int Cin,
+                                      int Cin4, int taps, int Ktot, float* __restrict__ G, float* __restrict__ db) {
+  const int n = Cout * taps * Cin + Cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    int co, col;
+    const bool isb = idx >= Cout * taps * Cin;
+    if (isb) { co = idx - Cout * taps * Cin; col = Ktot; }
+    else { co = idx / (taps * Cin); const int r = idx % (taps * Cin); col = (r / Cin) * Cin4 + (r % Cin); }
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[((int64_t)p * 64 + co) * ncols + col];
+    if (isb) db[co] += s;
+    else G[idx] = s;
+  }
+}
+
+// x (B,T,3) -> [B][1 chunk][T][4] (channel 3 = 0), TF32-rounded
+__global__ void pack_x4_kernel(const float* __restrict__ x, float* __restrict__ x4, int64_t n_rows, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = rna_tf32(__ldg(x + i * C));
+    if (C > 1) v.y = rna_tf32(__ldg(x + i * C + 1));
+    if (C > 2) v.z = rna_tf32(__ldg(x + i * C + 2));
+    reinterpret_cast<float4*>(x4)[i] = v;
+  }
+}
+
+// pooled[b][c*8+bin] = mean_{t in bin} a[b][c/4][t][c%4]     (AdaptiveAvgPool1d(8), models.py:312-315)
+__global__ void pool_fwd_chunk_kernel(const float* __restrict__ a, float* __restrict__ pooled, int64_t B, int C) {
+  const int64_t n = B * C * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int bin = (int)((i / C) % 8);
+    const int64_t b = i / ((int64_t)C * 8);
+    const float* p = a + ((b * (C / 4) + c / 4) * T + bin * 16) * 4 + (c & 3);
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) s += __ldg(p + t * 4);
+    pooled[b * C * 8 + c * 8 + bin] = s * (1.f / 16.f);
+  }
+}
+
+// dpre3[b][c/4][t][c%4] = LeakyReLU'(a3) * (dpool[b][c*8 + t/16] / 16 + dfeat)     (un-pool + LeakyReLU backward)
+__global__ void unpool_leaky_chunk_kernel(const float* __restrict__ dpool, const float* __restrict__ a3,
+                                          const float* __restrict__ dfeat, float* __restrict__ dpre, int64_t B, int C) {
+  const int64_t n = B * C * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 3);
+    const int t = (int)((i >> 2) % T);
+    const int q = (int)((i / (4 * T)) % (C / 4));
+    const int64_t b = i / ((int64_t)C * T);
+    const int c = q * 4 + c4;
+    float g = __ldg(dpool + b * C * 8 + c * 8 + (t >> 4)) * (1.f / 16.f);
+    if (dfeat) g += __ldg(dfeat + i);
+    dpre[i] = rna_tf32(__ldg(a3 + i) > 0.f ? g : kLeak * g);
+  }
+}
+
+// [B][Cc][T][4] (channel-chunked) -> (B, T, Cc*4) row-major, both sides coalesced through shared memory.
+// block = (b, 32 consecutive t); 256 threads
+__global__ void __launch_bounds__(256) chunk_to_rows_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                            int Cc) {
+  __shared__ float4 tile[32][17];
+  const int64_t b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < Cc * 32; i += 256) {
+    const int q = i / 32, tt = i % 32;
+    tile[tt][q] = __ldg(in + (b * Cc + q) * T + t0 + tt);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cc * 32; i += 256) {
+    const int tt = i / Cc, q = i % Cc;
+    out[(b * T + t0 + tt) * Cc + q] = tile[tt][q];
+  }
+}
+
+}  // namespace ctc
+
+// ---------------------------------------------------------------------------------------------
+// host launchers (used by disc.cu)
+// ---------------------------------------------------------------------------------------------
+int conv_tc_grid(wgg_ctx* ctx, int64_t B) { return (int)(B < ctx->sm_count ? B : ctx->sm_count); }
+
+int conv_tc_fwd_launch(wgg_ctx* ctx, const float* in, const float* wimg, const float* bias, float* out,
+                       const float* act_lower, const float* dfeat, int64_t B, int CinC, int taps, int pad, int N,
+                       int mode, const char* tag, cudaStream_t st) {
+  ctc::FwdArgs a;
+  a.in = in; a.wimg = wimg; a.bias = bias; a.out = out; a.act_lower = act_lower; a.dfeat = dfeat; a.B = B;
+  a.CinC = CinC; a.taps = taps; a.taps_p = (CinC == 1) ? taps + (taps & 1) : taps;
+  a.tap_row0 = ctc::PAD_ROWS - pad; a.N = N; a.mode = mode; a.gerr = ctx->async_err;
+  const int Kchunks = CinC == 1 ? a.taps_p : taps * CinC;
+  const int WCS = (N / 8) * 128;
+  const size_t smem = (size_t)((Kchunks * WCS + 1023) / 1024) * 1024 + 2 * (size_t)CinC * ctc::CS + 64 * 4 + 8 * 8 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(ctc::conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return wgg_fail(ctx, WGG_ECUDA, "conv_tc_fwd_kernel: cannot reserve shared memory%s");
+    configured = smem;
+  }
+  const double flops = 2.0 * (double)B * ctc::T * N * (double)(taps * CinC * 4);
+  ProfScope prof(ctx, "conv_tc_fwd_kernel", st, flops, (double)B * ctc::T * 4.0 * (CinC * 4 + N), tag);
+  ctc::conv_tc_fwd_kernel<<<conv_tc_grid(ctx, B), ctc::NTHREADS, smem, st>>>(a);
+  WGG_CHECK_LAUNCH(ctx, "conv_tc_fwd_kernel");
+  return WGG_OK;
+}
+
+int64_t conv_tc_wgrad_ws_floats(wgg_ctx* ctx, int ncols_max) { return (int64_t)ctx->sm_count * 64 * ncols_max; }
+
+// G (Cout x taps*Cin, forward layout) is overwritten; db (Cout) is accumulated.
+int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int Cout, int Cin, int taps,
+                         int pad, float* G, float* db, float* ws, cudaStream_t st) {
+  const int CoutC = Cout / 4, CinC = (Cin + 3) / 4;
+  ctc::WgradArgs a;
+  a.dpre = dpre; a.in = in; a.partial = ws; a.B = B; a.CoutC = CoutC; a.CinC = CinC; a.taps = taps;
+  a.taps_p = (CinC == 1) ? taps + (taps & 1) : taps;
+  a.tap_row0 = ctc::PAD_ROWS - pad;
+  const int Ktot = CinC == 1 ? a.taps_p * 4 : taps * CinC * 4;
+  a.ncols = Ktot + 8;
+  a.gerr = ctx->async_err;
+  const size_t smem = (size_t)2 * 16 * ctc::CS + 2 * (size_t)CinC * ctc::CS + 2 * ctc::CS + 8 * 8 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(ctc::conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad_kernel: cannot reserve shared memory%s");
+    configured = smem;
+  }
+  const int grid = conv_tc_grid(ctx, B);
+  {
+    ProfScope prof(ctx, "conv_tc_wgrad_kernel", st, 2.0 * (double)B * ctc::T * Cout * (double)(taps * Cin),
+                   (double)B * ctc::T * 4.0 * (Cout + CinC * 4), "conv_tc_wgrad_kernel");
+    ctc::conv_tc_wgrad_kernel<<<grid, ctc::NTHREADS, smem, st>>>(a);
+    WGG_CHECK_LAUNCH(ctx, "conv_tc_wgrad_kernel");
+  }
+  ctc::wgrad_finalize_kernel<<<32, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, CinC * 4, taps, Ktot, G, db);
+  WGG_CHECK_LAUNCH(ctx, "wgrad_finalize_kernel");
+  return WGG_OK;
+}
+
+int pack_x4_launch(wgg_ctx* ctx, const float* x, float* x4, int64_t B, int C, cudaStream_t st) {
+  ctc::pack_x4_kernel<<<ew_blocks(B * ctc::T), 256, 0, st>>>(x, x4, B * ctc::T, C);
+  WGG_CHECK_LAUNCH(ctx, "pack_x4_kernel");
+  return WGG_OK;
+}
+
+int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B, int C, cudaStream_t st) {
+  ctc::pool_fwd_chunk_kernel<<<ew_blocks(B * C * 8), 256, 0, st>>>(a, pooled, B, C);
+  WGG_CHECK_LAUNCH(ctx, "pool_fwd_chunk_kernel");
+  return WGG_OK;
+}
+
+int unpool_leaky_chunk_launch(wgg_ctx* ctx, const float* dpool, const float* a3, const float* dfeat, float* dpre,
+                              int64_t B, int C, cudaStream_t st) {
+  ctc::unpool_leaky_chunk_kernel<<<ew_blocks(B * C * ctc::T), 256, 0, st>>>(dpool, a3, dfeat, dpre, B, C);
+  WGG_CHECK_LAUNCH(ctx, "unpool_leaky_chunk_kernel");
+  return WGG_OK;
+}
+
+// ---- debug / test hooks (exported): run one tcgen05 conv kernel on caller-provided chunk-layout tensors ----
+extern "C" __attribute__((visibility("default"))) int wgg_debug_conv_tc_wgrad(wgg_ctx* ctx, const float* dpre,
+                                                                              const float* in, int64_t B, int Cout,
+                                                                              int Cin, int taps, int pad, float* G,
+                                                                              float* db, float* ws, void* stream) {
+  if (!ctx) return WGG_EINVAL;
+  return conv_tc_wgrad_launch(ctx, dpre, in, B, Cout, Cin, taps, pad, G, db, ws, (cudaStream_t)stream);
+}
+extern "C" __attribute__((visibility("default"))) int wgg_debug_conv_tc_fwd(wgg_ctx* ctx, const float* in,
+                                                                            const float* wimg, const float* bias,
+                                                                            float* out, int64_t B, int CinC, int taps,
+                                                                            int pad, int N, int mode, void* stream) {
+  if (!ctx) return WGG_EINVAL;
+  return conv_tc_fwd_launch(ctx, in, wimg, bias, out, nullptr, nullptr, B, CinC, taps, pad, N, mode, "debug",
+                            (cudaStream_t)stream);
+}
+
+int chunk_to_rows_launch(wgg_ctx* ctx, const float* in, float* out, int64_t B, int C, cudaStream_t st) {
+  if (C % 4 != 0 || C / 4 > 16 || B > 65535) return wgg_fail(ctx, WGG_EINVAL, "chunk_to_rows: unsupported shape%s");
+  dim3 grid(ctc::T / 32, (unsigned)B);
+  ctc::chunk_to_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), C / 4);
+  WGG_CHECK_LAUNCH(ctx, "chunk_to_rows_kernel");
+  return WGG_OK;
+}

@@ -21,6 +21,8 @@ struct DLayer {
   int64_t off_b, off_w;  // into flat params
   int64_t off_u, off_v;  // into flat uv
   int64_t sn_wf, sn_wb, sn_u, sn_v, sn_sigma;  // into sn
+  int64_t sn_tcf, sn_tcd;                      // tcgen05 weight images (conv layers): forward / backward-data
+  int tc_kf, tc_nd;                            // forward image K chunks; backward-data image N (>= 16)
   int64_t g_off;         // into the effective-weight-gradient scratch
   int in_width, out_width;  // per-sample activation widths
   int64_t in_off, out_off;  // per-sample offsets into stash (in_off < 0: network input x)
@@ -33,6 +35,7 @@ struct DLayout {
   int64_t param_total, uv_total, sn_total, g_total;
   int64_t stash_width;      // per sample
   int64_t pooled_off;       // per-sample offset of pooled block (temporal only)
+  int64_t x4_off;           // per-sample offset of the channel-padded input copy (tcgen05 path)
   int first_linear;         // index of the first Linear after the pool (temporal) or -1
   int nfeat;
   int64_t feat_off[kMaxLayers];
@@ -82,6 +85,16 @@ int disc_layout(const wgg_model_cfg* c, DLayout* d) {
     l.sn_u = so; so += l.rows;
     l.sn_v = so; so += l.cols;
     l.sn_sigma = so; so += 4;         // keep 16-byte alignment of the following blocks
+    so = (so + 3) & ~(int64_t)3;
+    l.sn_tcf = l.sn_tcd = so; l.tc_kf = 0; l.tc_nd = 0;
+    if (l.is_conv) {
+      const int CinC = (l.Cin + 3) / 4;
+      const int taps_p = CinC == 1 ? l.ks + (l.ks & 1) : l.ks;
+      l.tc_kf = CinC == 1 ? taps_p : l.ks * CinC;
+      l.tc_nd = CinC * 4 < 16 ? 16 : CinC * 4;
+      l.sn_tcf = so; so += (int64_t)l.tc_kf * 4 * l.rows;
+      l.sn_tcd = so; so += (int64_t)l.ks * l.rows * l.tc_nd;
+    }
     l.g_off = go; go += wn;
     if (wn > d->max_wn) d->max_wn = wn;
     if (l.rows > d->max_rows) d->max_rows = l.rows;
@@ -103,6 +116,7 @@ int disc_layout(const wgg_model_cfg* c, DLayout* d) {
       l.out_off = -1;
     }
   }
+  d->x4_off = sw; sw += (int64_t)d->T * 4;
   d->nfeat = nf;
   d->param_total = po; d->uv_total = uo; d->sn_total = so; d->g_total = go; d->stash_width = sw;
   return WGG_OK;
@@ -117,6 +131,8 @@ struct SnArgs {
   int64_t off_w[kMaxLayers], off_u[kMaxLayers], off_v[kMaxLayers];
   int64_t sn_wf[kMaxLayers], sn_wb[kMaxLayers], sn_u[kMaxLayers], sn_v[kMaxLayers], sn_sigma[kMaxLayers];
   int64_t g_off[kMaxLayers];
+  int64_t sn_tcf[kMaxLayers], sn_tcd[kMaxLayers];
+  int tc_kf[kMaxLayers], tc_nd[kMaxLayers];
 };
 
 __global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restrict__ params, float* __restrict__ uv,
@@ -183,6 +199,28 @@ __global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restri
       const float w = W[idx] / sigma;
       wf[r * cols + k * Cin + ci] = w;                       // [co][(k,ci)]   forward / weight-grad layout
       wb[((ks - 1 - k) * rows + r) * Cin + ci] = w;          // [(k',co)][ci]  backward-data layout (flipped taps)
+    }
+    // tcgen05 images (TF32, UMMA K-major core-matrix order [K/4][N/8][8][4]); see conv_tc.cu
+    const int CinC = (Cin + 3) / 4, Cin4 = CinC * 4;
+    const int kf = a.tc_kf[l] * 4;                      // forward K (tap-major, channels padded to Cin4)
+    float* tf = sn + a.sn_tcf[l];
+    for (int idx = tid; idx < rows * kf; idx += 256) {
+      const int co = idx / kf, kk = idx % kf;
+      const int tap = kk / Cin4, ci = kk % Cin4;
+      const float w = (tap < ks && ci < Cin) ? W[(co * Cin + ci) * ks + tap] / sigma : 0.f;
+      uint32_t t32;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t32) : "f"(w));
+      tf[(kk >> 2) * (rows / 8) * 32 + (co >> 3) * 32 + (co & 7) * 4 + (kk & 3)] = __uint_as_float(t32);
+    }
+    const int nd = a.tc_nd[l], kd = ks * rows;          // backward-data: N = input channels, K = (flipped tap, co)
+    float* td = sn + a.sn_tcd[l];
+    for (int idx = tid; idx < nd * kd; idx += 256) {
+      const int ci = idx / kd, kk = idx % kd;
+      const int tp = kk / rows, co = kk % rows;
+      const float w = ci < Cin ? W[(co * Cin + ci) * ks + (ks - 1 - tp)] / sigma : 0.f;
+      uint32_t t32;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t32) : "f"(w));
+      td[(kk >> 2) * (nd / 8) * 32 + (ci >> 3) * 32 + (ci & 7) * 4 + (kk & 3)] = __uint_as_float(t32);
     }
   } else {
     for (int idx = tid; idx < n; idx += 256) wf[idx] = W[idx] / sigma;
@@ -269,6 +307,11 @@ __global__ void transpose_tc_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
+// tcgen05 conv path: TemporalDiscriminator with T == 128 (= UMMA M) and <= 4 input channels, in tf32 mode
+bool disc_use_tc(const wgg_ctx* ctx, const DLayout& d) {
+  return ctx->math_mode == 1 && d.temporal && d.T == 128 && d.C <= 4;
+}
+
 void fill_sn_args(const DLayout& d, SnArgs* a) {
   a->nl = d.nl;
   for (int i = 0; i < d.nl; ++i) {
@@ -277,6 +320,7 @@ void fill_sn_args(const DLayout& d, SnArgs* a) {
     a->off_w[i] = l.off_w; a->off_u[i] = l.off_u; a->off_v[i] = l.off_v;
     a->sn_wf[i] = l.sn_wf; a->sn_wb[i] = l.sn_wb; a->sn_u[i] = l.sn_u; a->sn_v[i] = l.sn_v;
     a->sn_sigma[i] = l.sn_sigma; a->g_off[i] = l.g_off;
+    a->sn_tcf[i] = l.sn_tcf; a->sn_tcd[i] = l.sn_tcd; a->tc_kf[i] = l.tc_kf; a->tc_nd[i] = l.tc_nd;
   }
 }
 
@@ -327,8 +371,11 @@ extern "C" int32_t wgg_disc_feature_width(const wgg_model_cfg* cfg, int32_t k) {
 extern "C" int64_t wgg_disc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
   DLayout d;
   if (disc_layout(cfg, &d) != WGG_OK) return -1;
-  return 2 * B * (int64_t)d.max_width + d.g_total + gemm_splitk_ws_floats(1, d.max_wn, 1) +
-         colsum_ws_floats(d.max_rows, 1);
+  int64_t part = gemm_splitk_ws_floats(1, d.max_wn, 1);
+  const int64_t tcp = (int64_t)256 * 64 * 336;  // tcgen05 wgrad partials: <= 256 CTAs x 64 rows x (5*64 + 8 -> 336) cols
+  if (d.temporal && tcp > part) part = tcp;
+  // 2 gradient ping-pong buffers (+ 2 row-major staging buffers for the tcgen05 path's weight gradients)
+  return (d.temporal ? 4 : 2) * B * (int64_t)d.max_width + d.g_total + part + colsum_ws_floats(d.max_rows, 1);
 }
 
 extern "C" int wgg_disc_spectral(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* uv, int training,
@@ -356,13 +403,29 @@ extern "C" int wgg_disc_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const fl
   if (B <= 0) return WGG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int last = d.nl - 1;
-  for (int i = 0; i < d.nl; ++i) {
+  const bool tc = disc_use_tc(ctx, d);
+  if (tc) {
+    // conv stack on tcgen05: activations channel-chunked [B][C/4][T][4] (see conv_tc.cu)
+    float* x4 = stash + d.x4_off * B;
+    WGG_TRY(pack_x4_launch(ctx, x, x4, B, d.C, st));
+    const float* in = x4;
+    for (int i = 0; i < d.first_linear; ++i) {
+      const DLayer& l = d.L[i];
+      float* out = stash + l.out_off * B;
+      WGG_TRY(conv_tc_fwd_launch(ctx, in, sn + l.sn_tcf, params + l.off_b, out, nullptr, nullptr, B, (l.Cin + 3) / 4, l.ks,
+                                 l.pad, l.rows, 0, "conv_tc_fwd_kernel/fwd", st));
+      in = out;
+    }
+    WGG_TRY(pool_fwd_chunk_launch(ctx, in, stash + d.pooled_off * B, B, d.L[d.first_linear - 1].rows, st));
+  }
+  for (int i = tc ? d.first_linear : 0; i < d.nl; ++i) {
     const DLayer& l = d.L[i];
     if (i == last && !score) break;
     const float* in = l.in_off < 0 ? x : stash + l.in_off * B;
     float* out = i == last ? score : stash + l.out_off * B;
     if (l.is_conv) {
       GemmP p;
+      p.tag = "gemm_kernel/conv_fwd";
       p.A = in - (int64_t)l.pad * l.Cin; p.M = B * d.T; p.K = l.cols; p.sam = l.Cin; p.sak = 1;
       p.conv_mode = 1; p.conv_T = d.T; p.conv_Cin = l.Cin; p.conv_pad = l.pad;
       p.B = sn + l.sn_wf; p.N = l.rows; p.sbk = 1; p.sbn = l.cols;
@@ -395,7 +458,9 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   cudaStream_t st = (cudaStream_t)stream;
   float* dcur = ws;
   float* dnext = dcur + B * (int64_t)d.max_width;
-  float* G = dnext + B * (int64_t)d.max_width;
+  float* rm_a = dnext + B * (int64_t)d.max_width;   // row-major staging (tcgen05 path only)
+  float* rm_b = d.temporal ? rm_a + B * (int64_t)d.max_width : rm_a;
+  float* G = d.temporal ? rm_b + B * (int64_t)d.max_width : rm_a;
   float* part = G + d.g_total;
   float* csws = part + gemm_splitk_ws_floats(1, d.max_wn, 1);
   const int last = d.nl - 1;
@@ -423,6 +488,7 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
       const int64_t R = B * d.T;
       if (dparams) {
         GemmP p;  // G[co][(k,ci)] = sum_r dpre[r][co] * window(in)(r,(k,ci))
+        p.tag = "gemm_kernel/conv_wgrad";
         p.A = dcur; p.M = l.rows; p.K = R; p.sam = 1; p.sak = l.rows;
         p.B = in - (int64_t)l.pad * l.Cin; p.N = l.cols; p.sbk = l.Cin; p.sbn = 1;
         p.conv_mode = 2; p.conv_T = d.T; p.conv_Cin = l.Cin; p.conv_pad = l.pad;
@@ -435,6 +501,7 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
         float* dst = (i == 0) ? dx : dnext;
         const int padb = l.ks - 1 - l.pad;
         GemmP p;  // d_in[r][ci] = sum_{k',co} window(dpre)(r,(k',co)) * Wb[(k',co)][ci]
+        p.tag = "gemm_kernel/conv_dgrad";
         p.A = dcur - (int64_t)padb * l.rows; p.M = R; p.K = (int64_t)l.ks * l.rows; p.sam = l.rows; p.sak = 1;
         p.conv_mode = 1; p.conv_T = d.T; p.conv_Cin = l.rows; p.conv_pad = padb;
         p.B = sn + l.sn_wb; p.N = l.Cin; p.sbk = l.Cin; p.sbn = 1;
@@ -449,6 +516,53 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
       if (need_dgrad) {
         float* dst = (i == 0) ? dx : dnext;
         WGG_TRY(wgg_linear_dgrad(ctx, dcur, l.rows, sn + l.sn_wf, dst, l.cols, B, l.rows, l.cols, 0, st));
+        if (d.temporal && i == d.first_linear && disc_use_tc(ctx, d)) {
+          // ---- conv stack backward on tcgen05 (conv_tc.cu): dnext holds d(pooled) ----
+          const float* x4 = stash + d.x4_off * B;
+          float* dp_hi = dcur;    // d(pre-activation) of the current conv layer, chunk layout
+          float* dp_lo = dnext;
+          {
+            const DLayer& c3 = d.L[i - 1];
+            // dnext (d pooled) is consumed into dcur (dpre of the last conv layer)
+            WGG_TRY(unpool_leaky_chunk_launch(ctx, dnext, stash + c3.out_off * B, dfeat ? dfeat + c3.out_off * B : nullptr,
+                                              dp_hi, B, c3.rows, st));
+          }
+          for (int j = i - 1; j >= 0; --j) {
+            const DLayer& c = d.L[j];
+            const float* cin = j == 0 ? x4 : stash + d.L[j - 1].out_off * B;
+            if (dparams) {
+              // weight gradient on the mma.sync engine (needs MN-major operands, which tcgen05 kind::tf32 does not
+              // take in the un-swizzled layout): stage dpre / input row-major, then the sliding-window TN GEMM
+              const int64_t R = B * d.T;
+              WGG_TRY(chunk_to_rows_launch(ctx, dp_hi, rm_a, B, c.rows, st));
+              const float* in_rm = x;
+              if (j > 0) {
+                WGG_TRY(chunk_to_rows_launch(ctx, cin, rm_b, B, c.Cin, st));
+                in_rm = rm_b;
+              }
+              GemmP p;
+              p.tag = "gemm_kernel/conv_wgrad";
+              p.A = rm_a; p.M = c.rows; p.K = R; p.sam = 1; p.sak = c.rows;
+              p.B = in_rm - (int64_t)c.pad * c.Cin; p.N = c.cols; p.sbk = c.Cin; p.sbn = 1;
+              p.conv_mode = 2; p.conv_T = d.T; p.conv_Cin = c.Cin; p.conv_pad = c.pad;
+              p.C = G + c.g_off; p.scm = c.cols; p.scn = 1;
+              p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 1); p.partial = part;
+              WGG_TRY(gemm_launch(ctx, p, st));
+              WGG_TRY(colsum_launch(ctx, rm_a, R, c.rows, c.rows, 1, 0, dparams + c.off_b, nullptr, 0, 1, csws, st));
+            }
+            if (j > 0) {
+              const DLayer& lo = d.L[j - 1];
+              WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dp_lo, stash + lo.out_off * B,
+                                         dfeat ? dfeat + lo.out_off * B : nullptr, B, c.rows / 4, c.ks, c.ks - 1 - c.pad,
+                                         c.tc_nd, 1, "conv_tc_fwd_kernel/dgrad", st));
+              float* t = dp_hi; dp_hi = dp_lo; dp_lo = t;
+            } else if (dx) {
+              WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dx, nullptr, nullptr, B, c.rows / 4, c.ks,
+                                         c.ks - 1 - c.pad, c.tc_nd, 2, "conv_tc_fwd_kernel/dx", st));
+            }
+          }
+          break;  // the conv layers are done
+        }
         if (d.temporal && i == d.first_linear) {
           // dnext holds d(pooled); un-pool into the conv activation gradient
           const DLayer& c = d.L[i - 1];
@@ -466,6 +580,36 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
     sn_grad_kernel<<<d.nl, 256, 0, st>>>(a, params, sn, G, dparams, dscore ? 1 : 0);
     WGG_CHECK_LAUNCH(ctx, "sn_grad_kernel");
   }
+  return WGG_OK;
+}
+
+namespace {
+// stash block of a conv feature <-> the public (B, C*T) layout of get_all_features (h.view(B,-1) of (B,C,T)).
+// chunked = 1: stash is [B][C/4][T][4] (tcgen05 path); 0: stash is (B,T,C) channel-last.
+__global__ void feature_convert_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t B, int T, int C,
+                                       int chunked, int to_stash) {
+  const int64_t n = B * (int64_t)T * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates the public layout: (b, c, t)
+    const int t = (int)(i % T);
+    const int c = (int)((i / T) % C);
+    const int64_t b = i / ((int64_t)T * C);
+    const int64_t s = chunked ? ((b * (C / 4) + c / 4) * T + t) * 4 + (c & 3) : (b * T + t) * C + c;
+    if (to_stash) out[s] = in[i];
+    else out[i] = in[s];
+  }
+}
+}  // namespace
+
+extern "C" int wgg_disc_feature_convert(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* in, float* out, int64_t B,
+                                        int32_t T, int32_t C, int to_stash, void* stream) {
+  DLayout d;
+  if (!ctx) return WGG_EINVAL;
+  if (disc_layout(cfg, &d) != WGG_OK) return wgg_fail(ctx, WGG_EINVAL, "disc: bad config%s");
+  if (B <= 0) return WGG_OK;
+  feature_convert_kernel<<<ew_blocks(B * T * C), 256, 0, (cudaStream_t)stream>>>(in, out, B, T, C,
+                                                                                 disc_use_tc(ctx, d) ? 1 : 0, to_stash);
+  WGG_CHECK_LAUNCH(ctx, "feature_convert_kernel");
   return WGG_OK;
 }
 

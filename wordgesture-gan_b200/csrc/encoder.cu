@@ -62,7 +62,7 @@ int linear_fwd(wgg_ctx* ctx, const float* A, int64_t lda, const float* W, const 
   p.A = A; p.M = M; p.K = K; p.sam = lda; p.sak = 1;
   p.B = W; p.N = N; p.sbk = 1; p.sbn = K;
   p.C = C; p.scm = ldc; p.scn = 1;
-  p.bias = bias; p.act = act; p.force_fp32 = 1;
+  p.bias = bias; p.act = act; p.force_fp32 = 1; p.tag = "gemm_kernel/linear_fwd";
   return gemm_launch(ctx, p, st);
 }
 
@@ -82,7 +82,7 @@ int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A,
   p.B = A; p.N = K; p.sbk = lda; p.sbn = 1;
   p.C = dW; p.scm = K; p.scn = 1; p.accumulate = accumulate;
   p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 1);
-  p.partial = part; p.force_fp32 = 1;
+  p.partial = part; p.force_fp32 = 1; p.tag = "gemm_kernel/linear_wgrad";
   return gemm_launch(ctx, p, st);
 }
 
@@ -92,7 +92,7 @@ int wgg_linear_dgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* W,
   GemmP p;
   p.A = dY; p.M = M; p.K = N; p.sam = ldy; p.sak = 1;
   p.B = W; p.N = K; p.sbk = K; p.sbn = 1;
-  p.C = dA; p.scm = lda; p.scn = 1; p.accumulate = accumulate; p.force_fp32 = 1;
+  p.C = dA; p.scm = lda; p.scn = 1; p.accumulate = accumulate; p.force_fp32 = 1; p.tag = "gemm_kernel/linear_dgrad";
   return gemm_launch(ctx, p, st);
 }
 

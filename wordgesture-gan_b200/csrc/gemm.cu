@@ -371,7 +371,7 @@ constexpr int kMaxSplit = 128;
 }  // namespace
 
 int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch) {
-  const bool tf32 = ctx->math_mode == 1;
+  const bool tf32 = ctx->math_mode >= 1;
   const int64_t tiles = cdiv64(M, tf32 ? TBM : BM) * cdiv64(N, tf32 ? TBN : BN) * nbatch;
   const int64_t ktiles = cdiv64(K, BK);
   int64_t want = cdiv64(2 * (int64_t)ctx->sm_count, tiles);
@@ -389,16 +389,18 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.M >= (1ll << 31) || p.K >= (1ll << 31)) return wgg_fail(ctx, WGG_EINVAL, "gemm: dimension too large%s");
   if (p.splitk > 1 && (!p.partial || p.act != ACT_NONE || p.bias || p.bias2))
     return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K needs a partial buffer and a plain epilogue%s");
-  const bool tf32 = ctx->math_mode == 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
+  const bool tf32 = ctx->math_mode >= 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
   const int bm = tf32 ? TBM : BM, bn = tf32 ? TBN : BN;
   dim3 grid((unsigned)cdiv64(p.M, bm), (unsigned)cdiv64(p.N, bn), (unsigned)(p.nbatch * p.splitk));
   if (grid.y > 65535 || grid.z > 65535) return wgg_fail(ctx, WGG_EINVAL, "gemm: grid too large%s");
   ProfScope prof(ctx, "gemm_kernel", st, 2.0 * (double)p.M * (double)p.N * (double)p.K * p.nbatch,
-                 4.0 * ((double)p.M * p.K + (double)p.K * p.N + (double)p.M * p.N) * p.nbatch);
+                 4.0 * ((double)p.M * p.K + (double)p.K * p.N + (double)p.M * p.N) * p.nbatch, p.tag);
   if (tf32) {
-    const bool x3 = p.conv_mode != 0 || p.x3;
-    if (p.conv_mode == 1) gemm_mma_kernel<1, 1><<<grid, 256, 0, st>>>(p);
-    else if (p.conv_mode == 2) gemm_mma_kernel<2, 1><<<grid, 256, 0, st>>>(p);
+    const bool x3 = ctx->math_mode == 2 && (p.conv_mode != 0 || p.x3);  // compensated convs only in tf32x3 mode
+    if (p.conv_mode == 1 && x3) gemm_mma_kernel<1, 1><<<grid, 256, 0, st>>>(p);
+    else if (p.conv_mode == 1) gemm_mma_kernel<1, 0><<<grid, 256, 0, st>>>(p);
+    else if (p.conv_mode == 2 && x3) gemm_mma_kernel<2, 1><<<grid, 256, 0, st>>>(p);
+    else if (p.conv_mode == 2) gemm_mma_kernel<2, 0><<<grid, 256, 0, st>>>(p);
     else if (x3) gemm_mma_kernel<0, 1><<<grid, 256, 0, st>>>(p);
     else gemm_mma_kernel<0, 0><<<grid, 256, 0, st>>>(p);
   } else if (p.conv_mode == 1) gemm_kernel<1><<<grid, 256, 0, st>>>(p);

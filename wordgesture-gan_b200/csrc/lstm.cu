@@ -394,7 +394,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   if (B <= 0) return WGG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t TB = (int64_t)g.T * B;
-  if (!stash && ctx->math_mode == 1 && generator_tc_supported(cfg)) {
+  if (!stash && ctx->math_mode >= 1 && generator_tc_supported(cfg)) {
     // no-grad calls (sampling, and the 10 critic-loop generations per batch) run on the tcgen05 path
     return generator_forward_tc(ctx, cfg, params, g.layer_off, g.dir_stride, g.off_whh, g.off_bih, g.off_bhh, g.off_wo,
                                 g.off_bo, proto, z, B, out, ws, ws_floats, st);
@@ -423,6 +423,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     float* cseq = stash ? sv.cseq[l] : nullptr;
     hout = stash ? sv.hseq[l] : hbuf[l & 1];
     GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
+    p.tag = "gemm_kernel/lstm_xproj";
     p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
     p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
     p.C = gates; p.scm = 4 * g.H; p.scn = 1;
@@ -433,6 +434,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     in = hout;
   }
   GemmP p;  // out[b][t][:] = tanh(h[t][b][:] * Wo^T + bo), batched over t to transpose (t,b)->(b,t)
+  p.tag = "gemm_kernel/head_fwd";
   p.A = hout; p.M = B; p.K = 2 * g.H; p.sam = 2 * g.H; p.sak = 1;
   p.B = params + g.off_wo; p.N = g.C; p.sbk = 1; p.sbn = 2 * g.H;
   p.C = out; p.scm = (int64_t)g.T * g.C; p.scn = 1;
@@ -467,6 +469,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   const float* hL = sv.hseq[g.L - 1];
   {
     GemmP p;  // dWo (C x 2H) += dpre^T * hL
+    p.tag = "gemm_kernel/head_wgrad";
     p.A = dpre; p.M = g.C; p.K = TB; p.sam = 1; p.sak = g.C;
     p.B = hL; p.N = 2 * H; p.sbk = 2 * H; p.sbn = 1;
     p.C = dparams + g.off_wo; p.scm = 2 * H; p.scn = 1; p.accumulate = 1; p.force_fp32 = 1;
@@ -474,6 +477,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     WGG_TRY(gemm_launch(ctx, p, st));
     WGG_TRY(colsum_launch(ctx, dpre, TB, g.C, g.C, 1, 0, dparams + g.off_bo, nullptr, 0, 1, csws, st));
     GemmP q;  // dh (TB x 2H) = dpre * Wo
+    q.tag = "gemm_kernel/head_dgrad";
     q.A = dpre; q.M = TB; q.K = g.C; q.sam = g.C; q.sak = 1;
     q.B = params + g.off_wo; q.N = 2 * H; q.sbk = 2 * H; q.sbn = 1;
     q.C = dh; q.scm = 2 * H; q.scn = 1; q.force_fp32 = 1;
@@ -488,6 +492,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, g.T, B, st));
     {
       GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
+      p.tag = "gemm_kernel/lstm_dWih";
       p.A = da; p.M = H4; p.K = TB; p.sam = 1; p.sak = H4;
       p.B = in; p.N = I; p.sbk = I; p.sbn = 1;
       p.C = dlp; p.scm = I; p.scn = 1; p.accumulate = 1;
@@ -497,6 +502,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     }
     if (g.T > 1) {
       GemmP p;  // dW_hh[d] (4H x H) += da[d][t]^T * h[d][t_prev]; time shift = pointer offset
+      p.tag = "gemm_kernel/lstm_dWhh";
       p.A = da + B * H4; p.M = H4; p.K = (int64_t)(g.T - 1) * B; p.sam = 1; p.sak = H4;
       p.B = sv.hseq[l]; p.N = H; p.sbk = 2 * H; p.sbn = 1;
       p.C = dlp + g.off_whh[l]; p.scm = H; p.scn = 1; p.accumulate = 1;
@@ -510,6 +516,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     if (l > 0 || dz) {
       for (int d = 0; d < 2; ++d) {
         GemmP p;  // dx (TB x I) (+)= da[d] * W_ih[d]
+        p.tag = "gemm_kernel/lstm_dx";
         p.A = da + (int64_t)d * TB * H4; p.M = TB; p.K = H4; p.sam = H4; p.sak = 1;
         p.B = lp + d * g.dir_stride[l]; p.N = I; p.sbk = I; p.sbn = 1;
         p.C = dx; p.scm = I; p.scn = 1; p.accumulate = d;

@@ -20,7 +20,7 @@
 // Layer activations live in HBM in exactly this layout per 128-row tile and timestep, so a timestep's tile is
 // ONE contiguous block: it is fetched with plain bulk copies (no tensor map) and written by the epilogue with
 // fully coalesced 16-byte stores (lane = row).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tc {
 
@@ -37,104 +37,10 @@ constexpr int NTHREADS = 320;                  // warp 0 producer, warp 1 MMA, w
 constexpr int ACC_COLS = N4;                   // TMEM columns per accumulator buffer
 constexpr int TMEM_COLS = 512;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: returns false if the kernel is being aborted (a peer timed out) or this wait timed out
-// (~2 s), in which case *abort_flag and the global error word are set.  A wedged pipeline therefore ends
-// the kernel instead of hanging the GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* gerr, int code) {
-  if (mbar_try(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (true) {
-#pragma unroll 1
-    for (int i = 0; i < 64; ++i)
-      if (mbar_try(bar, parity)) return true;
-    if (*abort_flag) return false;
-    if (clock64() - t0 > 4000000000ll) {
-      *abort_flag = 1;
-      atomicCAS(gerr, 0, code);
-      return false;
-    }
-  }
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-// K-major, no swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
+using namespace tcu;
 
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=192, M=128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N4 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // element (row, k) of a tc-layout tile with `rows` rows: float index
 __host__ __device__ __forceinline__ int64_t tc_index(int rows, int row, int k) {
@@ -301,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           for (int j = 0; j < chunks / 2; ++j) {
             const uint64_t ad = make_desc(xa + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
             const uint64_t bd = make_desc(wx + (sb * SB_CHUNKS + 2 * j) * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
-            mma_tf32_ss(tacc, ad, bd, (sb | j) ? 1u : 0u);
+            mma_tf32_ss(tacc, ad, bd, kIdesc, (sb | j) ? 1u : 0u);
           }
           mma_commit(BAR_EMPTY(stage));  // frees the ring stage once these MMAs have read it
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -314,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           for (int j = 0; j < KH_CHUNKS / 2; ++j) {
             const uint64_t ad = make_desc(hs + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
             const uint64_t bd = make_desc(wh + j * 2 * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
-            mma_tf32_ss(tacc, ad, bd, 1u);
+            mma_tf32_ss(tacc, ad, bd, kIdesc, 1u);
           }
         }
         mma_commit(BAR_ACC_FULL(b));

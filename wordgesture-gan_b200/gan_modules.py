@@ -389,6 +389,7 @@ class _DiscFn(torch.autograd.Function):
                                         _lib.ptr(stash), st), c)
         ctx.module = module
         ctx.with_score = with_score
+        ctx.math_mode = _lib.get_math_mode()
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, sn, stash)
         if with_score:
@@ -407,10 +408,12 @@ class _DiscFn(torch.autograd.Function):
         B = x.shape[0]
         if not ctx.with_score:
             dscore = None
+        if ctx.math_mode != _lib.get_math_mode():
+            raise _lib.WggError("math mode changed between a discriminator forward and its backward")
         n_in = len(ctx.needs_input_grad)
         if dscore is None and dstash is None:
             return (None,) * n_in
-        want_params = any(ctx.needs_input_grad[3:])
+        want_params = any(ctx.needs_input_grad[3:]) and not _lib.SKIP_DISC_WEIGHT_GRADS
         dflat = torch.zeros_like(flat) if want_params else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
         nws = lib.wgg_disc_workspace_floats(cfg, B)
@@ -428,29 +431,32 @@ class _FeatureViewFn(torch.autograd.Function):
     channel-major as ``h.view(B, -1)`` of a (B, C, T) tensor (models.py:339)."""
 
     @staticmethod
-    def forward(ctx, stash, off, B, T, C, conv):
-        ctx.meta = (off, B, T, C, conv, stash.numel())
+    def forward(ctx, stash, config, off, B, T, C, conv):
+        ctx.meta = (config, off, B, T, C, conv, stash.numel(), _lib.get_math_mode())
         block = stash[off:off + B * T * C]
         if not conv:
             return block.view(B, T * C).clone()
         out = torch.empty(B, C * T, dtype=torch.float32, device=stash.device)
         c = _lib.ctx(stash.device)
-        _lib.check(_lib.lib().wgg_transpose_tc(c, _lib.ptr(block), _lib.ptr(out), B, T, C, _lib.stream(stash.device)), c)
+        _lib.check(_lib.lib().wgg_disc_feature_convert(c, _lib.c_cfg(config), _lib.ptr(block), _lib.ptr(out), B, T, C, 0,
+                                                       _lib.stream(stash.device)), c)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        off, B, T, C, conv, n = ctx.meta
+        config, off, B, T, C, conv, n, mode = ctx.meta
+        if mode != _lib.get_math_mode():
+            raise _lib.WggError("math mode changed between a discriminator forward and its backward")
         dst = torch.zeros(n, dtype=torch.float32, device=g.device)
         g = g.contiguous()
         if not conv:
             dst[off:off + B * T * C].copy_(g.reshape(-1))
         else:
             c = _lib.ctx(g.device)
-            # (B, C, T) -> (B, T, C): same kernel with the roles of T and C swapped
-            _lib.check(_lib.lib().wgg_transpose_tc(c, _lib.ptr(g), _lib.ptr(dst[off:off + B * T * C]), B, C, T,
-                                                   _lib.stream(g.device)), c)
-        return dst, None, None, None, None, None
+            _lib.check(_lib.lib().wgg_disc_feature_convert(c, _lib.c_cfg(config), _lib.ptr(g),
+                                                           _lib.ptr(dst[off:off + B * T * C]), B, T, C, 1,
+                                                           _lib.stream(g.device)), c)
+        return dst, None, None, None, None, None, None
 
 
 class _DiscBase(FlatModule):
@@ -490,9 +496,9 @@ class _DiscBase(FlatModule):
             width = lib.wgg_disc_feature_width(cfg, k)
             C = self._conv_feature_channels(k)
             if C:
-                feats.append(_FeatureViewFn.apply(stash, off, B, width // C, C, True))
+                feats.append(_FeatureViewFn.apply(stash, self.config, off, B, width // C, C, True))
             else:
-                feats.append(_FeatureViewFn.apply(stash, off, B, 1, width, False))
+                feats.append(_FeatureViewFn.apply(stash, self.config, off, B, 1, width, False))
         return feats
 
 

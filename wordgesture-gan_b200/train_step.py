@@ -14,6 +14,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _lib
 from .gan_losses import WassersteinLoss
 
 
@@ -73,7 +74,13 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
     trainer.optimizer_E.zero_grad()
     _, loss1, d1 = trainer.cycle1_tensors(prototype, real_gesture, z=draw(), eps_recover=draw())
     _, loss2, d2 = trainer.cycle2_tensors(prototype, real_gesture, eps=draw())
-    (loss1 + loss2).backward()
+    # the discriminators' own weight gradients of this backward are never used (the reference zeroes them before
+    # the next critic step, utils.py:75,96): skip computing them, keep d(loss)/d(fake gesture)
+    _lib.SKIP_DISC_WEIGHT_GRADS = True
+    try:
+        (loss1 + loss2).backward()
+    finally:
+        _lib.SKIP_DISC_WEIGHT_GRADS = False
     if on_step is not None:
         on_step("G_grads", trainer.optimizer_G)
         on_step("E_grads", trainer.optimizer_E)
