@@ -19,7 +19,8 @@ def run(dpre, x, Cout, Cin, taps, pad):
     B = dpre.shape[0]
     G = torch.full((Cout, taps * Cin), -7.0, device=dev); db = torch.zeros(Cout, device=dev)
     ws = torch.full((256 * 64 * 336,), -3.0, device=dev)
-    rc = lib.wgg_debug_conv_tc_wgrad(c, chunk(dpre).data_ptr(), chunk(x).data_ptr(), B, Cout, Cin, taps, pad, G.data_ptr(), db.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    dpc, xc = chunk(dpre), chunk(x)  # keep the temporaries alive: the kernel reads them asynchronously
+    rc = lib.wgg_debug_conv_tc_wgrad(c, dpc.data_ptr(), xc.data_ptr(), B, Cout, Cin, taps, pad, G.data_ptr(), db.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     print("rc", rc, "async_err", _lib.async_error(dev))
     return G, db, ws

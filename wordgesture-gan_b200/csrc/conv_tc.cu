@@ -15,6 +15,8 @@
 // out of one extra N=8 MMA against a tile of ones.
 // Numerics: TF32 operands (round-to-nearest on write), fp32 accumulation - the numerics of the reference's own
 // CUDA path (cuDNN TF32 convs; measured deviation from fp64 in profiles/r01_ref_cuda_precision.json).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 using namespace tcu;
@@ -189,26 +191,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient: G[co][(tap, ci)] = sum_{b, t} dpre[b][t][co] * in[b][t + tap - pad][ci];  db[co] = sum dpre.
-// A = dpre tile (MN-major, M = 64 output channels; missing channels are zero chunks), B = shifted input tile
-// (MN-major, N = ci) per tap, K = time (16 steps of 8).  Accumulates over the CTA's samples in TMEM; each CTA
-// writes one partial [64][ncols] block, reduced by wgrad_finalize_kernel.
+// Both operands are MN-major (M = co, N = ci, K = time).  For TF32 the only MN-major shared-memory layout the
+// tensor core accepts is SWIZZLE_128B_BASE32B (verified on hardware, scripts/probe/umma_probe2.cu): a tile of
+// [32-channel blocks][time rows][128 B] whose four 32-byte pieces of a row are XOR-ed with (row & 3) on ABSOLUTE
+// address bits - so a start address advanced by whole rows still addresses a valid operand, which is how the tap
+// shift of the sliding window is expressed.  Producer warps fill the tiles from the channel-chunked HBM layout
+// with 16-byte cp.async copies (swizzle applied by the writer); the 3-channel input layer gets an explicit
+// [t][tap][4] im2col tile instead.  Accumulators stay in TMEM over all samples of the persistent CTA (M = 64:
+// rows sit in lanes 0..15 of each 32-lane quarter); the bias gradient is one extra N = 8 MMA against ones.
 // ---------------------------------------------------------------------------------------------
 struct WgradArgs {
   const float* dpre;  // [B][CoutC][T][4]
   const float* in;    // [B][CinC][T][4]
   float* partial;     // [grid][64][ncols]
   int64_t B;
-  int CoutC, CinC, taps, taps_p, tap_row0, ncols;
+  int CoutC, CinC, taps, pad, ncols;
+  int dbg_mask;  // debug bisect: bit0 skip tap MMAs, bit1 skip ones MMA, bit2 only k-step 5, bit3 only tap 2
+  int dump_all;  // debug: write all 128 TMEM lanes ([grid][128][ncols]) instead of the 64 accumulator rows
   int* gerr;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgradArgs a) {
+constexpr int W_ROWS = 136;                 // 2 zero rows + 128 + spare
+constexpr int W_BLK = W_ROWS * 128;         // bytes per 32-channel block (17408 = 17 * 1024)
+constexpr int W_THREADS = 160;              // warp 0: MMA issuer; warps 1..4: tile producers, then TMEM read-out
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  // MN-major SWIZZLE_128B_BASE32B: LBO = stride between 32-element MN blocks, SBO = 512 B between 4-row K atoms
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((W_BLK >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// byte offset inside a W tile of the 16-byte group (row r, channel chunk q)   [chunk = 4 channels]
+__device__ __forceinline__ uint32_t w_off(int r, int q) {
+  return (uint32_t)((q >> 3) * W_BLK + r * 128 + ((((q & 7) >> 1) ^ (r & 3)) << 5) + ((q & 1) << 4));
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int dp_bytes = 16 * CS, in_bytes = a.CinC * CS;
-  uint8_t* s_dp = smem;                      // 2 stages x 16 chunks
-  uint8_t* s_in = s_dp + 2 * dp_bytes;       // 2 stages x CinC chunks
-  uint8_t* s_one = s_in + 2 * in_bytes;      // 2 chunks of ones
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + 2 * CS);
+  uint8_t* s_dp = smem;                       // 2 stages x 2 blocks
+  uint8_t* s_in = s_dp + 2 * 2 * W_BLK;       // 2 stages x 2 blocks
+  uint8_t* s_one = s_in + 2 * 2 * W_BLK;      // 1 block of ones
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + W_BLK);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -218,13 +250,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgradArgs a)
   const uint32_t BAR_DONE = bar0 + 8u * 4;
   {
     float4* z = reinterpret_cast<float4*>(smem);
-    const int nz = (2 * dp_bytes + 2 * in_bytes) / 16;
-    for (int i = tid; i < nz; i += NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 8 * W_BLK / 16; i += W_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* o = reinterpret_cast<float4*>(s_one);
-    for (int i = tid; i < 2 * CS / 16; i += NTHREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = tid; i < W_BLK / 16; i += W_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 128); mbar_init(BAR_EMPTY(s), 1); }
     mbar_init(BAR_DONE, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,79 +266,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_wgrad_kernel(WgradArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int Ntap = a.CinC * 4;
-  const int Ktot = a.CinC == 1 ? a.taps_p * 4 : a.taps * Ntap;
-  int nsamples = 0;
-  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) ++nsamples;
+  const bool im2col = a.CinC == 1;
+  const int Ntap = im2col ? 32 : 64;                  // N of one B group
+  const int ngroups = im2col ? 1 : a.taps;
+  const int Ktot = ngroups * Ntap;
 
   if (warp == 0) {
     if (lane == 0) {
       int n = 0;
-      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-        const int st = n & 1;
-        if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 21)) break;
-        mbar_expect_tx(BAR_FULL(st), (a.CoutC + a.CinC) * CHUNK_G);
-        const uint8_t* sd = reinterpret_cast<const uint8_t*>(a.dpre) + b * (int64_t)a.CoutC * CHUNK_G;
-        for (int q = 0; q < a.CoutC; ++q)
-          bulk_g2s(smem_u32(s_dp + st * dp_bytes + q * CS + PAD_ROWS * 16), sd + (int64_t)q * CHUNK_G, CHUNK_G, BAR_FULL(st));
-        const uint8_t* si = reinterpret_cast<const uint8_t*>(a.in) + b * (int64_t)a.CinC * CHUNK_G;
-        for (int q = 0; q < a.CinC; ++q)
-          bulk_g2s(smem_u32(s_in + st * in_bytes + q * CS + PAD_ROWS * 16), si + (int64_t)q * CHUNK_G, CHUNK_G, BAR_FULL(st));
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int n = 0;
       bool ok = true;
       const uint32_t one = smem_u32(s_one);
-      const uint32_t id_tap = make_idesc(64, a.CinC == 1 ? a.taps_p * 4 : Ntap, 1, 1);
+      const uint32_t id_tap = make_idesc(64, Ntap, 1, 1);
       const uint32_t id_one = make_idesc(64, 8, 1, 1);
       for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
         const int st = n & 1;
         if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 22)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t dp = smem_u32(s_dp + st * dp_bytes) + PAD_ROWS * 16;
-        const uint32_t in = smem_u32(s_in + st * in_bytes);
+        const uint32_t dp = smem_u32(s_dp + st * 2 * W_BLK);
+        const uint32_t in = smem_u32(s_in + st * 2 * W_BLK);
         for (int ks = 0; ks < T / 8; ++ks) {
-          const uint32_t acc = (n | ks) ? 1u : 0u;
-          const uint64_t ad = make_desc(dp + ks * 128, 128, CS);
-          if (a.CinC == 1) {
-            const uint64_t bd = make_desc(in + a.tap_row0 * 16 + ks * 128, 128, 16);
-            mma_tf32_ss(tmem_base, ad, bd, id_tap, acc);
-          } else {
-            for (int j = 0; j < a.taps; ++j) {
-              const uint64_t bd = make_desc(in + (a.tap_row0 + j) * 16 + ks * 128, 128, CS);
-              mma_tf32_ss(tmem_base + (uint32_t)(j * Ntap), ad, bd, id_tap, acc);
+          uint32_t acc = (n | ks) ? 1u : 0u;
+          if (a.dbg_mask & 4) { if (ks != 5) continue; acc = 0u; }
+          const uint64_t ad = make_desc_mn(dp + (PAD_ROWS + 8 * ks) * 128);
+          if (!(a.dbg_mask & 1)) {
+            if (im2col) {
+              mma_tf32_ss(tmem_base, ad, make_desc_mn(in + (PAD_ROWS + 8 * ks) * 128), id_tap, acc);
+            } else {
+              for (int j = 0; j < a.taps; ++j) {
+                if ((a.dbg_mask & 8) && j != 2) continue;
+                mma_tf32_ss(tmem_base + (uint32_t)(j * Ntap), ad, make_desc_mn(in + (PAD_ROWS + j - a.pad + 8 * ks) * 128),
+                            id_tap, acc);
+              }
             }
           }
-          const uint64_t od = make_desc(one + ks * 128, 128, CS);
-          mma_tf32_ss(tmem_base + (uint32_t)Ktot, ad, od, id_one, acc);
+          if (!(a.dbg_mask & 2)) mma_tf32_ss(tmem_base + (uint32_t)Ktot, ad, make_desc_mn(one + 8 * ks * 128), id_one, acc);
         }
         mma_commit(BAR_EMPTY(st));
       }
       if (ok) mma_commit(BAR_DONE);
     }
   } else {
-    // M = 64 accumulators occupy lanes 0..15 of every 32-lane TMEM quarter: row = 16 * quarter + lane
-    if (nsamples > 0 && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 23)) {
+    // ---- producers: fill both operand tiles of a stage with swizzled 16-byte cp.async copies ----
+    const int ptid = tid - 32;  // 0..127
+    int n = 0;
+    bool ok = true;
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      const int st = n & 1;
+      if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 21)) { ok = false; break; }
+      const uint32_t dp = smem_u32(s_dp + st * 2 * W_BLK);
+      const uint32_t in = smem_u32(s_in + st * 2 * W_BLK);
+      const float4* sd = reinterpret_cast<const float4*>(a.dpre) + b * (int64_t)a.CoutC * T;
+      for (int i = ptid; i < a.CoutC * T; i += 128) {
+        const int q = i / T, t = i % T;
+        cp_async16(dp + w_off(t + PAD_ROWS, q), sd + i);
+      }
+      const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)a.CinC * T;
+      if (im2col) {
+        // row t of the tile = [x4[t-pad], x4[t-pad+1], ..., x4[t-pad+taps-1], 0...]: chunk index = tap
+        for (int i = ptid; i < a.taps * T; i += 128) {
+          const int j = i / T, t = i % T;
+          const int ts = t + j - a.pad;
+          if (ts >= 0 && ts < T) cp_async16(in + w_off(t + PAD_ROWS, j), si + ts);
+        }
+      } else {
+        for (int i = ptid; i < a.CinC * T; i += 128) {
+          const int q = i / T, t = i % T;
+          cp_async16(in + w_off(t + PAD_ROWS, q), si + i);
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_async_smem();
+      mbar_arrive(BAR_FULL(st));
+    }
+    // ---- read-out: M = 64 accumulator rows live in lanes 0..15 of each TMEM quarter ----
+    if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 23)) {
       tc_fence_after();
       const int quarter = warp & 3;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      float* dst = a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
+      float* dst = a.dump_all ? a.partial + ((int64_t)blockIdx.x * 128 + quarter * 32 + lane) * a.ncols
+                              : a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
       for (int c0 = 0; c0 < a.ncols; c0 += 16) {
         float r[16];
         tmem_ld16(taddr + c0, r);
-        if (lane < 16) {
+        if (lane < 16 || a.dump_all) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (c0 + i < a.ncols) dst[c0 + i] = r[i];
         }
-      }
-    } else if (nsamples == 0) {
-      const int quarter = warp & 3;
-      if (lane < 16) {
-        float* dst = a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
-        for (int c = 0; c < a.ncols; ++c) dst[c] = 0.f;
       }
     }
   }
@@ -431,28 +476,31 @@ int64_t conv_tc_wgrad_ws_floats(wgg_ctx* ctx, int ncols_max) { return (int64_t)c
 int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int Cout, int Cin, int taps,
                          int pad, float* G, float* db, float* ws, cudaStream_t st) {
   const int CoutC = Cout / 4, CinC = (Cin + 3) / 4;
+  if (Cout > 64 || (CinC != 1 && CinC != 16) || taps > 8 || (CinC == 1 && taps > 8))
+    return wgg_fail(ctx, WGG_EUNSUPPORTED, "conv_tc_wgrad: unsupported layer shape%s");
   ctc::WgradArgs a;
-  a.dpre = dpre; a.in = in; a.partial = ws; a.B = B; a.CoutC = CoutC; a.CinC = CinC; a.taps = taps;
-  a.taps_p = (CinC == 1) ? taps + (taps & 1) : taps;
-  a.tap_row0 = ctc::PAD_ROWS - pad;
-  const int Ktot = CinC == 1 ? a.taps_p * 4 : taps * CinC * 4;
+  a.dpre = dpre; a.in = in; a.partial = ws; a.B = B; a.CoutC = CoutC; a.CinC = CinC; a.taps = taps; a.pad = pad;
+  const int Cin4 = CinC == 1 ? 4 : 64;
+  const int Ktot = CinC == 1 ? 32 : taps * 64;
   a.ncols = Ktot + 8;
+  a.dump_all = getenv("WGG_DEBUG_WGRAD_DUMP") ? 1 : 0;
+  a.dbg_mask = getenv("WGG_DEBUG_WGRAD_MASK") ? atoi(getenv("WGG_DEBUG_WGRAD_MASK")) : 0;
   a.gerr = ctx->async_err;
-  const size_t smem = (size_t)2 * 16 * ctc::CS + 2 * (size_t)CinC * ctc::CS + 2 * ctc::CS + 8 * 8 + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
+  const size_t smem = (size_t)9 * ctc::W_BLK + 8 * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
     if (cudaFuncSetAttribute(ctc::conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad_kernel: cannot reserve shared memory%s");
-    configured = smem;
+    configured = true;
   }
   const int grid = conv_tc_grid(ctx, B);
   {
     ProfScope prof(ctx, "conv_tc_wgrad_kernel", st, 2.0 * (double)B * ctc::T * Cout * (double)(taps * Cin),
                    (double)B * ctc::T * 4.0 * (Cout + CinC * 4), "conv_tc_wgrad_kernel");
-    ctc::conv_tc_wgrad_kernel<<<grid, ctc::NTHREADS, smem, st>>>(a);
+    ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);
     WGG_CHECK_LAUNCH(ctx, "conv_tc_wgrad_kernel");
   }
-  ctc::wgrad_finalize_kernel<<<32, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, CinC * 4, taps, Ktot, G, db);
+  ctc::wgrad_finalize_kernel<<<32, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);
   WGG_CHECK_LAUNCH(ctx, "wgrad_finalize_kernel");
   return WGG_OK;
 }

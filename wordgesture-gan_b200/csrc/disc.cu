@@ -530,26 +530,9 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
           for (int j = i - 1; j >= 0; --j) {
             const DLayer& c = d.L[j];
             const float* cin = j == 0 ? x4 : stash + d.L[j - 1].out_off * B;
-            if (dparams) {
-              // weight gradient on the mma.sync engine (needs MN-major operands, which tcgen05 kind::tf32 does not
-              // take in the un-swizzled layout): stage dpre / input row-major, then the sliding-window TN GEMM
-              const int64_t R = B * d.T;
-              WGG_TRY(chunk_to_rows_launch(ctx, dp_hi, rm_a, B, c.rows, st));
-              const float* in_rm = x;
-              if (j > 0) {
-                WGG_TRY(chunk_to_rows_launch(ctx, cin, rm_b, B, c.Cin, st));
-                in_rm = rm_b;
-              }
-              GemmP p;
-              p.tag = "gemm_kernel/conv_wgrad";
-              p.A = rm_a; p.M = c.rows; p.K = R; p.sam = 1; p.sak = c.rows;
-              p.B = in_rm - (int64_t)c.pad * c.Cin; p.N = c.cols; p.sbk = c.Cin; p.sbn = 1;
-              p.conv_mode = 2; p.conv_T = d.T; p.conv_Cin = c.Cin; p.conv_pad = c.pad;
-              p.C = G + c.g_off; p.scm = c.cols; p.scn = 1;
-              p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 1); p.partial = part;
-              WGG_TRY(gemm_launch(ctx, p, st));
-              WGG_TRY(colsum_launch(ctx, rm_a, R, c.rows, c.rows, 1, 0, dparams + c.off_b, nullptr, 0, 1, csws, st));
-            }
+            if (dparams)
+              WGG_TRY(conv_tc_wgrad_launch(ctx, dp_hi, cin, B, c.rows, c.Cin, c.ks, c.pad, G + c.g_off, dparams + c.off_b,
+                                           part, st));
             if (j > 0) {
               const DLayer& lo = d.L[j - 1];
               WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dp_lo, stash + lo.out_off * B,
