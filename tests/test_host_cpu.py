@@ -58,7 +58,8 @@ def test_flat_layout_sizes_agree_with_c(kw):
     else:
         assert widths == list(mc.disc_hidden_dims)
     assert lib.wgg_disc_stash_floats(cfg, B) >= B * sum(widths)
-    assert lib.wgg_generator_stash_floats(cfg, B) == mc.seq_length * B * (
+    # large enough for the FMA-path layout (x0 + per layer hseq/gates/c); the tcgen05 layout may need more
+    assert lib.wgg_generator_stash_floats(cfg, B) >= mc.seq_length * B * (
         (3 if mc.prototype_has_time else 2) + mc.latent_dim + 12 * mc.gen_hidden_dim * mc.gen_num_layers)
 
 

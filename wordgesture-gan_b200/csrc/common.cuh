@@ -211,7 +211,13 @@ int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
 int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
-                         int64_t B, float* out, float* ws, int64_t ws_floats, cudaStream_t st);
+                         int64_t B, float* out, float* ws, int64_t ws_floats, float* gc_stash, float* const* hseq_rm,
+                         cudaStream_t st);
+// grad-carrying variant: gc_stash = per-layer gate/cell stash (generator_tc_gc_layer_floats each), hseq_rm[l] = row-major
+// layer outputs [T][B][2H]
+int64_t generator_tc_gc_layer_floats(const wgg_model_cfg* cfg, int64_t B);
+int lstm_tc_bwd_layer(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* lp, int64_t dir_stride, int64_t off_whh,
+                      const float* gc, const float* dh_out, float* da_rm, float* wimg_ws, int64_t B, cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05 conv1d layers of the TemporalDiscriminator (conv_tc.cu)

@@ -104,11 +104,17 @@ __global__ void build_x0_tc_kernel(const float* __restrict__ proto, const float*
 // the persistent layer kernel.  grid (ntiles, 2 directions), 320 threads, 1 CTA / SM.
 // xin : [T][ntiles][KXC][16][8][4]   hout : [T][ntiles][24][16][8][4] (this direction fills chunks dir*12..+12)
 // ---------------------------------------------------------------------------------------------
-template <int KXC>
+// STASH = 1 (grad-carrying forward) additionally writes, per step, what BPTT needs:
+//   gc   : [2 dirs][T][ntiles][GC_CHUNKS][128 rows][4]  chunk u < 48 = (i,f,g,o) of hidden unit u, chunk 48 + u/4 = c
+//   h_rm : [T][B][2H] row-major, un-rounded fp32 (operand of the weight-gradient GEMMs and of the output head)
+constexpr int GC_CHUNKS = HID + HID / 4;  // 60
+
+template <int KXC, int STASH>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
                                                                   const float* __restrict__ wimg, int64_t img_stride,
                                                                   float* __restrict__ hout, int T, int ntiles,
-                                                                  int* __restrict__ gerr) {
+                                                                  float* __restrict__ gc, float* __restrict__ h_rm,
+                                                                  int64_t B, int* __restrict__ gerr) {
   constexpr int NSB = (KXC + SB_CHUNKS - 1) / SB_CHUNKS;
   constexpr int WX_BYTES = KXC * CHUNK_BYTES_W;
   constexpr int WH_BYTES = KH_CHUNKS * CHUNK_BYTES_W;
@@ -252,7 +258,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
         }
-        float hv[8];
+        float hv[8], hraw[8];
+        float4* gc4 = nullptr;
+        if (STASH)
+          gc4 = reinterpret_cast<float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
           const int ul = ch * 8 + uu;                 // unit index inside this thread's 24
@@ -262,7 +271,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           const float gg = tanh_fast(v[4 * uu + 2] + bb.z);
           const float og = sigmoid_fast(v[4 * uu + 3] + bb.w);
           c[ul] = fg * c[ul] + ig * gg;
-          hv[uu] = rna_tf32(og * tanh_fast(c[ul]));
+          hraw[uu] = og * tanh_fast(c[ul]);
+          hv[uu] = rna_tf32(hraw[uu]);
+          if (STASH) gc4[(int64_t)(half * 24 + ul) * TM] = make_float4(ig, fg, gg, og);
         }
 #pragma unroll
         for (int k2 = 0; k2 < 2; ++k2) {
@@ -270,6 +281,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           const float4 q = make_float4(hv[4 * k2], hv[4 * k2 + 1], hv[4 * k2 + 2], hv[4 * k2 + 3]);
           hs4[chunk * TM + row] = q;                  // next step's A operand
           hg4[(int64_t)chunk * TM] = q;               // next layer's input (coalesced: lane = row)
+          if (STASH) {
+            const int ul = ch * 8 + 4 * k2;
+            gc4[(int64_t)(HID + chunk) * TM] = make_float4(c[ul], c[ul + 1], c[ul + 2], c[ul + 3]);
+            const int64_t bidx = (int64_t)tile * TM + row;
+            if (bidx < B)
+              *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
+                  make_float4(hraw[4 * k2], hraw[4 * k2 + 1], hraw[4 * k2 + 2], hraw[4 * k2 + 3]);
+          }
         }
       }
       fence_async_smem();
@@ -282,6 +301,168 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BPTT on tensor cores.  One CTA = 128 samples of one direction, reverse scan over time.  Per step the epilogue
+// warps turn (gates, c, c_prev, dh) into d(pre-activation) `da` [128 x 192] (written to shared memory as the next
+// MMA's A operand and to HBM row-major for the weight-gradient / input-gradient GEMMs), and one elected thread
+// issues dh_rec = da * W_hh (M=128, N=48, K=192) whose accumulator the NEXT (earlier) step reads from TMEM.
+//   gc     : [2][T][ntiles][60][128][4]   (forward stash)         dh_out : [T][B][2H] row-major
+//   da_rm  : [2][T][B][4H] row-major, PyTorch gate order (i,f,g,o blocks of H)
+// ---------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 288;  // warp 0: MMA issuer; warps 1..8: epilogue (TMEM quarter = warp % 4)
+constexpr int WT_CHUNK_BYTES = (HID / 8) * 128;  // 768: one K chunk of the [48 x 192] W_hh^T image
+
+// B operand of dh_rec = da * W_hh:  img[u'][n'] = W_hh[(g*H + u)][u'] with n' = 4u + g   ([N=48][K=192], K-major)
+__global__ void prep_whhT_kernel(const float* __restrict__ lp, int64_t dir_stride, int64_t off_whh,
+                                 float* __restrict__ img) {
+  const int dir = blockIdx.y;
+  const float* w = lp + dir * dir_stride + off_whh;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < HID * N4; idx += gridDim.x * blockDim.x) {
+    const int up = idx / N4, kk = idx % N4;
+    const int u = kk >> 2, g = kk & 3;
+    img[dir * HID * N4 + tc_index(HID, up, kk)] = rna_tf32(w[(int64_t)(g * HID + u) * HID + up]);
+  }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float* __restrict__ gc,
+                                                                     const float* __restrict__ wimg,
+                                                                     const float* __restrict__ dh_out,
+                                                                     float* __restrict__ da_rm, int T, int ntiles,
+                                                                     int64_t B, int* __restrict__ gerr) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_da = smem;                                   // [48 chunks][128 rows][16 B]
+  uint8_t* s_w = s_da + HID * CHUNK_BYTES_A;              // [48 chunks][6 groups][128 B]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + HID * WT_CHUNK_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const uint32_t BAR_DA = smem_u32(s_bar), BAR_ACC = smem_u32(s_bar) + 8;
+  {
+    const float4* src = reinterpret_cast<const float4*>(wimg + dir * HID * N4);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < HID * N4 / 4; i += BWD_THREADS) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    mbar_init(BAR_DA, 8);
+    mbar_init(BAR_ACC, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TM, HID);
+      const uint32_t da = smem_u32(s_da), wb = smem_u32(s_w);
+      int n = 0;
+      for (int step = T - 1; step >= 1; --step, ++n) {
+        if (!mbar_wait(BAR_DA, (uint32_t)(n & 1), s_abort, gerr, 31)) break;
+        tc_fence_after();
+#pragma unroll 4
+        for (int j = 0; j < N4 / 8; ++j) {
+          const uint64_t ad = make_desc(da + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
+          const uint64_t bd = make_desc(wb + j * 2 * WT_CHUNK_BYTES, WT_CHUNK_BYTES, 128);
+          mma_tf32_ss(tmem_base, ad, bd, idesc, j ? 1u : 0u);
+        }
+        mma_commit(BAR_ACC);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 1) >> 2;
+    const int row = quarter * 32 + lane;
+    const int64_t bidx = (int64_t)tile * TM + row;
+    const bool valid = bidx < B;
+    float dc[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) dc[i] = 0.f;
+    float4* da4 = reinterpret_cast<float4*>(s_da);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 24);
+    int n = 0;
+    for (int step = T - 1; step >= 0; --step, ++n) {
+      const int t = dir ? T - 1 - step : step;
+      const int tp = dir ? t + 1 : t - 1;
+      const float4* g4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
+      const float4* gp4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + tp) * ntiles + tile) * GC_CHUNKS) * TM + row;
+      const float* dhp = dh_out + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + half * 24;
+      float* dap = da_rm + (((int64_t)dir * T + t) * B + bidx) * N4 + half * 24;
+      if (step < T - 1) {
+        if (!mbar_wait(BAR_ACC, (uint32_t)((n - 1) & 1), s_abort, gerr, 32)) break;
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float rec[8];
+        if (step < T - 1) tmem_ld8(taddr + ch * 8, rec);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rec[i] = 0.f;
+        }
+        float dho[8], cc[8], cp[8];
+        {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a0 = valid ? __ldg(reinterpret_cast<const float4*>(dhp + ch * 8)) : z4;
+          const float4 a1 = valid ? __ldg(reinterpret_cast<const float4*>(dhp + ch * 8 + 4)) : z4;
+          dho[0] = a0.x; dho[1] = a0.y; dho[2] = a0.z; dho[3] = a0.w; dho[4] = a1.x; dho[5] = a1.y; dho[6] = a1.z; dho[7] = a1.w;
+          const int cchunk = HID + half * 6 + ch * 2;
+          const float4 c0 = __ldg(g4 + (int64_t)cchunk * TM), c1 = __ldg(g4 + (int64_t)(cchunk + 1) * TM);
+          cc[0] = c0.x; cc[1] = c0.y; cc[2] = c0.z; cc[3] = c0.w; cc[4] = c1.x; cc[5] = c1.y; cc[6] = c1.z; cc[7] = c1.w;
+          if (step > 0) {
+            const float4 p0 = __ldg(gp4 + (int64_t)cchunk * TM), p1 = __ldg(gp4 + (int64_t)(cchunk + 1) * TM);
+            cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp[i] = 0.f;
+          }
+        }
+        float dai[8], daf[8], dag[8], dao[8];
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          const int ul = ch * 8 + uu;
+          const float4 gt = __ldg(g4 + (int64_t)(half * 24 + ul) * TM);  // (i, f, g, o)
+          const float tch = tanh_fast(cc[uu]);
+          const float dh = dho[uu] + rec[uu];
+          const float d_o = dh * tch;
+          const float dct = dc[ul] + dh * gt.w * (1.f - tch * tch);
+          dai[uu] = dct * gt.z * gt.x * (1.f - gt.x);
+          daf[uu] = dct * cp[uu] * gt.y * (1.f - gt.y);
+          dag[uu] = dct * gt.x * (1.f - gt.z * gt.z);
+          dao[uu] = d_o * gt.w * (1.f - gt.w);
+          dc[ul] = dct * gt.y;
+          da4[(half * 24 + ul) * TM + row] = make_float4(rna_tf32(dai[uu]), rna_tf32(daf[uu]), rna_tf32(dag[uu]), rna_tf32(dao[uu]));
+        }
+        if (valid) {
+          float4* o;
+          o = reinterpret_cast<float4*>(dap + 0 * HID + ch * 8);
+          o[0] = make_float4(dai[0], dai[1], dai[2], dai[3]); o[1] = make_float4(dai[4], dai[5], dai[6], dai[7]);
+          o = reinterpret_cast<float4*>(dap + 1 * HID + ch * 8);
+          o[0] = make_float4(daf[0], daf[1], daf[2], daf[3]); o[1] = make_float4(daf[4], daf[5], daf[6], daf[7]);
+          o = reinterpret_cast<float4*>(dap + 2 * HID + ch * 8);
+          o[0] = make_float4(dag[0], dag[1], dag[2], dag[3]); o[1] = make_float4(dag[4], dag[5], dag[6], dag[7]);
+          o = reinterpret_cast<float4*>(dap + 3 * HID + ch * 8);
+          o[0] = make_float4(dao[0], dao[1], dao[2], dao[3]); o[1] = make_float4(dao[4], dao[5], dao[6], dao[7]);
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_DA);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -360,14 +541,14 @@ bool tc_plan(const wgg_model_cfg* c, int64_t B, TcPlan* p) {
   return true;
 }
 
-template <int KXC>
+template <int KXC, int STASH>
 int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_stride, float* hout, int T, int ntiles,
-                 int64_t B, cudaStream_t st) {
+                 int64_t B, float* gc, float* h_rm, cudaStream_t st) {
   constexpr size_t smem = (size_t)KXC * tc::CHUNK_BYTES_W + tc::KH_CHUNKS * tc::CHUNK_BYTES_W + tc::NSTAGE * tc::SB_BYTES +
                           tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 16 * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc::lstm_tc_fwd_kernel<KXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc::lstm_tc_fwd_kernel<KXC, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_fwd_kernel: cannot reserve shared memory%s");
     configured = true;
   }
@@ -375,11 +556,40 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
   // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out
   ProfScope prof(ctx, "lstm_tc_fwd_kernel", st, 2.0 * T * (double)B * 2.0 * tc::N4 * (KXC * 4 + tc::HID),
                  (double)T * B * 4.0 * (2.0 * KXC * 4 + 96));
-  tc::lstm_tc_fwd_kernel<KXC><<<grid, tc::NTHREADS, smem, st>>>(xin, img, img_stride, hout, T, ntiles, ctx->async_err);
+  tc::lstm_tc_fwd_kernel<KXC, STASH><<<grid, tc::NTHREADS, smem, st>>>(xin, img, img_stride, hout, T, ntiles, gc, h_rm, B,
+                                                                         ctx->async_err);
   WGG_CHECK_LAUNCH(ctx, "lstm_tc_fwd_kernel");
   return WGG_OK;
 }
 }  // namespace
+
+int64_t generator_tc_gc_layer_floats(const wgg_model_cfg* cfg, int64_t B) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return 0;
+  return (int64_t)2 * p.T * p.rows * (tc::GC_CHUNKS * 4);
+}
+
+// BPTT of one layer (both directions) on the tcgen05 path: gc (forward stash) + dh_out -> da_rm
+int lstm_tc_bwd_layer(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* lp, int64_t dir_stride, int64_t off_whh,
+                      const float* gc, const float* dh_out, float* da_rm, float* wimg_ws, int64_t B, cudaStream_t st) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "lstm_tc_bwd_layer: unsupported configuration%s");
+  tc::prep_whhT_kernel<<<dim3(8, 2), 256, 0, st>>>(lp, dir_stride, off_whh, wimg_ws);
+  WGG_CHECK_LAUNCH(ctx, "prep_whhT_kernel");
+  constexpr size_t smem = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc::lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_bwd_kernel: cannot reserve shared memory%s");
+    configured = true;
+  }
+  dim3 grid((unsigned)p.ntiles, 2);
+  ProfScope prof(ctx, "lstm_tc_bwd_kernel", st, 2.0 * p.T * (double)B * 2.0 * tc::N4 * tc::HID,
+                 2.0 * p.T * (double)B * 4.0 * (tc::GC_CHUNKS * 4 + tc::HID + tc::HID + tc::N4));
+  tc::lstm_tc_bwd_kernel<<<grid, tc::BWD_THREADS, smem, st>>>(gc, wimg_ws, dh_out, da_rm, p.T, p.ntiles, B, ctx->async_err);
+  WGG_CHECK_LAUNCH(ctx, "lstm_tc_bwd_kernel");
+  return WGG_OK;
+}
 
 int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
   TcPlan p;
@@ -395,8 +605,10 @@ bool generator_tc_supported(const wgg_model_cfg* cfg) {
 int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
-                         int64_t B, float* out, float* ws, int64_t ws_floats, cudaStream_t st) {
+                         int64_t B, float* out, float* ws, int64_t ws_floats, float* gc_stash, float* const* hseq_rm,
+                         cudaStream_t st) {
   TcPlan p;
+  const int64_t gc_layer_floats = generator_tc_gc_layer_floats(cfg, B);
   if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_forward_tc: unsupported configuration%s");
   if (!ws || ws_floats < p.total) return wgg_fail(ctx, WGG_EWORKSPACE, "generator_forward_tc: workspace too small%s");
   float* x0 = ws;
@@ -413,10 +625,14 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
   const float* in = x0;
   for (int l = 0; l < p.L; ++l) {
     float* hout = hbuf[l & 1];
+    float* gcl = gc_stash ? gc_stash + (int64_t)l * gc_layer_floats : nullptr;
+    float* hrm = gc_stash ? hseq_rm[l] : nullptr;
     if (l == 0) {
-      WGG_TRY(launch_layer<kKX0 / 4>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, st));
+      if (gc_stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
+      else WGG_TRY((launch_layer<kKX0 / 4, 0>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     } else {
-      WGG_TRY(launch_layer<24>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, st));
+      if (gc_stash) WGG_TRY((launch_layer<24, 1>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
+      else WGG_TRY((launch_layer<24, 0>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     }
     in = hout;
   }

@@ -206,16 +206,15 @@ class _GeneratorFn(torch.autograd.Function):
         stash = None
         if need_grad:
             stash = torch.empty(lib.wgg_generator_stash_floats(cfg, B), dtype=torch.float32, device=dev)
-            ws, nws = None, 0
-        else:
-            nws = lib.wgg_generator_workspace_floats(cfg, B, 0)
-            ws = _lib.workspace(dev, nws)
+        nws = lib.wgg_generator_workspace_floats(cfg, B, 0)
+        ws = _lib.workspace(dev, nws)
         _lib.check(lib.wgg_generator_forward(c, cfg, _lib.ptr(flat), _lib.ptr(prototype), _lib.ptr(z), B,
                                              _lib.ptr(out), _lib.ptr(stash), _lib.ptr(ws),
                                              ws.numel() if ws is not None else 0, _lib.stream(dev)), c)
         ctx.module = module
         ctx.B = B
         ctx.stash = stash
+        ctx.math_mode = _lib.get_math_mode()
         ctx.save_for_backward(out)
         return out
 
@@ -230,6 +229,8 @@ class _GeneratorFn(torch.autograd.Function):
         flat = module.flat_params()
         if ctx.stash is None:
             raise _lib.WggError("generator backward called twice (the activation stash is consumed by backward)")
+        if ctx.math_mode != _lib.get_math_mode():
+            raise _lib.WggError("math mode changed between a generator forward and its backward")
         B = ctx.B
         dflat = torch.zeros_like(flat)
         dz = torch.empty(B, module.config.latent_dim, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
