@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"],
                     help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); fp32: FMA only")
     args = ap.parse_args()
@@ -187,13 +188,19 @@ def main():
     real_d, proto_d = real_h.to(dev), proto_h.to(dev)
     keys = ("d1_loss", "d2_loss", "cycle1_total", "cycle2_total")
 
-    def step_resident():
+    gs = None if args.no_graph else wgg.GraphedTrainStep(tr, B, 1.0)
+
+    def step_eager():
         return wgg.train_batch(tr, real_d, proto_d, 1.0)
 
+    def step_resident():
+        return gs(real_d, proto_d) if gs is not None else step_eager()
+
     def step_e2e():
-        r = real_h.to(dev, non_blocking=True)
-        p = proto_h.to(dev, non_blocking=True)
-        out = wgg.train_batch(tr, r, p, 1.0)
+        if gs is not None:
+            out = gs(real_h, proto_h)  # pinned host -> the graph's static device inputs, then one replay
+        else:
+            out = wgg.train_batch(tr, real_h.to(dev, non_blocking=True), proto_h.to(dev, non_blocking=True), 1.0)
         return torch.stack([out[k] for k in keys]).tolist()  # D2H read of the step's losses
 
     def sync():
@@ -223,9 +230,10 @@ def main():
     prof_kernel = args.profile_kernel
     shares = {}
     if prof_kernel == "auto":
-        for cand in ("gemm_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel"):
+        for cand in ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel", "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel",
+                     "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel"):
             _lib.profile_enable(dev, cand)
-            step_resident()
+            step_eager()
             shares[cand] = _lib.profile_read(dev)["ms"]
         prof_kernel = max(shares, key=shares.get)
     _lib.profile_enable(dev, None)
@@ -235,12 +243,12 @@ def main():
         sampler.start()
     l0 = _lib.launch_count(dev)
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count(dev) - l0
+    launches = (_lib.launch_count(dev) - l0) if gs is None else gs.launches_per_step * args.steps
     # second timed pass with event brackets around the dominant kernel class (kept separate so that the
     # brackets cannot perturb the headline number)
     _lib.profile_enable(dev, prof_kernel)
     prof_steps = min(args.steps, 4)
-    ms_prof = timed(step_resident, prof_steps)
+    ms_prof = timed(step_eager, prof_steps)  # brackets need eager launches (events cannot be recorded inside a replay)
     prof = _lib.profile_read(dev)
     _lib.profile_enable(dev, None)
     ms_e2e = timed(step_e2e, args.steps)
@@ -293,7 +301,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
                                "T=128), BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
+                   "parallelism": f"dp{world}", "launch": "eager" if gs is None else "cuda-graph (1 replay per step)", "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 128 * 3 * 4,
                 "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

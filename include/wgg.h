@@ -191,6 +191,12 @@ WGG_API int wgg_clip_adam(wgg_ctx* ctx, float* p, float* g, float* m, float* v, 
                   float beta2, float eps, int64_t step, float max_norm, float* grad_norm_out, float* ws,
                   void* stream);
 
+/* Same update with the step counter (int32, incremented by the call) and the learning rate held in DEVICE memory,
+ * so that nothing step-dependent is baked into the launch: this is the variant a captured CUDA graph replays. */
+WGG_API int wgg_clip_adam_dev(wgg_ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                      float beta1, float beta2, float eps, int* step_dev, float max_norm, float* grad_norm_out,
+                      float* ws, void* stream);
+
 /* ---- generic building block exposed for tests/bench: C[M,N] = act(A[M,K] * W[N,K]^T + bias) ---- */
 WGG_API int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
                int32_t K, int act /*0 none, 1 leaky(0.2), 2 tanh*/, void* stream);

@@ -1,0 +1,24 @@
+"""One warm-up + N timed training steps (for ncu launch lists and quick timing)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import wgg_b200 as wgg
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+mode = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+dev = torch.device("cuda:0")
+wgg.set_math_mode(mode)
+wgg.seed_everything(42)
+tr = wgg.WordGestureGANTrainer(wgg.ModelConfig(), wgg.TrainingConfig(), dev)
+for m in (tr.generator, tr.encoder, tr.discriminator_1, tr.discriminator_2): m.train()
+real = torch.rand(B, 128, 3, device=dev) * 2 - 1
+proto = torch.rand(B, 128, 3, device=dev) * 2 - 1
+wgg.train_batch(tr, real, proto, 1.0)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(nsteps): wgg.train_batch(tr, real, proto, 1.0)
+t_issue = time.perf_counter() - t0
+e1.record(); torch.cuda.synchronize()
+print(f"B={B} mode={mode}: {e0.elapsed_time(e1)/nsteps:.2f} ms/step device, CPU issue time {t_issue/nsteps*1e3:.2f} ms/step")

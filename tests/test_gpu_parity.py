@@ -491,3 +491,50 @@ def test_tcgen05_generator_forward(tf32_mode, B):
         y1 = G(to_t(proto[:1]), to_t(z[:1]))
     assert torch.equal(y, y2)
     assert torch.equal(y1[0], y[0])
+
+
+def test_cuda_graph_step_matches_eager():
+    """The captured whole-batch CUDA graph performs the same update as the eager step: identical RNG state in,
+    bit-identical parameters / Adam moments / spectral-norm buffers / losses out, over several replays; the host
+    step counters and an LR change made between replays are honoured."""
+    g = Golden("tiny_temporal")
+    real, proto, _ = g.inputs()
+    real_t, proto_t = to_t(real), to_t(proto)
+
+    def fresh():
+        tr = trainer_from_golden(g)
+        for m in (tr.generator, tr.encoder, tr.discriminator_1, tr.discriminator_2):
+            m.train()
+        return tr
+
+    tr_e, tr_g = fresh(), fresh()
+    gs = wgg.GraphedTrainStep(tr_g, real_t.shape[0], 1.0)
+    for m in MODS:  # construction (warm-up + capture) must leave training state untouched
+        assert torch.equal(getattr(tr_g, ATTR[m]).flat_params(), getattr(tr_e, ATTR[m]).flat_params())
+    for it in range(3):
+        if it == 2:
+            for tr in (tr_e, tr_g):
+                tr.optimizer_G.param_groups[0]["lr"] = 1e-4
+        torch.manual_seed(100 + it)
+        torch.cuda.manual_seed(100 + it)
+        out_e = wgg.train_batch(tr_e, real_t, proto_t, 1.0)
+        out_e = {k: v.clone() for k, v in out_e.items()}
+        torch.manual_seed(100 + it)
+        torch.cuda.manual_seed(100 + it)
+        out_g = gs(real_t, proto_t)
+        torch.cuda.synchronize()
+        for k in LOSS_KEYS:
+            assert out_e[k].item() == out_g[k].item(), (it, k, out_e[k].item(), out_g[k].item())
+        for m in MODS:
+            a, b = getattr(tr_e, ATTR[m]), getattr(tr_g, ATTR[m])
+            assert torch.equal(a.flat_params(), b.flat_params()), (it, m)
+            if a.flat_buffers() is not None:
+                assert torch.equal(a.flat_buffers(), b.flat_buffers()), (it, m)
+    assert tr_g.optimizer_D1._step == tr_e.optimizer_D1._step == 15
+    assert tr_g.optimizer_G._step == tr_e.optimizer_G._step == 3
+    assert torch.equal(tr_g.optimizer_G._m, tr_e.optimizer_G._m)
+    # the drop-in epoch function uses the graph when asked to
+    tr_g.use_cuda_graph = True
+    loader = [{"gesture": real_t.cpu(), "prototype": proto_t.cpu()}] * 2
+    res = wgg.train_epoch_with_grad_clip(tr_g, loader, 1.0, tr_g.model_config, tr_g.training_config, DEV)
+    assert set(res) == {"d1_loss", "d2_loss", "cycle1_total", "cycle2_total"} and all(np.isfinite(v) for v in res.values())

@@ -9,6 +9,7 @@ from .gan_losses import (FeatureMatchingLoss, KLDivergenceLoss, LatentEncodingLo
                          WassersteinLoss, feature_matching_from_stash)
 from .gan_modules import Discriminator, Generator, TemporalDiscriminator, VariationalEncoder
 from .gan_trainer import WordGestureGANTrainer
+from .graph_step import GraphedTrainStep
 from .optim import FusedClipAdam
 from .train_step import log, seed_everything, train_batch, train_epoch_with_grad_clip
 
@@ -16,6 +17,6 @@ __all__ = [
     "ModelConfig", "TrainingConfig", "DEFAULT_MODEL_CONFIG", "DEFAULT_TRAINING_CONFIG",
     "Generator", "VariationalEncoder", "Discriminator", "TemporalDiscriminator",
     "WassersteinLoss", "FeatureMatchingLoss", "ReconstructionLoss", "LatentEncodingLoss", "KLDivergenceLoss",
-    "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam",
+    "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam", "GraphedTrainStep",
     "set_math_mode", "get_math_mode", "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
 ]

@@ -78,6 +78,7 @@ _SIG = {
     "wgg_clip_adam_workspace_floats": (c_int64, []),
     "wgg_clip_adam": (c_int, [_P, _P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float,
                               _P, _P, _P]),
+    "wgg_clip_adam_dev": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, _P, c_float, _P, _P, _P]),
     "wgg_linear": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIG)

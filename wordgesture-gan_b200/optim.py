@@ -25,6 +25,9 @@ class FusedClipAdam(torch.optim.Optimizer):
         self._m = None
         self._v = None
         self._step = 0
+        self._step_dev = None   # int32 device counter (what the kernels read; CUDA-graph capturable)
+        self._lr_dev = None     # float32 device scalar mirroring param_groups[0]['lr']
+        self._lr_cached = None
         self.process_group = None  # set by parallel.DataParallelGAN: all-reduce (mean) grads before clipping
         self.world_size = 1
         self.last_grad_norm = None  # device scalar: pre-clip global L2 norm of the last step
@@ -44,7 +47,27 @@ class FusedClipAdam(torch.optim.Optimizer):
                 self._v.copy_(old_v)
         if len(self.state) != len(self._params()) or not self._state_is_aliased():
             self._alias_state()
+        if self._step_dev is None or self._step_dev.device != flat.device:
+            self._step_dev = torch.full((1,), self._step, dtype=torch.int32, device=flat.device)
+            self._lr_dev = torch.zeros((1,), dtype=torch.float32, device=flat.device)
+            self._lr_cached = None
         return flat
+
+    def refresh_device_scalars(self, force_step: bool = False):
+        """Mirror the host-side learning rate (mutated by LR schedulers) and, on request, the step count onto the
+        device scalars the kernels read.  Called before every eager step and before every graph replay."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_cached:
+            self._lr_dev.fill_(lr)
+            self._lr_cached = lr
+        if force_step:
+            self._step_dev.fill_(self._step)
+
+    def note_graph_replays(self, n_steps: int):
+        """A captured graph advanced the device step counter by ``n_steps``: keep the host bookkeeping in sync."""
+        self._step += n_steps
+        for st in self.state.values():
+            st["step"].fill_(float(self._step))
 
     def _state_is_aliased(self) -> bool:
         off = self._m.data_ptr()
@@ -113,18 +136,23 @@ class FusedClipAdam(torch.optim.Optimizer):
         if self.process_group is not None and self.world_size > 1:
             from .parallel import allreduce_mean_
             allreduce_mean_(g, self.process_group, self.world_size)
-        self._step += 1
         dev = flat.device
         c = _lib.ctx(dev)
         lib = _lib.lib()
         ws = _lib.workspace(dev, lib.wgg_clip_adam_workspace_floats())
         if self.last_grad_norm is None or self.last_grad_norm.device != dev:
             self.last_grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.refresh_device_scalars()
         b1, b2 = group["betas"]
-        _lib.check(lib.wgg_clip_adam(c, _lib.ptr(flat), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), flat.numel(),
-                                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), self._step,
-                                     float(max_norm) if max_norm else 0.0, _lib.ptr(self.last_grad_norm), _lib.ptr(ws),
-                                     _lib.stream(dev)), c)
+        _lib.check(lib.wgg_clip_adam_dev(c, _lib.ptr(flat), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), flat.numel(),
+                                         self._lr_dev.data_ptr(), float(b1), float(b2), float(group["eps"]),
+                                         self._step_dev.data_ptr(), float(max_norm) if max_norm else 0.0,
+                                         _lib.ptr(self.last_grad_norm), _lib.ptr(ws), _lib.stream(dev)), c)
+        if capturing:
+            return loss  # host bookkeeping is done per replay (note_graph_replays)
+        self._step += 1
         for st in self.state.values():
             st["step"].fill_(float(self._step))
         return loss
@@ -138,3 +166,5 @@ class FusedClipAdam(torch.optim.Optimizer):
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
             self._alias_state()
+            if self._step_dev is not None:
+                self._step_dev.fill_(self._step)
