@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log | cut -c1-400
+timeout 600 python scripts/prof_sites.py 4096 tf32 > gpurun_out/prof_sites.log 2>&1; sed -n '/filter kernel/,$p' gpurun_out/prof_sites.log | head -30

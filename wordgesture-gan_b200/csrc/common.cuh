@@ -208,16 +208,17 @@ int disc_feature_table(const wgg_model_cfg* cfg, int64_t B, FeatTable* ft);
 // ----------------------------------------------------------------------------------------------
 bool generator_tc_supported(const wgg_model_cfg* cfg);
 int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
+int64_t generator_tc_bwd_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
+int64_t generator_tc_stash_floats(const wgg_model_cfg* cfg, int64_t B);
+float* generator_tc_stash_hrm(const wgg_model_cfg* cfg, int64_t B, float* stash);
 int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
-                         int64_t B, float* out, float* ws, int64_t ws_floats, float* gc_stash, float* const* hseq_rm,
-                         cudaStream_t st);
-// grad-carrying variant: gc_stash = per-layer gate/cell stash (generator_tc_gc_layer_floats each), hseq_rm[l] = row-major
-// layer outputs [T][B][2H]
-int64_t generator_tc_gc_layer_floats(const wgg_model_cfg* cfg, int64_t B);
-int lstm_tc_bwd_layer(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* lp, int64_t dir_stride, int64_t off_whh,
-                      const float* gc, const float* dh_out, float* da_rm, float* wimg_ws, int64_t B, cudaStream_t st);
+                         int64_t B, float* out, float* ws, int64_t ws_floats, float* stash, cudaStream_t st);
+int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* dparams,
+                                 const int64_t* layer_off, const int64_t* dir_stride, const int64_t* off_whh,
+                                 const int64_t* off_bih, const int64_t* off_bhh, int64_t B, const float* stash,
+                                 const float* dh_rm, float* dz, float* ws, int64_t ws_floats, cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05 conv1d layers of the TemporalDiscriminator (conv_tc.cu)

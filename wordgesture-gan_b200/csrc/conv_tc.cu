@@ -158,25 +158,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
         float4* o4 = reinterpret_cast<float4*>(a.out) + (b * (a.N / 4)) * T + t;
         const float4* y4 = a.mode == 1 ? reinterpret_cast<const float4*>(a.act_lower) + (b * (a.N / 4)) * T + t : nullptr;
         const float4* f4 = (a.mode == 1 && a.dfeat) ? reinterpret_cast<const float4*>(a.dfeat) + (b * (a.N / 4)) * T + t : nullptr;
+        if (a.mode == 0) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          if (q >= a.N / 4) break;
-          float x[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
-          if (a.mode == 0) {
+          for (int q = 0; q < 16; ++q) {
+            if (q >= a.N / 4) break;
+            float x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = leaky_f(x[i] + s_bias[4 * q + i]);
-          } else {
-            const float4 y = __ldg(y4 + (int64_t)q * T);
-            if (f4) {
-              const float4 f = __ldg(f4 + (int64_t)q * T);
-              x[0] += f.x; x[1] += f.y; x[2] += f.z; x[3] += f.w;
-            }
-            x[0] = y.x > 0.f ? x[0] : kLeak * x[0];
-            x[1] = y.y > 0.f ? x[1] : kLeak * x[1];
-            x[2] = y.z > 0.f ? x[2] : kLeak * x[2];
-            x[3] = y.w > 0.f ? x[3] : kLeak * x[3];
+            for (int i = 0; i < 4; ++i) x[i] = leaky_f(v[4 * q + i] + s_bias[4 * q + i]);
+            o4[(int64_t)q * T] = make_float4(rna_tf32(x[0]), rna_tf32(x[1]), rna_tf32(x[2]), rna_tf32(x[3]));
           }
-          o4[(int64_t)q * T] = make_float4(rna_tf32(x[0]), rna_tf32(x[1]), rna_tf32(x[2]), rna_tf32(x[3]));
+        } else {
+          // LeakyReLU backward (+ feature-matching gradient injection): issue all loads first, then the math
+          float4 ys[16], fs[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < a.N / 4) {
+              ys[q] = __ldg(y4 + (int64_t)q * T);
+              fs[q] = f4 ? __ldg(f4 + (int64_t)q * T) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (q >= a.N / 4) break;
+            float x[4] = {v[4 * q] + fs[q].x, v[4 * q + 1] + fs[q].y, v[4 * q + 2] + fs[q].z, v[4 * q + 3] + fs[q].w};
+            x[0] = ys[q].x > 0.f ? x[0] : kLeak * x[0];
+            x[1] = ys[q].y > 0.f ? x[1] : kLeak * x[1];
+            x[2] = ys[q].z > 0.f ? x[2] : kLeak * x[2];
+            x[3] = ys[q].w > 0.f ? x[3] : kLeak * x[3];
+            o4[(int64_t)q * T] = make_float4(rna_tf32(x[0]), rna_tf32(x[1]), rna_tf32(x[2]), rna_tf32(x[3]));
+          }
         }
       }
     }

@@ -7,6 +7,8 @@
 // split-K) forms through operand strides; conv1d is an implicit GEMM through a sliding-window
 // view of the channel-last activation tensor (no im2col materialisation).
 // fp32 FMA path: 64x64x16 tiles, 256 threads, 4x4 register tile, register-prefetched global loads.
+#include <stdint.h>
+
 #include "common.cuh"
 
 namespace {
@@ -325,6 +327,168 @@ __global__ void __launch_bounds__(256, 2) gemm_mma_kernel(GemmP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vectorised tensor-core variant for operands that have a unit-stride dimension (all LSTM gradient GEMMs):
+// 16-byte cp.async copies straight into the shared-memory layout the fragments are read from (no register
+// staging, no transposition), 3-stage pipeline, 128x64x32 tiles.  A_KFAST: A(m,k) is contiguous in k (row-major
+// activations) -> tile [m][k]; otherwise contiguous in m (transposed operand of a weight gradient) -> tile [k][m].
+// B_NFAST: B(k,n) contiguous in n -> tile [k][n]; otherwise contiguous in k -> tile [n][k].
+// Requirements (checked by the launcher): the other stride is a multiple of 4 floats, bases 16-byte aligned,
+// M / N / K multiples of 4, no conv window.
+// ---------------------------------------------------------------------------------------------
+constexpr int VBK = 32, VSTAGES = 3;
+constexpr int VA_KF_LD = VBK + 4;    // [128][36]
+constexpr int VA_MF_LD = TBM + 8;    // [32][136]
+constexpr int VB_NF_LD = TBN + 8;    // [32][72]
+constexpr int VB_KF_LD = VBK + 4;    // [64][36]
+constexpr int VA_FLOATS = TBM * VA_KF_LD > VBK * VA_MF_LD ? TBM * VA_KF_LD : VBK * VA_MF_LD;  // 4608
+constexpr int VB_FLOATS = VBK * VB_NF_LD > TBN * VB_KF_LD ? VBK * VB_NF_LD : TBN * VB_KF_LD;  // 2304
+constexpr int VSTAGE_FLOATS = VA_FLOATS + VB_FLOATS;
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <int A_KFAST, int B_NFAST>
+__global__ void __launch_bounds__(256, 2) gemm_mma_vec_kernel(GemmP p) {
+  extern __shared__ __align__(16) float vsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+  const float* __restrict__ A = p.A + (int64_t)batch * p.bsA;
+  const float* __restrict__ B = p.B + (int64_t)batch * p.bsB;
+  const int64_t m0 = (int64_t)blockIdx.x * TBM;
+  const int64_t n0 = (int64_t)blockIdx.y * TBN;
+  const int64_t ktiles = (p.K + VBK - 1) / VBK;
+  const int64_t per = (ktiles + p.splitk - 1) / p.splitk;
+  const int64_t kt_begin = (int64_t)split * per;
+  const int64_t kt_end = min(ktiles, kt_begin + per);
+  const int nkt = (int)(kt_end - kt_begin);
+
+  auto issue = [&](int kt_local, int stage) {
+    float* sa = vsm + stage * VSTAGE_FLOATS;
+    float* sb = sa + VA_FLOATS;
+    const int64_t k0 = (kt_begin + kt_local) * VBK;
+    // A tile: 128 x 32 floats = 1024 float4, 4 per thread
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      if (A_KFAST) {
+        const int mm = idx >> 3, k4 = (idx & 7) * 4;
+        const int64_t m = m0 + mm, k = k0 + k4;
+        const bool v = m < p.M && k < p.K;
+        cp_async16_zfill(sa + mm * VA_KF_LD + k4, A + (v ? m * p.sam + k : 0), v);
+      } else {
+        const int kk = idx >> 5, m4 = (idx & 31) * 4;
+        const int64_t m = m0 + m4, k = k0 + kk;
+        const bool v = m < p.M && k < p.K;
+        cp_async16_zfill(sa + kk * VA_MF_LD + m4, A + (v ? k * p.sak + m : 0), v);
+      }
+    }
+    // B tile: 32 x 64 floats = 512 float4, 2 per thread
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int idx = tid + e * 256;
+      if (B_NFAST) {
+        const int kk = idx >> 4, n4 = (idx & 15) * 4;
+        const int64_t k = k0 + kk, n = n0 + n4;
+        const bool v = k < p.K && n < p.N;
+        cp_async16_zfill(sb + kk * VB_NF_LD + n4, B + (v ? k * p.sbk + n : 0), v);
+      } else {
+        const int nn = idx >> 3, k4 = (idx & 7) * 4;
+        const int64_t k = k0 + k4, n = n0 + nn;
+        const bool v = k < p.K && n < p.N;
+        cp_async16_zfill(sb + nn * VB_KF_LD + k4, B + (v ? n * p.sbn + k : 0), v);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int g = lane >> 2, q = lane & 3;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  for (int s = 0; s < VSTAGES - 1; ++s) {
+    if (s < nkt) issue(s, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nkt; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(VSTAGES - 2) : "memory");
+    __syncthreads();
+    // prefetch tile kt + STAGES - 1 into the stage consumed at iteration kt - 1 (safe after the barrier above)
+    if (kt + VSTAGES - 1 < nkt) issue(kt + VSTAGES - 1, (kt + VSTAGES - 1) % VSTAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* sa = vsm + (kt % VSTAGES) * VSTAGE_FLOATS;
+    const float* sb = sa + VA_FLOATS;
+#pragma unroll
+    for (int ks = 0; ks < VBK; ks += 8) {
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int mb = wm + i * 16;
+        if (A_KFAST) {
+          af[i][0] = to_tf32(sa[(mb + g) * VA_KF_LD + ks + q]);
+          af[i][1] = to_tf32(sa[(mb + g + 8) * VA_KF_LD + ks + q]);
+          af[i][2] = to_tf32(sa[(mb + g) * VA_KF_LD + ks + q + 4]);
+          af[i][3] = to_tf32(sa[(mb + g + 8) * VA_KF_LD + ks + q + 4]);
+        } else {
+          af[i][0] = to_tf32(sa[(ks + q) * VA_MF_LD + mb + g]);
+          af[i][1] = to_tf32(sa[(ks + q) * VA_MF_LD + mb + g + 8]);
+          af[i][2] = to_tf32(sa[(ks + q + 4) * VA_MF_LD + mb + g]);
+          af[i][3] = to_tf32(sa[(ks + q + 4) * VA_MF_LD + mb + g + 8]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nb = wn + j * 8;
+        if (B_NFAST) {
+          bf[j][0] = to_tf32(sb[(ks + q) * VB_NF_LD + nb + g]);
+          bf[j][1] = to_tf32(sb[(ks + q + 4) * VB_NF_LD + nb + g]);
+        } else {
+          bf[j][0] = to_tf32(sb[(nb + g) * VB_KF_LD + ks + q]);
+          bf[j][1] = to_tf32(sb[(nb + g) * VB_KF_LD + ks + q + 4]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], af[i], bf[j]);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+
+  float* C = p.C + (int64_t)batch * p.bsC;
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
+  const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
+  const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int64_t m = m0 + wm + i * 16 + g + rr * 8;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int64_t n = n0 + wn + j * 8 + 2 * q + cc;
+          if (n >= p.N) continue;
+          const float v = acc[i][j][rr * 2 + cc];
+          if (P) P[m * p.N + n] = v;
+          else store_out(p, C, bias, bias2, m, n, v);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ P, int S, int64_t n,
                                                               int64_t bsP, float* __restrict__ out,
                                                               float* __restrict__ out2, int64_t bsOut,
@@ -395,7 +559,26 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (grid.y > 65535 || grid.z > 65535) return wgg_fail(ctx, WGG_EINVAL, "gemm: grid too large%s");
   ProfScope prof(ctx, "gemm_kernel", st, 2.0 * (double)p.M * (double)p.N * (double)p.K * p.nbatch,
                  4.0 * ((double)p.M * p.K + (double)p.K * p.N + (double)p.M * p.N) * p.nbatch, p.tag);
-  if (tf32) {
+  const bool a_kf = p.sak == 1, a_mf = p.sam == 1, b_nf = p.sbn == 1, b_kf = p.sbk == 1;
+  const bool vec_ok = tf32 && ctx->math_mode == 1 && p.conv_mode == 0 && !p.x3 && (a_kf || a_mf) && (b_nf || b_kf) &&
+                      (p.M % 4 == 0) && (p.N % 4 == 0) && (p.K % 4 == 0) &&
+                      ((a_kf ? p.sam : p.sak) % 4 == 0) && ((b_nf ? p.sbk : p.sbn) % 4 == 0) && (p.bsA % 4 == 0) &&
+                      (p.bsB % 4 == 0) && (((uintptr_t)p.A | (uintptr_t)p.B) % 16 == 0);
+  if (vec_ok) {
+    constexpr size_t vsmem = (size_t)VSTAGES * VSTAGE_FLOATS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(gemm_mma_vec_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
+      cudaFuncSetAttribute(gemm_mma_vec_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
+      cudaFuncSetAttribute(gemm_mma_vec_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
+      cudaFuncSetAttribute(gemm_mma_vec_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
+      configured = true;
+    }
+    if (a_kf && b_nf) gemm_mma_vec_kernel<1, 1><<<grid, 256, vsmem, st>>>(p);
+    else if (a_kf) gemm_mma_vec_kernel<1, 0><<<grid, 256, vsmem, st>>>(p);
+    else if (b_nf) gemm_mma_vec_kernel<0, 1><<<grid, 256, vsmem, st>>>(p);
+    else gemm_mma_vec_kernel<0, 0><<<grid, 256, vsmem, st>>>(p);
+  } else if (tf32) {
     const bool x3 = ctx->math_mode == 2 && (p.conv_mode != 0 || p.x3);  // compensated convs only in tf32x3 mode
     if (p.conv_mode == 1 && x3) gemm_mma_kernel<1, 1><<<grid, 256, 0, st>>>(p);
     else if (p.conv_mode == 1) gemm_mma_kernel<1, 0><<<grid, 256, 0, st>>>(p);

@@ -349,13 +349,6 @@ int64_t stash_floats(const GenLayout& g, int64_t B) {
   return TB * (g.I0 + (int64_t)g.L * 12 * g.H);
 }
 
-// tcgen05 training path (math mode >= 1): x0 | hseq[l] row-major as above, then per layer the gate/cell stash in
-// the tensor-core chunk layout (generator_tc_gc_layer_floats each)
-int64_t stash_floats_tc(const wgg_model_cfg* cfg, const GenLayout& g, int64_t B) {
-  const int64_t TB = (int64_t)g.T * B;
-  return TB * (g.I0 + (int64_t)g.L * 2 * g.H) + (int64_t)g.L * generator_tc_gc_layer_floats(cfg, B);
-}
-
 void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
   const int64_t TB = (int64_t)g.T * B;
   v->x0 = s;
@@ -377,7 +370,7 @@ extern "C" int64_t wgg_generator_stash_floats(const wgg_model_cfg* cfg, int64_t 
   GenLayout g;
   if (gen_layout(cfg, &g) != WGG_OK) return -1;
   const int64_t a = stash_floats(g, B);
-  const int64_t b = generator_tc_supported(cfg) ? stash_floats_tc(cfg, g, B) : 0;
+  const int64_t b = generator_tc_supported(cfg) ? generator_tc_stash_floats(cfg, B) : 0;
   return a > b ? a : b;  // either math mode fits
 }
 
@@ -391,9 +384,9 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
     return simt > tcw ? simt : tcw;
   }
   const int64_t maxI = g.I0 > 2 * g.H ? g.I0 : 2 * g.H;
-  // dpre | dh | dx | (tcgen05 path: da row-major [2][T][B][4H] + W_hh^T images) | split-K partials | column-sum scratch
-  return TB * (g.C + 2 * maxI) + TB * 8 * g.H + 2 * 4 * g.H * g.H + gemm_splitk_ws_floats(4 * g.H, maxI, 2) +
-         colsum_ws_floats(4 * g.H, 2);
+  // dpre | dh | dx | split-K partials | column-sum scratch | (tcgen05 path: its own backward workspace)
+  return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2) +
+         generator_tc_bwd_workspace_floats(cfg, B);
 }
 
 extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
@@ -406,22 +399,12 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t TB = (int64_t)g.T * B;
   if (ctx->math_mode >= 1 && generator_tc_supported(cfg)) {
-    // tcgen05 path: no-grad calls (sampling, the 10 critic-loop generations per batch) and, with a stash, the
-    // grad-carrying forward (gate/cell stash in chunk layout + row-major layer outputs for the gradient GEMMs)
+    // tcgen05 path (lstm_tc.cu): no-grad calls (sampling, the critic loop's generations) and, with a stash, the
+    // grad-carrying forward
     if (!ws || ws_floats < generator_tc_workspace_floats(cfg, B))
       return wgg_fail(ctx, WGG_EWORKSPACE, "generator_forward: workspace too small for the tcgen05 path%s");
-    float* hrm[WGG_MAX_HIDDEN_LAYERS] = {nullptr};
-    float* gcs = nullptr;
-    if (stash) {
-      float* sp = stash;
-      build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sp, g.T, B, g.C, g.pd, g.Z);
-      WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
-      sp += TB * g.I0;
-      for (int l = 0; l < g.L; ++l) { hrm[l] = sp; sp += TB * 2 * g.H; }
-      gcs = sp;
-    }
     return generator_forward_tc(ctx, cfg, params, g.layer_off, g.dir_stride, g.off_whh, g.off_bih, g.off_bhh, g.off_wo,
-                                g.off_bo, proto, z, B, out, ws, ws_floats, gcs, hrm, st);
+                                g.off_bo, proto, z, B, out, ws, ws_floats, stash, st);
   }
   StashView sv;
   float* hbuf[2] = {nullptr, nullptr};
@@ -482,20 +465,17 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   const int64_t maxI = g.I0 > 2 * H ? g.I0 : 2 * H;
   const bool tcp = ctx->math_mode >= 1 && generator_tc_supported(cfg);
   StashView sv;
-  stash_view(g, B, stash, &sv);  // x0 and hseq[l] sit at the same offsets in both stash layouts
-  float* gc_base = sv.hseq[g.L - 1] + TB * 2 * H;
-  const int64_t gc_layer = tcp ? generator_tc_gc_layer_floats(cfg, B) : 0;
+  if (!tcp) stash_view(g, B, stash, &sv);
   float* dpre = ws;
   float* dh = dpre + TB * g.C;
   float* dx = dh + TB * maxI;
-  float* da_ws = dx + TB * maxI;
-  float* whhT = da_ws + TB * 8 * H;
-  float* part = whhT + 2 * 4 * H * H;
+  float* part = dx + TB * maxI;
   float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
+  float* tcws = csws + colsum_ws_floats(H4, 2);
 
   head_bwd_kernel<<<ew_grid(TB * g.C), 256, 0, st>>>(out, dout, dpre, g.T, B, g.C);
   WGG_CHECK_LAUNCH(ctx, "head_bwd_kernel");
-  const float* hL = sv.hseq[g.L - 1];
+  const float* hL = tcp ? generator_tc_stash_hrm(cfg, B, stash) : sv.hseq[g.L - 1];
   {
     GemmP p;  // dWo (C x 2H) += dpre^T * hL
     p.tag = "gemm_kernel/head_wgrad";
@@ -512,18 +492,18 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     q.C = dh; q.scm = 2 * H; q.scn = 1; q.force_fp32 = 1;
     WGG_TRY(gemm_launch(ctx, q, st));
   }
+  if (tcp) {
+    // the LSTM stack's backward runs entirely on the tcgen05 path (BPTT, dx and dW/db kernels, chunk layouts)
+    return generator_backward_tc_layers(ctx, cfg, params, dparams, g.layer_off, g.dir_stride, g.off_whh, g.off_bih,
+                                        g.off_bhh, B, stash, dh, dz, tcws, generator_tc_bwd_workspace_floats(cfg, B), st);
+  }
   for (int l = g.L - 1; l >= 0; --l) {
     const int I = g.in_dim(l);
     const float* lp = params + g.layer_off[l];
     float* dlp = dparams + g.layer_off[l];
-    float* da = tcp ? da_ws : sv.gates[l];
+    float* da = sv.gates[l];
     const float* in = l == 0 ? sv.x0 : sv.hseq[l - 1];
-    if (tcp) {
-      WGG_TRY(lstm_tc_bwd_layer(ctx, cfg, lp, g.dir_stride[l], g.off_whh[l], gc_base + (int64_t)l * gc_layer, dh, da, whhT,
-                                B, st));
-    } else {
-      WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, g.T, B, st));
-    }
+    WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, g.T, B, st));
     {
       GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
       p.tag = "gemm_kernel/lstm_dWih";

@@ -266,12 +266,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
         for (int uu = 0; uu < 8; ++uu) {
           const int ul = ch * 8 + uu;                 // unit index inside this thread's 24
           const float4 bb = *reinterpret_cast<const float4*>(s_bias + (half * 24 + ul) * 4);
-          const float ig = sigmoid_fast(v[4 * uu + 0] + bb.x);
-          const float fg = sigmoid_fast(v[4 * uu + 1] + bb.y);
-          const float gg = tanh_fast(v[4 * uu + 2] + bb.z);
-          const float og = sigmoid_fast(v[4 * uu + 3] + bb.w);
+          // 5 gate non-linearities with 5 EX2 + 2 RCP (instead of 5 + 5): the sigmoids / tanh of a unit share their
+          // reciprocals.  sigma(x) = 1/(1+E(x)), tanh(x) = (1-E2(x))/(1+E2(x)) with E = exp(-x), E2 = exp(-2x);
+          // arguments are clamped to +-28 so that products of three (1+E) stay finite (sigma(-28) = 7e-13).
+          const float ai = fminf(fmaxf(v[4 * uu + 0] + bb.x, -28.f), 28.f);
+          const float af = fminf(fmaxf(v[4 * uu + 1] + bb.y, -28.f), 28.f);
+          const float ag = fminf(fmaxf(v[4 * uu + 2] + bb.z, -14.f), 14.f);
+          const float ao = fminf(fmaxf(v[4 * uu + 3] + bb.w, -28.f), 28.f);
+          const float pi = 1.f + __expf(-ai), pf = 1.f + __expf(-af), eg = __expf(-2.f * ag), pg = 1.f + eg;
+          const float r1 = __fdividef(1.f, pf * pi * pg);
+          const float ig = r1 * pf * pg;
+          const float fg = r1 * pi * pg;
+          const float gg = (1.f - eg) * r1 * pf * pi;
           c[ul] = fg * c[ul] + ig * gg;
-          hraw[uu] = og * tanh_fast(c[ul]);
+          const float cl = fminf(fmaxf(c[ul], -14.f), 14.f);
+          const float ec = __expf(-2.f * cl), pc = 1.f + ec, po = 1.f + __expf(-ao);
+          const float r2 = __fdividef(1.f, po * pc);
+          const float og = r2 * pc;
+          hraw[uu] = (1.f - ec) * r2;  // = og * tanh(c)
           hv[uu] = rna_tf32(hraw[uu]);
           if (STASH) gc4[(int64_t)(half * 24 + ul) * TM] = make_float4(ig, fg, gg, og);
         }
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
             const int ul = ch * 8 + 4 * k2;
             gc4[(int64_t)(HID + chunk) * TM] = make_float4(c[ul], c[ul + 1], c[ul + 2], c[ul + 3]);
             const int64_t bidx = (int64_t)tile * TM + row;
-            if (bidx < B)
+            if (h_rm != nullptr && bidx < B)
               *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
                   make_float4(hraw[4 * k2], hraw[4 * k2 + 1], hraw[4 * k2 + 2], hraw[4 * k2 + 3]);
           }
@@ -309,8 +321,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
 // warps turn (gates, c, c_prev, dh) into d(pre-activation) `da` [128 x 192] (written to shared memory as the next
 // MMA's A operand and to HBM row-major for the weight-gradient / input-gradient GEMMs), and one elected thread
 // issues dh_rec = da * W_hh (M=128, N=48, K=192) whose accumulator the NEXT (earlier) step reads from TMEM.
-//   gc     : [2][T][ntiles][60][128][4]   (forward stash)         dh_out : [T][B][2H] row-major
-//   da_rm  : [2][T][B][4H] row-major, PyTorch gate order (i,f,g,o blocks of H)
+//   gc     : [2][T][ntiles][60][128][4]   (forward stash)
+//   dh_out : [T][ntiles][24][128][4]      d(layer output), chunk layout (chunks dir*12.. belong to this direction)
+//   da_out : [2][T][ntiles][48][128][4]   chunk u = (da_i, da_f, da_g, da_o) of hidden unit u - exactly the A tile
 // ---------------------------------------------------------------------------------------------
 constexpr int BWD_THREADS = 288;  // warp 0: MMA issuer; warps 1..8: epilogue (TMEM quarter = warp % 4)
 constexpr int WT_CHUNK_BYTES = (HID / 8) * 128;  // 768: one K chunk of the [48 x 192] W_hh^T image
@@ -330,7 +343,7 @@ __global__ void prep_whhT_kernel(const float* __restrict__ lp, int64_t dir_strid
 __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float* __restrict__ gc,
                                                                      const float* __restrict__ wimg,
                                                                      const float* __restrict__ dh_out,
-                                                                     float* __restrict__ da_rm, int T, int ntiles,
+                                                                     float* __restrict__ da_out, int T, int ntiles,
                                                                      int64_t B, int* __restrict__ gerr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_da = smem;                                   // [48 chunks][128 rows][16 B]
@@ -393,25 +406,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
       const int tp = dir ? t + 1 : t - 1;
       const float4* g4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
       const float4* gp4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + tp) * ntiles + tile) * GC_CHUNKS) * TM + row;
-      const float* dhp = dh_out + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + half * 24;
-      float* dap = da_rm + (((int64_t)dir * T + t) * B + bidx) * N4 + half * 24;
+      const float4* dh4 = reinterpret_cast<const float4*>(dh_out) + (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS + half * 6) * TM + row;
+      float4* dao4 = reinterpret_cast<float4*>(da_out) + ((((int64_t)dir * T + t) * ntiles + tile) * HID + half * 24) * TM + row;
       if (step < T - 1) {
         if (!mbar_wait(BAR_ACC, (uint32_t)((n - 1) & 1), s_abort, gerr, 32)) break;
         tc_fence_after();
       }
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float rec[8];
-        if (step < T - 1) tmem_ld8(taddr + ch * 8, rec);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rec[i] = 0.f;
-        }
         float dho[8], cc[8], cp[8];
         {
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 a0 = valid ? __ldg(reinterpret_cast<const float4*>(dhp + ch * 8)) : z4;
-          const float4 a1 = valid ? __ldg(reinterpret_cast<const float4*>(dhp + ch * 8 + 4)) : z4;
+          const float4 a0 = valid ? __ldg(dh4 + (int64_t)(ch * 2) * TM) : z4;
+          const float4 a1 = valid ? __ldg(dh4 + (int64_t)(ch * 2 + 1) * TM) : z4;
           dho[0] = a0.x; dho[1] = a0.y; dho[2] = a0.z; dho[3] = a0.w; dho[4] = a1.x; dho[5] = a1.y; dho[6] = a1.z; dho[7] = a1.w;
           const int cchunk = HID + half * 6 + ch * 2;
           const float4 c0 = __ldg(g4 + (int64_t)cchunk * TM), c1 = __ldg(g4 + (int64_t)(cchunk + 1) * TM);
@@ -424,11 +431,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
             for (int i = 0; i < 8; ++i) cp[i] = 0.f;
           }
         }
+        // all global loads of this 8-unit chunk are issued before any dependent math (one memory round trip per chunk)
+        float4 gts[8];
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) gts[uu] = __ldg(g4 + (int64_t)(half * 24 + ch * 8 + uu) * TM);  // (i, f, g, o)
+        float rec[8];
+        if (step < T - 1) tmem_ld8(taddr + ch * 8, rec);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rec[i] = 0.f;
+        }
         float dai[8], daf[8], dag[8], dao[8];
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
           const int ul = ch * 8 + uu;
-          const float4 gt = __ldg(g4 + (int64_t)(half * 24 + ul) * TM);  // (i, f, g, o)
+          const float4 gt = gts[uu];
           const float tch = tanh_fast(cc[uu]);
           const float dh = dho[uu] + rec[uu];
           const float d_o = dh * tch;
@@ -438,18 +455,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
           dag[uu] = dct * gt.x * (1.f - gt.z * gt.z);
           dao[uu] = d_o * gt.w * (1.f - gt.w);
           dc[ul] = dct * gt.y;
-          da4[(half * 24 + ul) * TM + row] = make_float4(rna_tf32(dai[uu]), rna_tf32(daf[uu]), rna_tf32(dag[uu]), rna_tf32(dao[uu]));
-        }
-        if (valid) {
-          float4* o;
-          o = reinterpret_cast<float4*>(dap + 0 * HID + ch * 8);
-          o[0] = make_float4(dai[0], dai[1], dai[2], dai[3]); o[1] = make_float4(dai[4], dai[5], dai[6], dai[7]);
-          o = reinterpret_cast<float4*>(dap + 1 * HID + ch * 8);
-          o[0] = make_float4(daf[0], daf[1], daf[2], daf[3]); o[1] = make_float4(daf[4], daf[5], daf[6], daf[7]);
-          o = reinterpret_cast<float4*>(dap + 2 * HID + ch * 8);
-          o[0] = make_float4(dag[0], dag[1], dag[2], dag[3]); o[1] = make_float4(dag[4], dag[5], dag[6], dag[7]);
-          o = reinterpret_cast<float4*>(dap + 3 * HID + ch * 8);
-          o[0] = make_float4(dao[0], dao[1], dao[2], dao[3]); o[1] = make_float4(dao[4], dao[5], dao[6], dao[7]);
+          const float4 dq = make_float4(rna_tf32(dai[uu]), rna_tf32(daf[uu]), rna_tf32(dag[uu]), rna_tf32(dao[uu]));
+          da4[(half * 24 + ul) * TM + row] = dq;       // A operand of dh_rec = da * W_hh
+          dao4[(int64_t)ul * TM] = dq;                 // HBM copy for the dx / dW kernels (coalesced: lane = row)
         }
       }
       tc_fence_before();
@@ -464,6 +472,318 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
     tc_fence_after();
     tmem_dealloc(tmem_base, 64);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dx = sum_dir da_dir * W_ih_dir : the gradient w.r.t. a layer's input (= d(output) of the layer below).
+// One CTA = one half of the input features (N = 48) looping over (t, tile) pairs; per pair and direction the
+// 96 KB da tile arrives with ONE bulk copy (it is contiguous in the chunk layout) and feeds 24 K-major MMAs
+// (M=128 samples, N=48, K=192 gates); both directions accumulate into the same TMEM tile.
+//   da   : [2][T][ntiles][48][128][4]       wimg : [2 halves][2 dirs][48 x 192] K-major images of W_ih^T
+//   dx   : [T][ntiles][nchunks_out][128][4]  (this CTA writes chunks half*12 .. half*12+11)
+// ---------------------------------------------------------------------------------------------
+constexpr int DX_THREADS = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+
+// img[half][dir][feat][n'] = W_ih[dir][(g*H + u)][half*48 + feat]  (0 beyond I), n' = 4u + g
+__global__ void prep_wihT_kernel(const float* __restrict__ lp, int64_t dir_stride, int I, float* __restrict__ img) {
+  const int dir = blockIdx.y, half = blockIdx.z;
+  const float* w = lp + dir * dir_stride;
+  float* o = img + ((int64_t)half * 2 + dir) * HID * N4;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < HID * N4; idx += gridDim.x * blockDim.x) {
+    const int f = idx / N4, kk = idx % N4;
+    const int u = kk >> 2, g = kk & 3;
+    const int feat = half * HID + f;
+    o[tc_index(HID, f, kk)] = feat < I ? rna_tf32(w[(int64_t)(g * HID + u) * I + feat]) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* __restrict__ da,
+                                                                   const float* __restrict__ wimg,
+                                                                   float* __restrict__ dx, int T, int ntiles,
+                                                                   int out_chunks, int* __restrict__ gerr) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_a = smem;                                  // one da tile: 48 chunks x 2048 B
+  uint8_t* s_w = s_a + HID * CHUNK_BYTES_A;             // 2 dirs x (48 chunks x 768 B)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + 2 * HID * WT_CHUNK_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = blockIdx.y;
+  const uint32_t bar0 = smem_u32(s_bar);
+  const uint32_t BAR_FULL = bar0, BAR_EMPTY = bar0 + 8, BAR_ACC_FULL = bar0 + 16, BAR_ACC_EMPTY = bar0 + 24;
+  {
+    const float4* src = reinterpret_cast<const float4*>(wimg + (int64_t)half * 2 * HID * N4);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < 2 * HID * N4 / 4; i += DX_THREADS) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    mbar_init(BAR_FULL, 1);
+    mbar_init(BAR_EMPTY, 1);
+    mbar_init(BAR_ACC_FULL, 1);
+    mbar_init(BAR_ACC_EMPTY, 4);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int64_t npairs = (int64_t)T * ntiles;
+  const int64_t tile_floats = (int64_t)HID * TM * 4;  // one da tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x)
+        for (int d = 0; d < 2; ++d, ++n) {
+          if (!mbar_wait(BAR_EMPTY, (uint32_t)((n & 1) ^ 1), s_abort, gerr, 41)) return;
+          mbar_expect_tx(BAR_FULL, HID * CHUNK_BYTES_A);
+          bulk_g2s(smem_u32(s_a), da + ((int64_t)d * npairs + pr) * tile_floats, HID * CHUNK_BYTES_A, BAR_FULL);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TM, HID);
+      const uint32_t a0 = smem_u32(s_a), w0 = smem_u32(s_w);
+      int n = 0, np = 0;
+      for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++np) {
+        if (!mbar_wait(BAR_ACC_EMPTY, (uint32_t)((np & 1) ^ 1), s_abort, gerr, 42)) return;
+        for (int d = 0; d < 2; ++d, ++n) {
+          if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 43)) return;
+          tc_fence_after();
+#pragma unroll 4
+          for (int j = 0; j < N4 / 8; ++j) {
+            const uint64_t ad = make_desc(a0 + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
+            const uint64_t bd = make_desc(w0 + d * HID * WT_CHUNK_BYTES + j * 2 * WT_CHUNK_BYTES, WT_CHUNK_BYTES, 128);
+            mma_tf32_ss(tmem_base, ad, bd, idesc, (d | j) ? 1u : 0u);
+          }
+          mma_commit(BAR_EMPTY);
+        }
+        mma_commit(BAR_ACC_FULL);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int np = 0;
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++np) {
+      if (!mbar_wait(BAR_ACC_FULL, (uint32_t)(np & 1), s_abort, gerr, 44)) break;
+      tc_fence_after();
+      float v[48];
+#pragma unroll
+      for (int c0 = 0; c0 < 48; c0 += 16) {
+        float r[16];
+        tmem_ld16(taddr + c0, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[c0 + i] = r[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_ACC_EMPTY);
+      float4* o4 = reinterpret_cast<float4*>(dx) + (pr * out_chunks + half * KH_CHUNKS) * TM + row;
+#pragma unroll
+      for (int q = 0; q < KH_CHUNKS; ++q)
+        if (half * KH_CHUNKS + q < out_chunks)
+          o4[(int64_t)q * TM] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dW_ih, dW_hh, db of one layer: G[n'][feat] = sum_{t, sample} da[n'] * [x_t | h_prev][feat];  db[n'] = sum da[n'].
+// Both operands MN-major (SWIZZLE_128B_BASE32B tiles [32-wide blocks][128 sample rows][128 B], see conv_tc.cu),
+// K = the 128 samples of a (t, tile) pair; M = 192 gates as three M=64 MMAs, N = 160 = 96 input features + 48
+// recurrent features (+16 zero), plus an N=8 MMA against ones for the bias.  Accumulators stay in TMEM across all
+// pairs of the persistent CTA (3 x 168 = 504 columns); each CTA writes one partial block.
+//   grid (ctas_per_dir, 2 dirs); 288 threads: warp 0 MMA, warps 1..8 producers then read-out.
+// ---------------------------------------------------------------------------------------------
+constexpr int DW_THREADS = 288;
+constexpr int DW_BLK = TM * 128;      // 16384 B: one 32-wide block of 128 rows
+constexpr int DW_NB = 5;              // B operand blocks (160 features)
+constexpr int DW_COLS = 168;          // 160 + 8 (bias) columns per M group
+
+__device__ __forceinline__ uint64_t make_desc_mn_dw(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((DW_BLK >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t dw_off(int r, int q) {  // 16-byte group (row r, 4-wide chunk q) inside a tile
+  return (uint32_t)((q >> 3) * DW_BLK + r * 128 + ((((q & 7) >> 1) ^ (r & 3)) << 5) + ((q & 1) << 4));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* __restrict__ da,
+                                                                   const float* __restrict__ xin, int xin_chunks,
+                                                                   const float* __restrict__ hself,
+                                                                   float* __restrict__ partial, int T, int ntiles,
+                                                                   int* __restrict__ gerr) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_a = smem;                         // 6 blocks: da (192 gates, unit-major n')
+  uint8_t* s_b = s_a + 6 * DW_BLK;             // 5 blocks: [x (96) | h_prev (48) | 0 (16)]
+  uint8_t* s_one = s_b + DW_NB * DW_BLK;       // 1 block of ones
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + DW_BLK);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const uint32_t bar0 = smem_u32(s_bar);
+  const uint32_t BAR_FULL = bar0, BAR_EMPTY = bar0 + 8, BAR_DONE = bar0 + 16;
+  {
+    float4* z = reinterpret_cast<float4*>(smem);
+    for (int i = tid; i < 11 * DW_BLK / 16; i += DW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* o = reinterpret_cast<float4*>(s_one);
+    for (int i = tid; i < DW_BLK / 16; i += DW_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  if (tid == 0) {
+    mbar_init(BAR_FULL, 256);
+    mbar_init(BAR_EMPTY, 1);
+    mbar_init(BAR_DONE, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int64_t npairs = (int64_t)T * ntiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t id_main = make_idesc(64, 160, 1, 1), id_one = make_idesc(64, 8, 1, 1);
+      const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b), o0 = smem_u32(s_one);
+      int n = 0;
+      bool ok = true;
+      for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
+        if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 51)) { ok = false; break; }
+        tc_fence_after();
+        for (int ks = 0; ks < TM / 8; ++ks) {
+          const uint32_t acc = (n | ks) ? 1u : 0u;
+          const uint64_t bd = make_desc_mn_dw(b0 + ks * 1024);
+          const uint64_t od = make_desc_mn_dw(o0 + ks * 1024);
+#pragma unroll
+          for (int mg = 0; mg < 3; ++mg) {
+            const uint64_t ad = make_desc_mn_dw(a0 + 2 * mg * DW_BLK + ks * 1024);
+            mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS), ad, bd, id_main, acc);
+            mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS + 160), ad, od, id_one, acc);
+          }
+        }
+        mma_commit(BAR_EMPTY);
+      }
+      if (ok) mma_commit(BAR_DONE);
+    }
+  } else {
+    const int ptid = tid - 32;  // 0..255
+    int n = 0;
+    bool ok = true;
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
+      if (!mbar_wait(BAR_EMPTY, (uint32_t)((n & 1) ^ 1), s_abort, gerr, 52)) { ok = false; break; }
+      const int t = (int)(pr / ntiles), tile = (int)(pr % ntiles);
+      const int tp = dir ? t + 1 : t - 1;  // timestep whose h fed the recurrence at t
+      const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b);
+      const float4* sd = reinterpret_cast<const float4*>(da) + ((int64_t)dir * npairs + pr) * HID * TM;
+      for (int i = ptid; i < HID * TM; i += 256) cp16(a0 + dw_off(i % TM, i / TM), sd + i);
+      const float4* sx = reinterpret_cast<const float4*>(xin) + pr * xin_chunks * TM;
+      for (int i = ptid; i < xin_chunks * TM; i += 256) cp16(b0 + dw_off(i % TM, i / TM), sx + i);
+      if (tp >= 0 && tp < T) {
+        const float4* sh = reinterpret_cast<const float4*>(hself) + (((int64_t)tp * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * TM;
+        for (int i = ptid; i < KH_CHUNKS * TM; i += 256) cp16(b0 + dw_off(i % TM, 24 + i / TM), sh + i);
+      } else {
+        for (int i = ptid; i < KH_CHUNKS * TM; i += 256)
+          *reinterpret_cast<float4*>(s_b + dw_off(i % TM, 24 + i / TM)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_async_smem();
+      mbar_arrive(BAR_FULL);
+    }
+    if (ok && mbar_wait(BAR_DONE, 0, s_abort, gerr, 53)) {
+      tc_fence_after();
+      // M = 64 accumulators: rows in lanes 0..15 of each TMEM quarter; 8 producer warps = 2 per quarter split the columns
+      const int quarter = warp & 3, colhalf = (warp - 1) >> 2;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int mg = 0; mg < 3; ++mg) {
+        float* dst = partial + ((((int64_t)dir * gridDim.x + blockIdx.x) * 3 + mg) * 64 + quarter * 16 + lane) * DW_COLS;
+        for (int c0 = colhalf * 16; c0 < DW_COLS; c0 += 32) {
+          float r[16];
+          tmem_ld16(taddr + mg * DW_COLS + c0, r);
+          if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < DW_COLS) dst[c0 + i] = r[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// reduce the per-CTA partials into the flat gradient (+=), mapping n' = 4u + g back to PyTorch rows g*H + u
+__global__ void dw_finalize_kernel(const float* __restrict__ partial, int nparts, int I, float* __restrict__ dlp,
+                                   int64_t dir_stride, int64_t off_whh, int64_t off_bih, int64_t off_bhh) {
+  const int dir = blockIdx.y;
+  const int per_row = I + HID + 1;
+  float* o = dlp + dir * dir_stride;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N4 * per_row; idx += gridDim.x * blockDim.x) {
+    const int np = idx / per_row, c = idx % per_row;
+    const int u = np >> 2, g = np & 3, prow = g * HID + u;
+    const int col = c < I ? c : (c < I + HID ? 96 + (c - I) : 160);
+    const int mg = np >> 6, r = np & 63;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[((((int64_t)dir * nparts + p) * 3 + mg) * 64 + r) * DW_COLS + col];
+    if (c < I) o[(int64_t)prow * I + c] += s;
+    else if (c < I + HID) o[off_whh + (int64_t)prow * HID + (c - I)] += s;
+    else { o[off_bih + prow] += s; o[off_bhh + prow] += s; }
+  }
+}
+
+// [T][B][W] row-major  ->  [T][ntiles][W/4][128][4] chunk layout (rows beyond B are zero)
+__global__ void rows_to_chunk_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int64_t B,
+                                     int ntiles, int W) {
+  const int64_t n = (int64_t)T * ntiles * TM * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 3);
+    const int row = (int)((i >> 2) % TM);
+    const int q = (int)((i / (4 * TM)) % (W / 4));
+    const int64_t pr = i / ((int64_t)W * TM);
+    const int tile = (int)(pr % ntiles), t = (int)(pr / ntiles);
+    const int64_t b = (int64_t)tile * TM + row;
+    out[i] = b < B ? __ldg(in + ((int64_t)t * B + b) * W + q * 4 + c4) : 0.f;
+  }
+}
+
+// dz[b][j] = sum_t dx0[t][tile][chunk][row][.] at feature pd + j     (backward of repeat + cat, models.py:154-157)
+__global__ void dz_chunk_kernel(const float* __restrict__ dx0, float* __restrict__ dz, int T, int64_t B, int ntiles,
+                                int chunks, int pd, int Z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Z) return;
+  const int64_t b = i / Z;
+  const int f = pd + (int)(i % Z);
+  const int tile = (int)(b / TM), row = (int)(b % TM);
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __ldg(dx0 + ((((int64_t)t * ntiles + tile) * chunks + (f >> 2)) * TM + row) * 4 + (f & 3));
+  dz[i] = s;
 }
 
 // out[b][t][:] = tanh(W_o [h_fwd, h_bwd] + b_o) from the last layer's tc-layout output   (models.py:163)
@@ -563,32 +883,34 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
 }
 }  // namespace
 
-int64_t generator_tc_gc_layer_floats(const wgg_model_cfg* cfg, int64_t B) {
-  TcPlan p;
-  if (!tc_plan(cfg, B, &p)) return 0;
-  return (int64_t)2 * p.T * p.rows * (tc::GC_CHUNKS * 4);
+// ---- training stash of the tcgen05 path (floats):  x0_tc | h_tc[0..L-1] | gc[0..L-1] | h_rm (last layer) ----
+struct TcStash {
+  int64_t x0, h[WGG_MAX_HIDDEN_LAYERS], gc[WGG_MAX_HIDDEN_LAYERS], hrm, total;
+};
+static void tc_stash_layout(const TcPlan& p, int64_t B, TcStash* s) {
+  int64_t off = 0;
+  s->x0 = off; off += p.x0_floats;
+  for (int l = 0; l < p.L; ++l) { s->h[l] = off; off += p.h_floats; }
+  for (int l = 0; l < p.L; ++l) { s->gc[l] = off; off += (int64_t)2 * p.T * p.rows * (tc::GC_CHUNKS * 4); }
+  s->hrm = off; off += (int64_t)p.T * B * 96;
+  s->total = off;
 }
 
-// BPTT of one layer (both directions) on the tcgen05 path: gc (forward stash) + dh_out -> da_rm
-int lstm_tc_bwd_layer(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* lp, int64_t dir_stride, int64_t off_whh,
-                      const float* gc, const float* dh_out, float* da_rm, float* wimg_ws, int64_t B, cudaStream_t st) {
+int64_t generator_tc_stash_floats(const wgg_model_cfg* cfg, int64_t B) {
   TcPlan p;
-  if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "lstm_tc_bwd_layer: unsupported configuration%s");
-  tc::prep_whhT_kernel<<<dim3(8, 2), 256, 0, st>>>(lp, dir_stride, off_whh, wimg_ws);
-  WGG_CHECK_LAUNCH(ctx, "prep_whhT_kernel");
-  constexpr size_t smem = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc::lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_bwd_kernel: cannot reserve shared memory%s");
-    configured = true;
-  }
-  dim3 grid((unsigned)p.ntiles, 2);
-  ProfScope prof(ctx, "lstm_tc_bwd_kernel", st, 2.0 * p.T * (double)B * 2.0 * tc::N4 * tc::HID,
-                 2.0 * p.T * (double)B * 4.0 * (tc::GC_CHUNKS * 4 + tc::HID + tc::HID + tc::N4));
-  tc::lstm_tc_bwd_kernel<<<grid, tc::BWD_THREADS, smem, st>>>(gc, wimg_ws, dh_out, da_rm, p.T, p.ntiles, B, ctx->async_err);
-  WGG_CHECK_LAUNCH(ctx, "lstm_tc_bwd_kernel");
-  return WGG_OK;
+  if (!tc_plan(cfg, B, &p)) return 0;
+  TcStash s;
+  tc_stash_layout(p, B, &s);
+  return s.total;
+}
+
+// row-major last-layer output inside a tcgen05 training stash (operand of the head's weight gradient)
+float* generator_tc_stash_hrm(const wgg_model_cfg* cfg, int64_t B, float* stash) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return nullptr;
+  TcStash s;
+  tc_stash_layout(p, B, &s);
+  return stash + s.hrm;
 }
 
 int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
@@ -596,22 +918,32 @@ int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
   return tc_plan(cfg, B, &p) ? p.total : 0;
 }
 
+// backward workspace: dh ping-pong (2 x T*R*96) | da (2*T*R*192) | W images | dW partials
+static const int kDwCtasPerDir = 74;
+int64_t generator_tc_bwd_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return 0;
+  return 2 * p.h_floats + (int64_t)2 * p.T * p.rows * tc::N4 + 2 * tc::HID * tc::N4 + 4 * tc::HID * tc::N4 +
+         (int64_t)2 * kDwCtasPerDir * 3 * 64 * tc::DW_COLS;
+}
+
 bool generator_tc_supported(const wgg_model_cfg* cfg) {
   TcPlan p;
   return tc_plan(cfg, 1, &p);
 }
 
-// no-grad generator forward on the tcgen05 path.  `layer_off`, `dir_stride`, ... describe the flat parameter layout.
+// Generator forward on the tcgen05 path.  stash == nullptr: no-grad (activations ping-pong in ws); otherwise the
+// grad-carrying forward keeps every layer's input/output (chunk layout), gates and cell states for BPTT.
 int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,
-                         int64_t B, float* out, float* ws, int64_t ws_floats, float* gc_stash, float* const* hseq_rm,
-                         cudaStream_t st) {
+                         int64_t B, float* out, float* ws, int64_t ws_floats, float* stash, cudaStream_t st) {
   TcPlan p;
-  const int64_t gc_layer_floats = generator_tc_gc_layer_floats(cfg, B);
   if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_forward_tc: unsupported configuration%s");
   if (!ws || ws_floats < p.total) return wgg_fail(ctx, WGG_EWORKSPACE, "generator_forward_tc: workspace too small%s");
-  float* x0 = ws;
+  TcStash sl;
+  tc_stash_layout(p, B, &sl);
+  float* x0 = stash ? stash + sl.x0 : ws;
   float* hbuf[2] = {ws + p.x0_floats, ws + p.x0_floats + p.h_floats};
   for (int l = 0; l < p.L; ++l) {
     const int I = l == 0 ? p.pd + p.Z : 96;
@@ -624,20 +956,103 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
   WGG_CHECK_LAUNCH(ctx, "build_x0_tc_kernel");
   const float* in = x0;
   for (int l = 0; l < p.L; ++l) {
-    float* hout = hbuf[l & 1];
-    float* gcl = gc_stash ? gc_stash + (int64_t)l * gc_layer_floats : nullptr;
-    float* hrm = gc_stash ? hseq_rm[l] : nullptr;
+    float* hout = stash ? stash + sl.h[l] : hbuf[l & 1];
+    float* gcl = stash ? stash + sl.gc[l] : nullptr;
+    float* hrm = (stash && l == p.L - 1) ? stash + sl.hrm : nullptr;
+    const float* img = ws + p.img_off[l];
     if (l == 0) {
-      if (gc_stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else WGG_TRY((launch_layer<kKX0 / 4, 0>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      if (stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
+      else WGG_TRY((launch_layer<kKX0 / 4, 0>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     } else {
-      if (gc_stash) WGG_TRY((launch_layer<24, 1>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else WGG_TRY((launch_layer<24, 0>(ctx, in, ws + p.img_off[l], p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      if (stash) WGG_TRY((launch_layer<24, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
+      else WGG_TRY((launch_layer<24, 0>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     }
     in = hout;
   }
   dim3 grid((unsigned)cdiv64(B, 32), (unsigned)((p.T + 7) / 8));
   tc::head_tc_kernel<<<grid, 256, 0, st>>>(in, params + off_wo, params + off_bo, out, p.T, B, p.ntiles, p.C);
   WGG_CHECK_LAUNCH(ctx, "head_tc_kernel");
+  return WGG_OK;
+}
+
+// LSTM stack backward on the tcgen05 path.  dh_rm = d(last layer output) [T][B][2H] row-major (from the head's
+// backward); accumulates all LSTM parameter gradients into dparams and writes dz (may be null).
+int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* dparams,
+                                 const int64_t* layer_off, const int64_t* dir_stride, const int64_t* off_whh,
+                                 const int64_t* off_bih, const int64_t* off_bhh, int64_t B, const float* stash,
+                                 const float* dh_rm, float* dz, float* ws, int64_t ws_floats, cudaStream_t st) {
+  TcPlan p;
+  if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_backward_tc: unsupported configuration%s");
+  if (!ws || ws_floats < generator_tc_bwd_workspace_floats(cfg, B))
+    return wgg_fail(ctx, WGG_EWORKSPACE, "generator_backward_tc: workspace too small%s");
+  TcStash sl;
+  tc_stash_layout(p, B, &sl);
+  float* dh[2] = {ws, ws + p.h_floats};
+  float* da = dh[1] + p.h_floats;
+  float* whhT = da + (int64_t)2 * p.T * p.rows * tc::N4;
+  float* wihT = whhT + 2 * tc::HID * tc::N4;
+  float* part = wihT + 4 * tc::HID * tc::N4;
+  tc::rows_to_chunk_kernel<<<ew_blocks(p.h_floats), 256, 0, st>>>(dh_rm, dh[0], p.T, B, p.ntiles, 96);
+  WGG_CHECK_LAUNCH(ctx, "rows_to_chunk_kernel");
+  int cur = 0;
+  constexpr size_t smem_bwd = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
+  constexpr size_t smem_dx = (size_t)tc::HID * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
+  constexpr size_t smem_dw = (size_t)12 * tc::DW_BLK + 4 * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc::lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::lstm_tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dx) != cudaSuccess ||
+        cudaFuncSetAttribute(tc::lstm_tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw) != cudaSuccess)
+      return wgg_fail(ctx, WGG_ECUDA, "generator_backward_tc: cannot reserve shared memory%s");
+    configured = true;
+  }
+  const int64_t npairs = (int64_t)p.T * p.ntiles;
+  for (int l = p.L - 1; l >= 0; --l) {
+    const int I = l == 0 ? p.pd + p.Z : 96;
+    const float* lp = params + layer_off[l];
+    float* dlp = dparams + layer_off[l];
+    tc::prep_whhT_kernel<<<dim3(8, 2), 256, 0, st>>>(lp, dir_stride[l], off_whh[l], whhT);
+    WGG_CHECK_LAUNCH(ctx, "prep_whhT_kernel");
+    {
+      dim3 grid((unsigned)p.ntiles, 2);
+      ProfScope prof(ctx, "lstm_tc_bwd_kernel", st, 2.0 * p.T * (double)B * 2.0 * tc::N4 * tc::HID,
+                     2.0 * p.T * (double)B * 4.0 * (tc::GC_CHUNKS * 4 + tc::HID + tc::HID + tc::N4));
+      tc::lstm_tc_bwd_kernel<<<grid, tc::BWD_THREADS, smem_bwd, st>>>(stash + sl.gc[l], whhT, dh[cur], da, p.T, p.ntiles, B,
+                                                                      ctx->async_err);
+      WGG_CHECK_LAUNCH(ctx, "lstm_tc_bwd_kernel");
+    }
+    {
+      const float* xin = l == 0 ? stash + sl.x0 : stash + sl.h[l - 1];
+      const int xin_chunks = l == 0 ? kKX0 / 4 : 24;
+      dim3 grid((unsigned)(npairs < kDwCtasPerDir ? npairs : kDwCtasPerDir), 2);
+      ProfScope prof(ctx, "lstm_tc_dw_kernel", st, 2.0 * p.T * (double)B * 2.0 * tc::N4 * (I + tc::HID),
+                     2.0 * p.T * (double)B * 4.0 * (tc::N4 + I + tc::HID));
+      tc::lstm_tc_dw_kernel<<<grid, tc::DW_THREADS, smem_dw, st>>>(da, xin, xin_chunks, stash + sl.h[l], part, p.T, p.ntiles,
+                                                                   ctx->async_err);
+      WGG_CHECK_LAUNCH(ctx, "lstm_tc_dw_kernel");
+      tc::dw_finalize_kernel<<<dim3(48, 2), 256, 0, st>>>(part, (int)grid.x, I, dlp, dir_stride[l], off_whh[l], off_bih[l],
+                                                          off_bhh[l]);
+      WGG_CHECK_LAUNCH(ctx, "dw_finalize_kernel");
+    }
+    if (l > 0 || dz) {
+      const int halves = l == 0 ? 1 : 2;
+      const int out_chunks = l == 0 ? kKX0 / 4 : 24;
+      tc::prep_wihT_kernel<<<dim3(8, 2, halves), 256, 0, st>>>(lp, dir_stride[l], I, wihT);
+      WGG_CHECK_LAUNCH(ctx, "prep_wihT_kernel");
+      int gx = ctx->sm_count / halves;
+      if (gx > npairs) gx = (int)npairs;
+      dim3 grid((unsigned)gx, (unsigned)halves);
+      ProfScope prof(ctx, "lstm_tc_dx_kernel", st, 2.0 * p.T * (double)B * 2.0 * tc::N4 * I,
+                     p.T * (double)B * 4.0 * (2.0 * tc::N4 + I));
+      tc::lstm_tc_dx_kernel<<<grid, tc::DX_THREADS, smem_dx, st>>>(da, wihT, dh[cur ^ 1], p.T, p.ntiles, out_chunks,
+                                                                   ctx->async_err);
+      WGG_CHECK_LAUNCH(ctx, "lstm_tc_dx_kernel");
+      cur ^= 1;
+    }
+  }
+  if (dz) {
+    tc::dz_chunk_kernel<<<(unsigned)cdiv64(B * p.Z, 256), 256, 0, st>>>(dh[cur], dz, p.T, B, p.ntiles, kKX0 / 4, p.pd, p.Z);
+    WGG_CHECK_LAUNCH(ctx, "dz_chunk_kernel");
+  }
   return WGG_OK;
 }
