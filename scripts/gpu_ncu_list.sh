@@ -4,6 +4,8 @@ mkdir -p gpurun_out
 python scripts/one_step.py 4096 tf32 3 > gpurun_out/one_step.log 2>&1 && cat gpurun_out/one_step.log && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/one_step.py 4096 tf32 1 > gpurun_out/ncu_list.log 2>&1
 echo "ncu exit $?"
+python scripts/parse_ncu_list.py gpurun_out/launches.csv gpurun_out/launch_summary.txt "ncu launch list"
+exit 0
 python - <<'PY'
 import csv, collections, re
 rows = []

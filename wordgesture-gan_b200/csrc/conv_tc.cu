@@ -383,7 +383,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int npa
     if (isb) { co = idx - Cout * taps * Cin; col = Ktot; }
     else { co = idx / (taps * Cin); const int r = idx % (taps * Cin); col = (r / Cin) * Cin4 + (r % Cin); }
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[((int64_t)p * 64 + co) * ncols + col];
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) s += __ldg(partial + ((int64_t)p * 64 + co) * ncols + col);
     if (isb) db[co] += s;
     else G[idx] = s;
   }
@@ -509,7 +510,7 @@ int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64
     ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);
     WGG_CHECK_LAUNCH(ctx, "conv_tc_wgrad_kernel");
   }
-  ctc::wgrad_finalize_kernel<<<32, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);
+  ctc::wgrad_finalize_kernel<<<96, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);
   WGG_CHECK_LAUNCH(ctx, "wgrad_finalize_kernel");
   return WGG_OK;
 }

@@ -135,65 +135,76 @@ struct SnArgs {
   int tc_kf[kMaxLayers], tc_nd[kMaxLayers];
 };
 
-__global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restrict__ params, float* __restrict__ uv,
-                                                 float* __restrict__ sn, int training, int with_output) {
+__global__ void __launch_bounds__(1024) sn_kernel(SnArgs a, const float* __restrict__ params, float* __restrict__ uv,
+                                                  float* __restrict__ sn, int training, int with_output) {
   extern __shared__ float sm[];
   const int l = blockIdx.x;
   if (l == a.nl - 1 && !with_output) return;  // get_all_features never calls output_layer (models.py:319-353)
   const int rows = a.rows[l], cols = a.cols[l];
+  const int NT = blockDim.x;
   float* u_s = sm;
   float* v_s = u_s + rows;
   float* wv_s = v_s + cols;
-  float* red = wv_s + rows;  // 33 floats
+  float* red = wv_s + rows;        // 33 floats
+  float* vpart = red + 40;         // [4][cols] partial sums of W^T u over row slices
   const float* __restrict__ W = params + a.off_w[l];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int r = tid; r < rows; r += 256) u_s[r] = uv[a.off_u[l] + r];
-  for (int c = tid; c < cols; c += 256) v_s[c] = uv[a.off_v[l] + c];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  for (int r = tid; r < rows; r += NT) u_s[r] = uv[a.off_u[l] + r];
+  for (int c = tid; c < cols; c += NT) v_s[c] = uv[a.off_v[l] + c];
   __syncthreads();
   if (training) {
-    // v = normalize(W^T u)
-    float ss = 0.f;
-    for (int c = tid; c < cols; c += 256) {
+    // v = normalize(W^T u): 4 row slices x column threads, combined in fixed order (deterministic)
+    const int slice = tid / (NT / 4), ct = tid % (NT / 4);
+    const int r0 = (rows * slice) / 4, r1 = (rows * (slice + 1)) / 4;
+    for (int c = ct; c < cols; c += NT / 4) {
       float s = 0.f;
-      for (int r = 0; r < rows; ++r) s = fmaf(W[(int64_t)r * cols + c], u_s[r], s);
+#pragma unroll 8
+      for (int r = r0; r < r1; ++r) s = fmaf(__ldg(W + (int64_t)r * cols + c), u_s[r], s);
+      vpart[slice * cols + c] = s;
+    }
+    __syncthreads();
+    float ss = 0.f;
+    for (int c = tid; c < cols; c += NT) {
+      const float s = (vpart[c] + vpart[cols + c]) + (vpart[2 * cols + c] + vpart[3 * cols + c]);
       v_s[c] = s;
       ss += s * s;
     }
     const float nv = sqrtf(block_sum(ss, red));
     const float dv = fmaxf(nv, 1e-12f);
-    for (int c = tid; c < cols; c += 256) v_s[c] = v_s[c] / dv;
+    for (int c = tid; c < cols; c += NT) v_s[c] = v_s[c] / dv;
     __syncthreads();
   }
   // wv = W v   (warp per row)
-  for (int r = warp; r < rows; r += 8) {
+  for (int r = warp; r < rows; r += nwarp) {
     float s = 0.f;
-    for (int c = lane; c < cols; c += 32) s = fmaf(W[(int64_t)r * cols + c], v_s[c], s);
+#pragma unroll 4
+    for (int c = lane; c < cols; c += 32) s = fmaf(__ldg(W + (int64_t)r * cols + c), v_s[c], s);
     s = warp_sum(s);
     if (lane == 0) wv_s[r] = s;
   }
   __syncthreads();
   if (training) {
     float ss = 0.f;
-    for (int r = tid; r < rows; r += 256) ss += wv_s[r] * wv_s[r];
+    for (int r = tid; r < rows; r += NT) ss += wv_s[r] * wv_s[r];
     const float nu = sqrtf(block_sum(ss, red));
     const float du = fmaxf(nu, 1e-12f);
-    for (int r = tid; r < rows; r += 256) u_s[r] = wv_s[r] / du;
+    for (int r = tid; r < rows; r += NT) u_s[r] = wv_s[r] / du;
     __syncthreads();
-    for (int r = tid; r < rows; r += 256) uv[a.off_u[l] + r] = u_s[r];
-    for (int c = tid; c < cols; c += 256) uv[a.off_v[l] + c] = v_s[c];
+    for (int r = tid; r < rows; r += NT) uv[a.off_u[l] + r] = u_s[r];
+    for (int c = tid; c < cols; c += NT) uv[a.off_v[l] + c] = v_s[c];
   }
   float sp = 0.f;
-  for (int r = tid; r < rows; r += 256) sp += u_s[r] * wv_s[r];
+  for (int r = tid; r < rows; r += NT) sp += u_s[r] * wv_s[r];
   const float sigma = block_sum(sp, red);
-  for (int r = tid; r < rows; r += 256) sn[a.sn_u[l] + r] = u_s[r];
-  for (int c = tid; c < cols; c += 256) sn[a.sn_v[l] + c] = v_s[c];
+  for (int r = tid; r < rows; r += NT) sn[a.sn_u[l] + r] = u_s[r];
+  for (int c = tid; c < cols; c += NT) sn[a.sn_v[l] + c] = v_s[c];
   if (tid == 0) sn[a.sn_sigma[l]] = sigma;
   float* wf = sn + a.sn_wf[l];
   float* wb = sn + a.sn_wb[l];
   const int n = rows * cols;
   if (a.is_conv[l]) {
     const int ks = a.ks[l], Cin = a.Cin[l];
-    for (int idx = tid; idx < n; idx += 256) {
+    for (int idx = tid; idx < n; idx += NT) {
       const int r = idx / cols, c = idx % cols;
       const int ci = c / ks, k = c % ks;
       const float w = W[idx] / sigma;
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restri
     const int CinC = (Cin + 3) / 4, Cin4 = CinC * 4;
     const int kf = a.tc_kf[l] * 4;                      // forward K (tap-major, channels padded to Cin4)
     float* tf = sn + a.sn_tcf[l];
-    for (int idx = tid; idx < rows * kf; idx += 256) {
+    for (int idx = tid; idx < rows * kf; idx += NT) {
       const int co = idx / kf, kk = idx % kf;
       const int tap = kk / Cin4, ci = kk % Cin4;
       const float w = (tap < ks && ci < Cin) ? W[(co * Cin + ci) * ks + tap] / sigma : 0.f;
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restri
     }
     const int nd = a.tc_nd[l], kd = ks * rows;          // backward-data: N = input channels, K = (flipped tap, co)
     float* td = sn + a.sn_tcd[l];
-    for (int idx = tid; idx < nd * kd; idx += 256) {
+    for (int idx = tid; idx < nd * kd; idx += NT) {
       const int ci = idx / kd, kk = idx % kd;
       const int tp = kk / rows, co = kk % rows;
       const float w = ci < Cin ? W[(co * Cin + ci) * ks + (ks - 1 - tp)] / sigma : 0.f;
@@ -223,12 +234,12 @@ __global__ void __launch_bounds__(256) sn_kernel(SnArgs a, const float* __restri
       td[(kk >> 2) * (nd / 8) * 32 + (ci >> 3) * 32 + (ci & 7) * 4 + (kk & 3)] = __uint_as_float(t32);
     }
   } else {
-    for (int idx = tid; idx < n; idx += 256) wf[idx] = W[idx] / sigma;
+    for (int idx = tid; idx < n; idx += NT) wf[idx] = W[idx] / sigma;
   }
 }
 
 // dW_orig += G/sigma - (<G, W_orig>/sigma^2) u v^T, G given in the forward layout of that layer.
-__global__ void __launch_bounds__(256) sn_grad_kernel(SnArgs a, const float* __restrict__ params,
+__global__ void __launch_bounds__(1024) sn_grad_kernel(SnArgs a, const float* __restrict__ params,
                                                       const float* __restrict__ sn, const float* __restrict__ G,
                                                       float* __restrict__ dparams, int with_output) {
   __shared__ float red[33];
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(256) sn_grad_kernel(SnArgs a, const float* __r
   const int rows = a.rows[l], cols = a.cols[l], n = rows * cols;
   const float* __restrict__ W = params + a.off_w[l];
   const float* __restrict__ g = G + a.g_off[l];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, NT = blockDim.x;
   const int ks = a.ks[l], Cin = a.Cin[l], conv = a.is_conv[l];
   auto gidx = [&](int idx) {
     if (!conv) return idx;
@@ -245,14 +256,15 @@ __global__ void __launch_bounds__(256) sn_grad_kernel(SnArgs a, const float* __r
     return r * cols + (c % ks) * Cin + c / ks;
   };
   float ip = 0.f;
-  for (int idx = tid; idx < n; idx += 256) ip = fmaf(g[gidx(idx)], W[idx], ip);
+#pragma unroll 4
+  for (int idx = tid; idx < n; idx += NT) ip = fmaf(__ldg(g + gidx(idx)), __ldg(W + idx), ip);
   const float inner = block_sum(ip, red);
   const float sigma = sn[a.sn_sigma[l]];
   const float k2 = inner / (sigma * sigma);
   const float* u = sn + a.sn_u[l];
   const float* v = sn + a.sn_v[l];
   float* dW = dparams + a.off_w[l];
-  for (int idx = tid; idx < n; idx += 256) {
+  for (int idx = tid; idx < n; idx += NT) {
     const int r = idx / cols, c = idx % cols;
     dW[idx] += g[gidx(idx)] / sigma - k2 * u[r] * v[c];
   }
@@ -387,9 +399,9 @@ extern "C" int wgg_disc_spectral(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   fill_sn_args(d, &a);
   int maxr = 0, maxc = 0;
   for (int i = 0; i < d.nl; ++i) { maxr = d.L[i].rows > maxr ? d.L[i].rows : maxr; maxc = d.L[i].cols > maxc ? d.L[i].cols : maxc; }
-  const size_t smem = (size_t)(2 * maxr + maxc + 40) * sizeof(float);
+  const size_t smem = (size_t)(2 * maxr + maxc + 80 + 4 * maxc) * sizeof(float);
   if (smem > 48 * 1024) return wgg_fail(ctx, WGG_EUNSUPPORTED, "disc_spectral: layer too wide for the SN kernel%s");
-  sn_kernel<<<d.nl, 256, smem, (cudaStream_t)stream>>>(a, params, uv, sn, training, with_output_layer);
+  sn_kernel<<<d.nl, 1024, smem, (cudaStream_t)stream>>>(a, params, uv, sn, training, with_output_layer);
   WGG_CHECK_LAUNCH(ctx, "sn_kernel");
   return WGG_OK;
 }
@@ -560,7 +572,7 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   if (dparams) {
     SnArgs a;
     fill_sn_args(d, &a);
-    sn_grad_kernel<<<d.nl, 256, 0, st>>>(a, params, sn, G, dparams, dscore ? 1 : 0);
+    sn_grad_kernel<<<d.nl, 1024, 0, st>>>(a, params, sn, G, dparams, dscore ? 1 : 0);
     WGG_CHECK_LAUNCH(ctx, "sn_grad_kernel");
   }
   return WGG_OK;

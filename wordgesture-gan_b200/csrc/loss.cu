@@ -2,6 +2,8 @@
 // Replaces src/gan/losses.py: WassersteinLoss :43,:58; FeatureMatchingLoss :86-93; ReconstructionLoss :120;
 // LatentEncodingLoss :147; KLDivergenceLoss :174-175.  Scalars stay on the device (no .item() sync);
 // reductions are two-stage and deterministic (fixed block partition, fixed summation order).
+#include <stdint.h>
+
 #include "common.cuh"
 
 namespace {
@@ -31,6 +33,30 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(SegTable tb, const floa
     float v;
     if (OP == OP_SUM) v = __ldg(a + j);
     else v = fabsf(__ldg(a + j) - __ldg(b + j));
+    acc = fmaf(tb.w[k], v, acc);
+  }
+  const float s = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// float4 variant: every segment offset / length is a multiple of 4 and the bases are 16-byte aligned
+template <int OP>
+__global__ void __launch_bounds__(256) seg_reduce4_kernel(SegTable tb, const float4* __restrict__ a,
+                                                          const float4* __restrict__ b, float* __restrict__ partial) {
+  __shared__ float red[33];
+  const int64_t total = tb.end[tb.n - 1] >> 2;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (i >= (tb.end[k] >> 2)) ++k;
+    const int64_t j = (tb.off[k] >> 2) + (i - (k ? (tb.end[k - 1] >> 2) : 0));
+    const float4 x = __ldg(a + j);
+    float v;
+    if (OP == OP_SUM) v = (x.x + x.y) + (x.z + x.w);
+    else {
+      const float4 y = __ldg(b + j);
+      v = (fabsf(x.x - y.x) + fabsf(x.y - y.y)) + (fabsf(x.z - y.z) + fabsf(x.w - y.w));
+    }
     acc = fmaf(tb.w[k], v, acc);
   }
   const float s = block_sum(acc, red);
@@ -104,8 +130,11 @@ int seg_reduce(wgg_ctx* ctx, const SegTable& tb, const float* a, const float* b,
                float* out, cudaStream_t st) {
   float* partial = next_partial(ctx);
   if (!partial) return wgg_fail(ctx, WGG_ECUDA, "loss: cannot allocate reduction scratch%s");
-  const int nb = red_blocks(tb.end[tb.n - 1]);
-  seg_reduce_kernel<OP><<<nb, 256, 0, st>>>(tb, a, b, partial);
+  bool vec = (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+  for (int k = 0; k < tb.n; ++k) vec = vec && (tb.off[k] % 4 == 0) && (tb.end[k] % 4 == 0);
+  const int nb = red_blocks(vec ? tb.end[tb.n - 1] / 4 : tb.end[tb.n - 1]);
+  if (vec) seg_reduce4_kernel<OP><<<nb, 256, 0, st>>>(tb, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), partial);
+  else seg_reduce_kernel<OP><<<nb, 256, 0, st>>>(tb, a, b, partial);
   WGG_CHECK_LAUNCH(ctx, "seg_reduce_kernel");
   finalize_kernel<<<1, 256, 0, st>>>(partial, nb, scale, accumulate, out);
   WGG_CHECK_LAUNCH(ctx, "finalize_kernel");

@@ -751,7 +751,8 @@ __global__ void dw_finalize_kernel(const float* __restrict__ partial, int nparts
     const int col = c < I ? c : (c < I + HID ? 96 + (c - I) : 160);
     const int mg = np >> 6, r = np & 63;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[((((int64_t)dir * nparts + p) * 3 + mg) * 64 + r) * DW_COLS + col];
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) s += __ldg(partial + ((((int64_t)dir * nparts + p) * 3 + mg) * 64 + r) * DW_COLS + col);
     if (c < I) o[(int64_t)prow * I + c] += s;
     else if (c < I + HID) o[off_whh + (int64_t)prow * HID + (c - I)] += s;
     else { o[off_bih + prow] += s; o[off_bhh + prow] += s; }
@@ -1030,7 +1031,7 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
       tc::lstm_tc_dw_kernel<<<grid, tc::DW_THREADS, smem_dw, st>>>(da, xin, xin_chunks, stash + sl.h[l], part, p.T, p.ntiles,
                                                                    ctx->async_err);
       WGG_CHECK_LAUNCH(ctx, "lstm_tc_dw_kernel");
-      tc::dw_finalize_kernel<<<dim3(48, 2), 256, 0, st>>>(part, (int)grid.x, I, dlp, dir_stride[l], off_whh[l], off_bih[l],
+      tc::dw_finalize_kernel<<<dim3(72, 2), 256, 0, st>>>(part, (int)grid.x, I, dlp, dir_stride[l], off_whh[l], off_bih[l],
                                                           off_bhh[l]);
       WGG_CHECK_LAUNCH(ctx, "dw_finalize_kernel");
     }
