@@ -373,6 +373,143 @@ __global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient, 64-input-channel layers, full-rate formulation: the transposed problem
+//     G^T[(tap, ci)][co] = sum_t in[t + tap - pad][ci] * dpre[t][co]
+// with M = 128 = TWO taps x 64 input channels per MMA (M = 64 MMAs run far below the M = 128 rate).  The A operand
+// is a 4-block MN-major tile [x_b0, x_b1, x'_b0, x'_b1] where x' is a second copy of the input tile stored one
+// row earlier, so that one start address reads tap j from the first copy and tap j+1 from the second; B = dpre
+// (N = co).  The bias gradient is one M = 64 MMA per k-step with A = ones.  Single-stage tiles (139 KB).
+// ---------------------------------------------------------------------------------------------
+constexpr int W2_THREADS = 288;  // warp 0: MMA issuer; warps 1..8: producers, then TMEM read-out
+
+__device__ __forceinline__ uint64_t make_desc_mn_lbo(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
+constexpr int W2_STAGE = 6 * W_BLK;  // x (4 blocks: two copies) + dpre (2 blocks)
+
+__global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_one = smem + 2 * W2_STAGE;   // 2 blocks x 8 rows of ones (every k-step reads the same 8 rows)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + 2048);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_EMPTY = [&](int s) { return bar0 + 16u + 8u * s; };
+  const uint32_t BAR_DONE = bar0 + 32u;
+  {
+    float4* z = reinterpret_cast<float4*>(smem);
+    for (int i = tid; i < 2 * W2_STAGE / 16; i += W2_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* o = reinterpret_cast<float4*>(s_one);
+    for (int i = tid; i < 2048 / 16; i += W2_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR_FULL(s), 256);
+      mbar_init(BAR_EMPTY(s), 1);
+    }
+    mbar_init(BAR_DONE, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int Cout = a.CoutC * 4;
+  const int npairs = (a.taps + 1) / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t id_main = make_idesc(128, Cout, 1, 1), id_bias = make_idesc(64, Cout, 1, 1);
+      const uint64_t od = make_desc_mn_lbo(smem_u32(s_one), 1024);
+      int n = 0;
+      bool ok = true;
+      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 26)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t x0 = smem_u32(smem) + st * W2_STAGE, d0 = x0 + 4 * W_BLK;
+        for (int ks = 0; ks < T / 8; ++ks) {
+          const uint32_t acc = (n | ks) ? 1u : 0u;
+          const uint64_t bd = make_desc_mn(d0 + (PAD_ROWS + 8 * ks) * 128);
+          for (int p = 0; p < npairs; ++p)
+            mma_tf32_ss(tmem_base + (uint32_t)(p * Cout), make_desc_mn(x0 + (PAD_ROWS + 2 * p - a.pad + 8 * ks) * 128), bd,
+                        id_main, acc);
+          mma_tf32_ss(tmem_base + (uint32_t)(npairs * Cout), od, bd, id_bias, acc);
+        }
+        mma_commit(BAR_EMPTY(st));
+      }
+      if (ok) mma_commit(BAR_DONE);
+    }
+  } else {
+    const int ptid = tid - 32;  // 0..255
+    int n = 0;
+    bool ok = true;
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      const int st = n & 1;
+      if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, a.gerr, 27)) { ok = false; break; }
+      const uint32_t x0 = smem_u32(smem) + st * W2_STAGE, d0 = x0 + 4 * W_BLK;
+      const float4* sd = reinterpret_cast<const float4*>(a.dpre) + b * (int64_t)a.CoutC * T;
+      for (int i = ptid; i < a.CoutC * T; i += 256) cp_async16(d0 + w_off(i % T + PAD_ROWS, i / T), sd + i);
+      const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)16 * T;
+      for (int i = ptid; i < 16 * T; i += 256) {
+        const int q = i / T, t = i % T;
+        cp_async16(x0 + w_off(t + PAD_ROWS, q), si + i);                   // copy 1: row t + 2
+        cp_async16(x0 + 2 * W_BLK + w_off(t + PAD_ROWS - 1, q), si + i);   // copy 2: one row earlier (= tap + 1)
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_async_smem();
+      mbar_arrive(BAR_FULL(st));
+    }
+    if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 28)) {
+      tc_fence_after();
+      // D_p[m = tapbit*64 + ci][co] (M = 128: lane = m).  Two warps per TMEM quarter split the co columns.
+      const int quarter = warp & 3, chalf = (warp - 1) >> 2;
+      const int m = quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float* prow = a.partial + (int64_t)blockIdx.x * 64 * a.ncols;
+      for (int p = 0; p < npairs; ++p) {
+        const int tap = 2 * p + (m >> 6), ci = m & 63;
+        for (int c0 = chalf * 16; c0 < Cout; c0 += 32) {
+          float r[16];
+          tmem_ld16(taddr + p * Cout + c0, r);
+          if (tap < a.taps) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) prow[(int64_t)(c0 + i) * a.ncols + tap * 64 + ci] = r[i];
+          }
+        }
+      }
+      // bias: every row of the M = 64 accumulator holds db[co]; rows < 16 of quarter 0 are lanes 0..15
+      for (int c0 = chalf * 16; c0 < Cout; c0 += 32) {
+        float r[16];
+        tmem_ld16(taddr + npairs * Cout + c0, r);
+        if (quarter == 0 && lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) prow[(int64_t)(c0 + i) * a.ncols + a.taps * 64] = r[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // G[co][(tap,ci)] = sum_cta partial[cta][co][tap*Cin4 + ci];  db[co] += sum_cta partial[cta][co][Ktot]
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int nparts, int ncols, int Cout, int Cin,
                                       int Cin4, int taps, int Ktot, float* __restrict__ G, float* __restrict__ db) {
@@ -507,7 +644,18 @@ int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64
   {
     ProfScope prof(ctx, "conv_tc_wgrad_kernel", st, 2.0 * (double)B * ctc::T * Cout * (double)(taps * Cin),
                    (double)B * ctc::T * 4.0 * (Cout + CinC * 4), "conv_tc_wgrad_kernel");
-    ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);
+    if (CinC == 16) {
+      const size_t smem2 = (size_t)2 * ctc::W2_STAGE + 2048 + 8 * 8 + 16;
+      static bool configured2 = false;
+      if (!configured2) {
+        if (cudaFuncSetAttribute(ctc::conv_tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+          return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad2_kernel: cannot reserve shared memory%s");
+        configured2 = true;
+      }
+      ctc::conv_tc_wgrad2_kernel<<<grid, ctc::W2_THREADS, smem2, st>>>(a);
+    } else {
+      ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);
+    }
     WGG_CHECK_LAUNCH(ctx, "conv_tc_wgrad_kernel");
   }
   ctc::wgrad_finalize_kernel<<<96, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);

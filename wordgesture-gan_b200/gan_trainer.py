@@ -89,6 +89,38 @@ class WordGestureGANTrainer:
         return fake, total, {"cycle2_wgan": wgan, "cycle2_feat": feat, "cycle2_rec": rec, "cycle2_kld": kld,
                              "cycle2_total": total}
 
+    def cycles_tensors(self, prototype, real_gesture, z: Optional[torch.Tensor] = None,
+                       eps_recover: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+        """Cycle 1 and cycle 2 together, with ONE generator call on the stacked batch [z ; z_enc] (the two cycles'
+        generator passes are independent, so stacking them is exact and doubles the SM fill of the persistent
+        recurrent kernels; autograd then runs one generator backward for both).  The three normal draws are made
+        in the reference's order (trainer.py:105, :118 via models.py:85, :161) before any of them is consumed.
+        Returns (fake1, fake2, total1, total2, dict1, dict2) with the same values as cycle1_tensors / cycle2_tensors."""
+        tc = self.training_config
+        B = prototype.size(0)
+        Z = self.model_config.latent_dim
+        if z is None:
+            z = torch.randn(B, Z, device=self.device)
+        if eps_recover is None:
+            eps_recover = torch.randn(B, Z, device=self.device)
+        if eps is None:
+            eps = torch.randn(B, Z, device=self.device)
+        z_enc, mu, log_var = self.encoder(real_gesture, eps)
+        fake = self.generator(torch.cat([prototype, prototype], 0), torch.cat([z, z_enc], 0))
+        fake1, fake2 = fake[:B], fake[B:]
+        wgan1, feat1 = self._adversarial_terms(self.discriminator_1, fake1, real_gesture)
+        with torch.no_grad():
+            z_rec, _, _ = self.encoder(fake1, eps_recover)
+        lat = self.latent_encoding_loss(z, z_rec)
+        total1 = wgan1 + tc.lambda_feat * feat1 + tc.lambda_lat * lat
+        wgan2, feat2 = self._adversarial_terms(self.discriminator_2, fake2, real_gesture)
+        rec = self.reconstruction_loss(real_gesture, fake2)
+        kld = self.kl_divergence_loss(mu, log_var)
+        total2 = wgan2 + tc.lambda_feat * feat2 + tc.lambda_rec * rec + tc.lambda_kld * kld
+        d1 = {"cycle1_wgan": wgan1, "cycle1_feat": feat1, "cycle1_lat": lat, "cycle1_total": total1}
+        d2 = {"cycle2_wgan": wgan2, "cycle2_feat": feat2, "cycle2_rec": rec, "cycle2_kld": kld, "cycle2_total": total2}
+        return fake1, fake2, total1, total2, d1, d2
+
     def train_generator_step_cycle1(self, prototype: torch.Tensor, real_gesture: torch.Tensor
                                     ) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, float]]:
         fake, total, d = self.cycle1_tensors(prototype, real_gesture)

@@ -90,8 +90,8 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
 
     trainer.optimizer_G.zero_grad()
     trainer.optimizer_E.zero_grad()
-    _, loss1, d1 = trainer.cycle1_tensors(prototype, real_gesture, z=draw(), eps_recover=draw())
-    _, loss2, d2 = trainer.cycle2_tensors(prototype, real_gesture, eps=draw())
+    z_c1, eps_rec, eps_c2 = draw(), draw(), draw()  # reference order: cycle-1 z, its recovery eps, cycle-2 eps
+    _, _, loss1, loss2, d1, d2 = trainer.cycles_tensors(prototype, real_gesture, z=z_c1, eps_recover=eps_rec, eps=eps_c2)
     # the discriminators' own weight gradients of this backward are never used (the reference zeroes them before
     # the next critic step, utils.py:75,96): skip computing them, keep d(loss)/d(fake gesture)
     _lib.SKIP_DISC_WEIGHT_GRADS = True
