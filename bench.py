@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying the captured CUDA graph")
-    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32", "tf32x3"],
                     help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); fp32: FMA only")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -230,8 +230,8 @@ def main():
     prof_kernel = args.profile_kernel
     shares = {}
     if prof_kernel == "auto":
-        for cand in ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel", "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel",
-                     "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel"):
+        for cand in ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel", "lstm_tc_dw_kernel", "lstm_tc_dx_kernel",
+                     "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel"):
             _lib.profile_enable(dev, cand)
             step_eager()
             shares[cand] = _lib.profile_read(dev)["ms"]
@@ -297,7 +297,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if args.math == "tf32" else "f32",
+        "dtype": {"tf32": "tf32", "tf32x3": "tf32x3", "fp32": "f32"}[args.math],
         "data": "synthetic",
         "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
                                "T=128), BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
