@@ -33,7 +33,8 @@ constexpr int CHUNK_BYTES_W = (N4 / 8) * 128;  // 3072: one 16-byte K chunk of t
 constexpr int SB_CHUNKS = 8;                   // K chunks per ring stage (32 floats)
 constexpr int SB_BYTES = SB_CHUNKS * CHUNK_BYTES_A;  // 16384
 constexpr int NSTAGE = 5;
-constexpr int NTHREADS = 320;                  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int NTHREADS = 576;                  // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
+constexpr int EPI_WARPS = 16;
 constexpr int ACC_COLS = N4;                   // TMEM columns per accumulator buffer
 constexpr int TMEM_COLS = 512;
 
@@ -109,6 +110,11 @@ __global__ void build_x0_tc_kernel(const float* __restrict__ proto, const float*
 //   h_rm : [T][B][2H] row-major, un-rounded fp32 (operand of the weight-gradient GEMMs and of the output head)
 constexpr int GC_CHUNKS = HID + HID / 4;  // 60
 
+// debug: per-step clock64 stamps of CTA (0,0) (enabled through wgg_debug_lstm_ts)
+__device__ long long g_fwd_ts[128 * 8];
+__device__ int g_fwd_ts_on = 0;
+#define TS(k) do { if (ts_on) g_fwd_ts[(step & 127) * 8 + (k)] = clock64(); } while (0)
+
 template <int KXC, int STASH>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
                                                                   const float* __restrict__ wimg, int64_t img_stride,
@@ -144,7 +150,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
     constexpr int n4 = (WX_BYTES + WH_BYTES) / 16;
     for (int i = tid; i < n4; i += NTHREADS) dst[i] = __ldg(src + i);
     const float* bsrc = wimg + dir * img_stride + (WX_BYTES + WH_BYTES) / 4;
-    for (int i = tid; i < N4; i += NTHREADS) s_bias[i] = __ldg(bsrc + i);
+    // bias pre-scaled for the exponent form of the gates: -b log2(e) for i, f, o and -2 b log2(e) for g
+    for (int i = tid; i < N4; i += NTHREADS) s_bias[i] = __ldg(bsrc + i) * ((i & 3) == 2 ? -2.f * kLog2e : -kLog2e);
   }
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -153,9 +160,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR_ACC_FULL(b), 1);
-      mbar_init(BAR_ACC_EMPTY(b), 8);
+      mbar_init(BAR_ACC_EMPTY(b), EPI_WARPS);
     }
-    mbar_init(BAR_H, 8);
+    mbar_init(BAR_H, EPI_WARPS);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -170,6 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const bool ts_on = g_fwd_ts_on && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0) {
     // ===== producer: stream x_t sub-blocks =====
@@ -203,6 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
         const uint32_t use = (uint32_t)(step >> 1);  // how many times this buffer has been used before
         if (!mbar_wait(BAR_ACC_EMPTY(b), (use & 1) ^ 1, s_abort, gerr, 2)) break;
         tc_fence_after();
+        TS(0);
         const uint32_t tacc = tmem_base + (uint32_t)(b * ACC_COLS);
 #pragma unroll 1
         for (int sb = 0; sb < NSB; ++sb) {
@@ -219,9 +228,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         if (!ok) break;
+        TS(1);
         if (step > 0) {
           if (!mbar_wait(BAR_H, (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) break;
           tc_fence_after();
+          TS(2);
 #pragma unroll
           for (int j = 0; j < KH_CHUNKS / 2; ++j) {
             const uint64_t ad = make_desc(hs + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
@@ -230,82 +241,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           }
         }
         mma_commit(BAR_ACC_FULL(b));
+        TS(3);
       }
     }
   } else {
-    // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    // ===== epilogue: 16 warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 (12 hidden units each) =====
+    // Four warps per scheduler keep the MUFU pipe (5 EX2 + 2 RCP per cell) and the FMA pipe busy at the same time.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    float c[24];
+    float c[12];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) c[i] = 0.f;
+    for (int i = 0; i < 12; ++i) c[i] = 0.f;
     float4* hs4 = reinterpret_cast<float4*>(s_h);
     for (int step = 0; step < T; ++step) {
       const int t = dir ? T - 1 - step : step;
       const int b = step & 1;
       if (!mbar_wait(BAR_ACC_FULL(b), (uint32_t)((step >> 1) & 1), s_abort, gerr, 5)) break;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + half * 96);
+      if (warp == 2 && lane == 0) TS(4);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + part * 48);
       float4* hg4 = reinterpret_cast<float4*>(hout) +
                     (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * (TM) + row;
+      float4* gc4 = nullptr;
+      if (STASH)
+        gc4 = reinterpret_cast<float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
+      float v[48];
+      {
+        float v0[16], v1[16], v2[16];
+        tmem_ld16(taddr, v0);
+        tmem_ld16(taddr + 16, v1);
+        tmem_ld16(taddr + 32, v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i] = v0[i]; v[16 + i] = v1[i]; v[32 + i] = v2[i]; }
+      }
+      // accumulator fully read by this warp: hand the buffer back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
+      if (warp == 2 && lane == 0) TS(5);
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        if (ch == 2) {  // accumulator fully read by this warp: hand the buffer back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
-        }
-        float hv[8], hraw[8];
-        float4* gc4 = nullptr;
-        if (STASH)
-          gc4 = reinterpret_cast<float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
+        const int chunk = part * 3 + ch;              // K chunk (4 hidden units) of this direction's h
+        float hv[4], hraw[4];
 #pragma unroll
-        for (int uu = 0; uu < 8; ++uu) {
-          const int ul = ch * 8 + uu;                 // unit index inside this thread's 24
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (half * 24 + ul) * 4);
+        for (int uu = 0; uu < 4; ++uu) {
+          const int ul = ch * 4 + uu;                 // unit index inside this thread's 12
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (part * 12 + ul) * 4);
           // 5 gate non-linearities with 5 EX2 + 2 RCP (instead of 5 + 5): the sigmoids / tanh of a unit share their
-          // reciprocals.  sigma(x) = 1/(1+E(x)), tanh(x) = (1-E2(x))/(1+E2(x)) with E = exp(-x), E2 = exp(-2x);
-          // arguments are clamped to +-28 so that products of three (1+E) stay finite (sigma(-28) = 7e-13).
-          const float ai = fminf(fmaxf(v[4 * uu + 0] + bb.x, -28.f), 28.f);
-          const float af = fminf(fmaxf(v[4 * uu + 1] + bb.y, -28.f), 28.f);
-          const float ag = fminf(fmaxf(v[4 * uu + 2] + bb.z, -14.f), 14.f);
-          const float ao = fminf(fmaxf(v[4 * uu + 3] + bb.w, -28.f), 28.f);
-          const float pi = 1.f + __expf(-ai), pf = 1.f + __expf(-af), eg = __expf(-2.f * ag), pg = 1.f + eg;
-          const float r1 = __fdividef(1.f, pf * pi * pg);
-          const float ig = r1 * pf * pg;
-          const float fg = r1 * pi * pg;
-          const float gg = (1.f - eg) * r1 * pf * pi;
-          c[ul] = fg * c[ul] + ig * gg;
-          const float cl = fminf(fmaxf(c[ul], -14.f), 14.f);
-          const float ec = __expf(-2.f * cl), pc = 1.f + ec, po = 1.f + __expf(-ao);
-          const float r2 = __fdividef(1.f, po * pc);
+          // reciprocals.  sigma(x) = 1/(1+E), E = 2^(-x log2 e); tanh(x) = (1-E2)/(1+E2), E2 = 2^(-2x log2 e).  The
+          // scale and the (pre-scaled) bias are one FMA; exponents are capped at 40 so that the product of three
+          // (1+E) stays finite (2^-40 = 9e-13 is below fp32 resolution of the gate values).
+          const float Ei = ex2_fast(fminf(fmaf(v[4 * ul + 0], -kLog2e, bb.x), 40.f));
+          const float Ef = ex2_fast(fminf(fmaf(v[4 * ul + 1], -kLog2e, bb.y), 40.f));
+          const float Eg = ex2_fast(fminf(fmaf(v[4 * ul + 2], -2.f * kLog2e, bb.z), 40.f));
+          const float Eo = ex2_fast(fminf(fmaf(v[4 * ul + 3], -kLog2e, bb.w), 40.f));
+          const float pi = 1.f + Ei, pf = 1.f + Ef, pg = 1.f + Eg, po = 1.f + Eo;
+          const float pfpi = pf * pi;
+          const float r1 = rcp_fast(pfpi * pg);
+          const float tg = r1 * pg;
+          const float ig = tg * pf;
+          const float fg = tg * pi;
+          const float qg = r1 * pfpi;                 // 1 / (1 + Eg)
+          const float gg = fmaf(-Eg, qg, qg);         // tanh
+          c[ul] = fmaf(fg, c[ul], ig * gg);
+          const float Ec = ex2_fast(fminf(c[ul] * (-2.f * kLog2e), 40.f));
+          const float pc = 1.f + Ec;
+          const float r2 = rcp_fast(po * pc);
           const float og = r2 * pc;
-          hraw[uu] = (1.f - ec) * r2;  // = og * tanh(c)
+          hraw[uu] = fmaf(-Ec, r2, r2);               // = og * tanh(c)
           hv[uu] = rna_tf32(hraw[uu]);
-          if (STASH) gc4[(int64_t)(half * 24 + ul) * TM] = make_float4(ig, fg, gg, og);
+          if (STASH) gc4[(int64_t)(part * 12 + ul) * TM] = make_float4(ig, fg, gg, og);
         }
-#pragma unroll
-        for (int k2 = 0; k2 < 2; ++k2) {
-          const int chunk = half * 6 + ch * 2 + k2;   // K chunk (4 hidden units) of this direction's h
-          const float4 q = make_float4(hv[4 * k2], hv[4 * k2 + 1], hv[4 * k2 + 2], hv[4 * k2 + 3]);
-          hs4[chunk * TM + row] = q;                  // next step's A operand
-          hg4[(int64_t)chunk * TM] = q;               // next layer's input (coalesced: lane = row)
-          if (STASH) {
-            const int ul = ch * 8 + 4 * k2;
-            gc4[(int64_t)(HID + chunk) * TM] = make_float4(c[ul], c[ul + 1], c[ul + 2], c[ul + 3]);
-            const int64_t bidx = (int64_t)tile * TM + row;
-            if (h_rm != nullptr && bidx < B)
-              *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
-                  make_float4(hraw[4 * k2], hraw[4 * k2 + 1], hraw[4 * k2 + 2], hraw[4 * k2 + 3]);
-          }
+        const float4 q = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        hs4[chunk * TM + row] = q;                    // next step's A operand
+        hg4[(int64_t)chunk * TM] = q;                 // next layer's input (coalesced: lane = row)
+        if (STASH) {
+          gc4[(int64_t)(HID + chunk) * TM] = make_float4(c[ch * 4], c[ch * 4 + 1], c[ch * 4 + 2], c[ch * 4 + 3]);
+          const int64_t bidx = (int64_t)tile * TM + row;
+          if (h_rm != nullptr && bidx < B)
+            *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
+                make_float4(hraw[0], hraw[1], hraw[2], hraw[3]);
         }
       }
+      if (warp == 2 && lane == 0) TS(6);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_H);
+      if (warp == 2 && lane == 0) TS(7);
     }
   }
   tc_fence_before();
@@ -1056,4 +1079,13 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
     WGG_CHECK_LAUNCH(ctx, "dz_chunk_kernel");
   }
   return WGG_OK;
+}
+
+// debug hook (not part of include/wgg.h): enable != 0 arms the per-step clock stamps of lstm_tc_fwd_kernel CTA (0,0);
+// out (host, 1024 int64) receives the stamps of the most recent launch.
+extern "C" __attribute__((visibility("default"))) int wgg_debug_lstm_ts(int enable, long long* out) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, tc::g_fwd_ts, sizeof(long long) * 1024);
+  cudaMemcpyToSymbol(tc::g_fwd_ts_on, &enable, sizeof(int));
+  return 0;
 }
