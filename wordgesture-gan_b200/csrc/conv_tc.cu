@@ -100,35 +100,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int n = 0;
-      const uint32_t wb = smem_u32(s_w);
-      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-        const int st = n & 1;
-        if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 12)) break;
-        if (!mbar_wait(BAR_ACC_EMPTY, (n & 1) ^ 1, s_abort, a.gerr, 13)) break;
-        tc_fence_after();
-        const uint32_t ab = smem_u32(s_in + st * in_bytes);
+    // MMA issuer: warp-uniform loop, one elected lane issues (operands stay in uniform registers)
+    int n = 0;
+    const uint32_t wb = smem_u32(s_w);
+    const uint64_t bd0 = make_desc(wb, WCS, 128);
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      const int st = n & 1;
+      if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 12)) break;
+      if (!mbar_wait(BAR_ACC_EMPTY, (n & 1) ^ 1, s_abort, a.gerr, 13)) break;
+      tc_fence_after();
+      const uint32_t ab = smem_u32(s_in + st * in_bytes);
+      if (elect_one()) {
         uint32_t first = 0;
         if (a.CinC == 1) {
+          const uint64_t ad0 = make_desc(ab + a.tap_row0 * 16, 16, 128);
           for (int jp = 0; jp < a.taps_p / 2; ++jp) {
-            const uint64_t ad = make_desc(ab + (a.tap_row0 + 2 * jp) * 16, 16, 128);
-            const uint64_t bd = make_desc(wb + (2 * jp) * WCS, WCS, 128);
-            mma_tf32_ss(tmem_base, ad, bd, idesc, first);
+            mma_tf32_ss(tmem_base, ad0 + (uint64_t)(2 * jp), bd0 + (uint64_t)(2 * jp * (WCS >> 4)), idesc, first);
             first = 1;
           }
         } else {
-          for (int j = 0; j < a.taps; ++j)
-            for (int p = 0; p < a.CinC / 2; ++p) {
-              const uint64_t ad = make_desc(ab + (2 * p) * CS + (a.tap_row0 + j) * 16, CS, 128);
-              const uint64_t bd = make_desc(wb + (j * a.CinC + 2 * p) * WCS, WCS, 128);
+          uint64_t ad_j = make_desc(ab + a.tap_row0 * 16, CS, 128), bd = bd0;
+          const uint64_t a_step = (uint64_t)((2 * CS) >> 4), b_step = (uint64_t)((2 * WCS) >> 4);
+          for (int j = 0; j < a.taps; ++j, ++ad_j) {
+            uint64_t ad = ad_j;
+#pragma unroll 8
+            for (int p = 0; p < a.CinC / 2; ++p, ad += a_step, bd += b_step) {
               mma_tf32_ss(tmem_base, ad, bd, idesc, first);
               first = 1;
             }
+          }
         }
         mma_commit(BAR_EMPTY(st));
         mma_commit(BAR_ACC_FULL);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -215,8 +220,6 @@ struct WgradArgs {
   float* partial;     // [grid][64][ncols]
   int64_t B;
   int CoutC, CinC, taps, pad, ncols;
-  int dbg_mask;  // debug bisect: bit0 skip tap MMAs, bit1 skip ones MMA, bit2 only k-step 5, bit3 only tap 2
-  int dump_all;  // debug: write all 128 TMEM lanes ([grid][128][ncols]) instead of the 64 accumulator rows
   int* gerr;
 };
 
@@ -244,123 +247,106 @@ __device__ __forceinline__ uint32_t w_off(int r, int q) {
   return (uint32_t)((q >> 3) * W_BLK + r * 128 + ((((q & 7) >> 1) ^ (r & 3)) << 5) + ((q & 1) << 4));
 }
 
+// First conv layer (Cin <= 4): im2col rows [x4[t-pad], ..., x4[t-pad+taps-1], 0...] make one 32-wide B block, so a
+// sample is 16 k-steps of one M = 64 (co) x N = 32 MMA plus the N = 8 bias MMA.  The kernel is bound by load latency,
+// not by the tensor pipe: four stages, each owned by one producer warp, keep four samples in flight.
+constexpr int W1_NST = 4;
+constexpr int W1_STAGE = 3 * W_BLK;  // dpre (2 blocks) + im2col rows (1 block)
+
 __global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_dp = smem;                       // 2 stages x 2 blocks
-  uint8_t* s_in = s_dp + 2 * 2 * W_BLK;       // 2 stages x 2 blocks
-  uint8_t* s_one = s_in + 2 * 2 * W_BLK;      // 1 block of ones
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + W_BLK);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  uint8_t* s_one = smem + W1_NST * W1_STAGE;  // 8 rows of ones
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + 1024);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * W1_NST + 1);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(s_bar);
   auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
-  const uint32_t BAR_DONE = bar0 + 8u * 4;
+  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (W1_NST + s); };
+  const uint32_t BAR_DONE = bar0 + 8u * (2 * W1_NST);
   {
     float4* z = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < 8 * W_BLK / 16; i += W_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < W1_NST * W1_STAGE / 16; i += W_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* o = reinterpret_cast<float4*>(s_one);
-    for (int i = tid; i < W_BLK / 16; i += W_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = tid; i < 1024 / 16; i += W_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 128); mbar_init(BAR_EMPTY(s), 1); }
+    for (int s = 0; s < W1_NST; ++s) { mbar_init(BAR_FULL(s), 32); mbar_init(BAR_EMPTY(s), 1); }
     mbar_init(BAR_DONE, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 64);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const bool im2col = a.CinC == 1;
-  const int Ntap = im2col ? 32 : 64;                  // N of one B group
-  const int ngroups = im2col ? 1 : a.taps;
-  const int Ktot = ngroups * Ntap;
+  constexpr int Ktot = 32;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int n = 0;
-      bool ok = true;
-      const uint32_t one = smem_u32(s_one);
-      const uint32_t id_tap = make_idesc(64, Ntap, 1, 1);
-      const uint32_t id_one = make_idesc(64, 8, 1, 1);
-      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-        const int st = n & 1;
-        if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 22)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t dp = smem_u32(s_dp + st * 2 * W_BLK);
-        const uint32_t in = smem_u32(s_in + st * 2 * W_BLK);
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    int n = 0;
+    bool ok = true;
+    const uint64_t od = make_desc_mn(smem_u32(s_one));
+    const uint32_t id_tap = make_idesc(64, 32, 1, 1);
+    const uint32_t id_one = make_idesc(64, 8, 1, 1);
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      const int st = n % W1_NST;
+      if (!mbar_wait(BAR_FULL(st), (n / W1_NST) & 1, s_abort, a.gerr, 22)) { ok = false; break; }
+      tc_fence_after();
+      const uint32_t dp = smem_u32(smem + st * W1_STAGE);
+      const uint64_t ad0 = make_desc_mn(dp + PAD_ROWS * 128), bd0 = make_desc_mn(dp + 2 * W_BLK + PAD_ROWS * 128);
+      if (elect_one()) {
+#pragma unroll 4
         for (int ks = 0; ks < T / 8; ++ks) {
-          uint32_t acc = (n | ks) ? 1u : 0u;
-          if (a.dbg_mask & 4) { if (ks != 5) continue; acc = 0u; }
-          const uint64_t ad = make_desc_mn(dp + (PAD_ROWS + 8 * ks) * 128);
-          if (!(a.dbg_mask & 1)) {
-            if (im2col) {
-              mma_tf32_ss(tmem_base, ad, make_desc_mn(in + (PAD_ROWS + 8 * ks) * 128), id_tap, acc);
-            } else {
-              for (int j = 0; j < a.taps; ++j) {
-                if ((a.dbg_mask & 8) && j != 2) continue;
-                mma_tf32_ss(tmem_base + (uint32_t)(j * Ntap), ad, make_desc_mn(in + (PAD_ROWS + j - a.pad + 8 * ks) * 128),
-                            id_tap, acc);
-              }
-            }
-          }
-          if (!(a.dbg_mask & 2)) mma_tf32_ss(tmem_base + (uint32_t)Ktot, ad, make_desc_mn(one + 8 * ks * 128), id_one, acc);
+          const uint32_t acc = (n | ks) ? 1u : 0u;
+          mma_tf32_ss(tmem_base, ad0 + (uint64_t)(ks * 64), bd0 + (uint64_t)(ks * 64), id_tap, acc);
+          mma_tf32_ss(tmem_base + (uint32_t)Ktot, ad0 + (uint64_t)(ks * 64), od, id_one, acc);
         }
         mma_commit(BAR_EMPTY(st));
       }
-      if (ok) mma_commit(BAR_DONE);
+      __syncwarp();
     }
+    if (ok && elect_one()) mma_commit(BAR_DONE);
   } else {
-    // ---- producers: fill both operand tiles of a stage with swizzled 16-byte cp.async copies ----
-    const int ptid = tid - 32;  // 0..127
-    int n = 0;
+    // ---- producer warp g fills stage g for samples g, g + 4, ...: swizzled 16-byte cp.async copies ----
+    const int g = warp - 1;
+    int k = 0;
     bool ok = true;
-    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-      const int st = n & 1;
-      if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 21)) { ok = false; break; }
-      const uint32_t dp = smem_u32(s_dp + st * 2 * W_BLK);
-      const uint32_t in = smem_u32(s_in + st * 2 * W_BLK);
+    const uint32_t dp = smem_u32(smem + g * W1_STAGE);
+    const uint32_t in = dp + 2 * W_BLK;
+    for (int64_t b = blockIdx.x + (int64_t)g * gridDim.x; b < a.B; b += (int64_t)W1_NST * gridDim.x, ++k) {
+      if (!mbar_wait(BAR_EMPTY(g), (k & 1) ^ 1, s_abort, a.gerr, 21)) { ok = false; break; }
       const float4* sd = reinterpret_cast<const float4*>(a.dpre) + b * (int64_t)a.CoutC * T;
-      for (int i = ptid; i < a.CoutC * T; i += 128) {
-        const int q = i / T, t = i % T;
-        cp_async16(dp + w_off(t + PAD_ROWS, q), sd + i);
+      // lane -> (4 consecutive rows) x (8 consecutive chunks): 64-byte global segments, conflict-free 512-byte smem rows
+      for (int i = lane; i < a.CoutC * T; i += 32) {
+        const int q = ((i >> 3) / T) * 8 + (i & 7), t = (i >> 3) % T;
+        if (q < a.CoutC) cp_async16(dp + w_off(t + PAD_ROWS, q), sd + q * T + t);
       }
-      const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)a.CinC * T;
-      if (im2col) {
-        // row t of the tile = [x4[t-pad], x4[t-pad+1], ..., x4[t-pad+taps-1], 0...]: chunk index = tap
-        for (int i = ptid; i < a.taps * T; i += 128) {
-          const int j = i / T, t = i % T;
-          const int ts = t + j - a.pad;
-          if (ts >= 0 && ts < T) cp_async16(in + w_off(t + PAD_ROWS, j), si + ts);
-        }
-      } else {
-        for (int i = ptid; i < a.CinC * T; i += 128) {
-          const int q = i / T, t = i % T;
-          cp_async16(in + w_off(t + PAD_ROWS, q), si + i);
-        }
+      const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)T;
+      // row t of the im2col tile = [x4[t-pad], x4[t-pad+1], ..., x4[t-pad+taps-1], 0...]: chunk index = tap
+      for (int i = lane; i < 8 * T; i += 32) {
+        const int j = i & 7, t = i >> 3;
+        const int ts = t + j - a.pad;
+        if (j < a.taps && ts >= 0 && ts < T) cp_async16(in + w_off(t + PAD_ROWS, j), si + ts);
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_async_smem();
-      mbar_arrive(BAR_FULL(st));
+      mbar_arrive(BAR_FULL(g));
     }
     // ---- read-out: M = 64 accumulator rows live in lanes 0..15 of each TMEM quarter ----
     if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 23)) {
       tc_fence_after();
       const int quarter = warp & 3;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      float* dst = a.dump_all ? a.partial + ((int64_t)blockIdx.x * 128 + quarter * 32 + lane) * a.ncols
-                              : a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
-      for (int c0 = 0; c0 < a.ncols; c0 += 16) {
-        float r[16];
-        tmem_ld16(taddr + c0, r);
-        if (lane < 16 || a.dump_all) {
+      float* dst = a.partial + ((int64_t)blockIdx.x * 64 + quarter * 16 + lane) * a.ncols;
+      for (int c0 = 0; c0 < a.ncols; c0 += 8) {
+        float r[8];
+        tmem_ld8(taddr + c0, r);
+        if (lane < 16) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < a.ncols) dst[c0 + i] = r[i];
+          for (int i = 0; i < 8; ++i) dst[c0 + i] = r[i];
         }
       }
     }
@@ -369,7 +355,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -414,7 +400,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
   }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR_FULL(s), 256);
+      mbar_init(BAR_FULL(s), 128);
       mbar_init(BAR_EMPTY(s), 1);
     }
     mbar_init(BAR_DONE, 1);
@@ -431,47 +417,57 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
   const int npairs = (a.taps + 1) / 2;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t id_main = make_idesc(128, Cout, 1, 1), id_bias = make_idesc(64, Cout, 1, 1);
-      const uint64_t od = make_desc_mn_lbo(smem_u32(s_one), 1024);
-      int n = 0;
-      bool ok = true;
-      for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-        const int st = n & 1;
-        if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 26)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t x0 = smem_u32(smem) + st * W2_STAGE, d0 = x0 + 4 * W_BLK;
-        for (int ks = 0; ks < T / 8; ++ks) {
-          const uint32_t acc = (n | ks) ? 1u : 0u;
-          const uint64_t bd = make_desc_mn(d0 + (PAD_ROWS + 8 * ks) * 128);
-          for (int p = 0; p < npairs; ++p)
-            mma_tf32_ss(tmem_base + (uint32_t)(p * Cout), make_desc_mn(x0 + (PAD_ROWS + 2 * p - a.pad + 8 * ks) * 128), bd,
-                        id_main, acc);
-          mma_tf32_ss(tmem_base + (uint32_t)(npairs * Cout), od, bd, id_bias, acc);
-        }
-        mma_commit(BAR_EMPTY(st));
-      }
-      if (ok) mma_commit(BAR_DONE);
-    }
-  } else {
-    const int ptid = tid - 32;  // 0..255
+    // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues
+    const uint32_t id_main = make_idesc(128, Cout, 1, 1), id_bias = make_idesc(64, Cout, 1, 1);
+    const uint64_t od = make_desc_mn_lbo(smem_u32(s_one), 1024);
     int n = 0;
     bool ok = true;
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
       const int st = n & 1;
-      if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, a.gerr, 27)) { ok = false; break; }
+      if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 26)) { ok = false; break; }
+      tc_fence_after();
       const uint32_t x0 = smem_u32(smem) + st * W2_STAGE, d0 = x0 + 4 * W_BLK;
+      // descriptors advance by 8 rows (1024 B -> 64 in the 16-byte address field) per k-step
+      const uint64_t bd0 = make_desc_mn(d0 + PAD_ROWS * 128);
+      const uint64_t ad0 = make_desc_mn(x0 + (PAD_ROWS - a.pad) * 128);
+      if (elect_one()) {
+#pragma unroll 4
+        for (int ks = 0; ks < T / 8; ++ks) {
+          const uint32_t acc = (n | ks) ? 1u : 0u;
+          const uint64_t bd = bd0 + (uint64_t)(ks * 64);
+          for (int p = 0; p < npairs; ++p)
+            mma_tf32_ss(tmem_base + (uint32_t)(p * Cout), ad0 + (uint64_t)(ks * 64 + p * 16), bd, id_main, acc);
+          mma_tf32_ss(tmem_base + (uint32_t)(npairs * Cout), od, bd, id_bias, acc);
+        }
+        mma_commit(BAR_EMPTY(st));
+      }
+      __syncwarp();
+    }
+    if (ok && elect_one()) mma_commit(BAR_DONE);
+  } else {
+    // two producer groups (4 warps each); group g owns stage g and the samples g, g + 2, ... so that two samples'
+    // loads are always in flight (a group blocks on its own copies only)
+    const int ptid = (tid - 32) & 127, g = (tid - 32) >> 7;
+    int k = 0;
+    bool ok = true;
+    const uint32_t x0 = smem_u32(smem) + g * W2_STAGE, d0 = x0 + 4 * W_BLK;
+    for (int64_t b = blockIdx.x + (int64_t)g * gridDim.x; b < a.B; b += 2 * (int64_t)gridDim.x, ++k) {
+      if (!mbar_wait(BAR_EMPTY(g), (uint32_t)((k & 1) ^ 1), s_abort, a.gerr, 27)) { ok = false; break; }
+      // lane -> (4 consecutive rows) x (8 consecutive chunks): 64-byte global segments, conflict-free 512-byte smem rows
       const float4* sd = reinterpret_cast<const float4*>(a.dpre) + b * (int64_t)a.CoutC * T;
-      for (int i = ptid; i < a.CoutC * T; i += 256) cp_async16(d0 + w_off(i % T + PAD_ROWS, i / T), sd + i);
+      for (int i = ptid; i < a.CoutC * T; i += 128) {
+        const int q = ((i >> 3) / T) * 8 + (i & 7), t = (i >> 3) % T;
+        cp_async16(d0 + w_off(t + PAD_ROWS, q), sd + q * T + t);
+      }
       const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)16 * T;
-      for (int i = ptid; i < 16 * T; i += 256) {
-        const int q = i / T, t = i % T;
-        cp_async16(x0 + w_off(t + PAD_ROWS, q), si + i);                   // copy 1: row t + 2
-        cp_async16(x0 + 2 * W_BLK + w_off(t + PAD_ROWS - 1, q), si + i);   // copy 2: one row earlier (= tap + 1)
+      for (int i = ptid; i < 16 * T; i += 128) {
+        const int q = ((i >> 3) / T) * 8 + (i & 7), t = (i >> 3) % T;
+        cp_async16(x0 + w_off(t + PAD_ROWS, q), si + q * T + t);                   // copy 1: row t + 2
+        cp_async16(x0 + 2 * W_BLK + w_off(t + PAD_ROWS - 1, q), si + q * T + t);   // copy 2: one row earlier (= tap + 1)
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_async_smem();
-      mbar_arrive(BAR_FULL(st));
+      mbar_arrive(BAR_FULL(g));
     }
     if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 28)) {
       tc_fence_after();
@@ -623,17 +619,15 @@ int64_t conv_tc_wgrad_ws_floats(wgg_ctx* ctx, int ncols_max) { return (int64_t)c
 int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int Cout, int Cin, int taps,
                          int pad, float* G, float* db, float* ws, cudaStream_t st) {
   const int CoutC = Cout / 4, CinC = (Cin + 3) / 4;
-  if (Cout > 64 || (CinC != 1 && CinC != 16) || taps > 8 || (CinC == 1 && taps > 8))
+  if (Cout > 64 || CoutC % 8 != 0 || (CinC != 1 && CinC != 16) || taps > 8)
     return wgg_fail(ctx, WGG_EUNSUPPORTED, "conv_tc_wgrad: unsupported layer shape%s");
   ctc::WgradArgs a;
   a.dpre = dpre; a.in = in; a.partial = ws; a.B = B; a.CoutC = CoutC; a.CinC = CinC; a.taps = taps; a.pad = pad;
   const int Cin4 = CinC == 1 ? 4 : 64;
   const int Ktot = CinC == 1 ? 32 : taps * 64;
   a.ncols = Ktot + 8;
-  a.dump_all = getenv("WGG_DEBUG_WGRAD_DUMP") ? 1 : 0;
-  a.dbg_mask = getenv("WGG_DEBUG_WGRAD_MASK") ? atoi(getenv("WGG_DEBUG_WGRAD_MASK")) : 0;
   a.gerr = ctx->async_err;
-  const size_t smem = (size_t)9 * ctc::W_BLK + 8 * 8 + 16;
+  const size_t smem = (size_t)ctc::W1_NST * ctc::W1_STAGE + 1024 + 16 * 8 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(ctc::conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

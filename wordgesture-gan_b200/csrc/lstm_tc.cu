@@ -200,49 +200,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      const uint32_t wx = smem_u32(s_wx), wh = smem_u32(s_wh), hs = smem_u32(s_h);
-      for (int step = 0; step < T && ok; ++step) {
-        const int b = step & 1;
-        const uint32_t use = (uint32_t)(step >> 1);  // how many times this buffer has been used before
-        if (!mbar_wait(BAR_ACC_EMPTY(b), (use & 1) ^ 1, s_abort, gerr, 2)) break;
-        tc_fence_after();
-        TS(0);
-        const uint32_t tacc = tmem_base + (uint32_t)(b * ACC_COLS);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (operands stay in uniform registers) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    const uint32_t wx = smem_u32(s_wx), wh = smem_u32(s_wh), hs = smem_u32(s_h);
+    const uint64_t bdx0 = make_desc(wx, CHUNK_BYTES_W, 128), bdh0 = make_desc(wh, CHUNK_BYTES_W, 128);
+    const uint64_t adh0 = make_desc(hs, CHUNK_BYTES_A, 128);
+    constexpr uint64_t kAStep = (2 * CHUNK_BYTES_A) >> 4, kWStep = (2 * CHUNK_BYTES_W) >> 4;
+    for (int step = 0; step < T && ok; ++step) {
+      const int b = step & 1;
+      const uint32_t use = (uint32_t)(step >> 1);  // how many times this buffer has been used before
+      if (!mbar_wait(BAR_ACC_EMPTY(b), (use & 1) ^ 1, s_abort, gerr, 2)) break;
+      tc_fence_after();
+      if (lane == 0) TS(0);
+      const uint32_t tacc = tmem_base + (uint32_t)(b * ACC_COLS);
 #pragma unroll 1
-        for (int sb = 0; sb < NSB; ++sb) {
-          if (!mbar_wait(BAR_FULL(stage), phase, s_abort, gerr, 3)) { ok = false; break; }
-          tc_fence_after();
-          const int chunks = (KXC - sb * SB_CHUNKS) < SB_CHUNKS ? (KXC - sb * SB_CHUNKS) : SB_CHUNKS;
-          const uint32_t xa = smem_u32(s_x + stage * SB_BYTES);
-          for (int j = 0; j < chunks / 2; ++j) {
-            const uint64_t ad = make_desc(xa + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
-            const uint64_t bd = make_desc(wx + (sb * SB_CHUNKS + 2 * j) * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
-            mma_tf32_ss(tacc, ad, bd, kIdesc, (sb | j) ? 1u : 0u);
-          }
+      for (int sb = 0; sb < NSB; ++sb) {
+        if (!mbar_wait(BAR_FULL(stage), phase, s_abort, gerr, 3)) { ok = false; break; }
+        tc_fence_after();
+        const int chunks = (KXC - sb * SB_CHUNKS) < SB_CHUNKS ? (KXC - sb * SB_CHUNKS) : SB_CHUNKS;
+        if (elect_one()) {
+          uint64_t ad = make_desc(smem_u32(s_x + stage * SB_BYTES), CHUNK_BYTES_A, 128);
+          uint64_t bd = bdx0 + (uint64_t)(sb * SB_CHUNKS / 2) * kWStep;
+          for (int j = 0; j < chunks / 2; ++j, ad += kAStep, bd += kWStep) mma_tf32_ss(tacc, ad, bd, kIdesc, (sb | j) ? 1u : 0u);
           mma_commit(BAR_EMPTY(stage));  // frees the ring stage once these MMAs have read it
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        if (!ok) break;
-        TS(1);
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (!ok) break;
+      if (lane == 0) TS(1);
+      if (step > 0) {
+        if (!mbar_wait(BAR_H, (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) break;
+        tc_fence_after();
+        if (lane == 0) TS(2);
+      }
+      if (elect_one()) {
         if (step > 0) {
-          if (!mbar_wait(BAR_H, (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) break;
-          tc_fence_after();
-          TS(2);
 #pragma unroll
-          for (int j = 0; j < KH_CHUNKS / 2; ++j) {
-            const uint64_t ad = make_desc(hs + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
-            const uint64_t bd = make_desc(wh + j * 2 * CHUNK_BYTES_W, CHUNK_BYTES_W, 128);
-            mma_tf32_ss(tacc, ad, bd, kIdesc, 1u);
-          }
+          for (int j = 0; j < KH_CHUNKS / 2; ++j)
+            mma_tf32_ss(tacc, adh0 + (uint64_t)j * kAStep, bdh0 + (uint64_t)j * kWStep, kIdesc, 1u);
         }
         mma_commit(BAR_ACC_FULL(b));
-        TS(3);
       }
+      __syncwarp();
+      if (lane == 0) TS(3);
     }
   } else {
     // ===== epilogue: 16 warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 (12 hidden units each) =====
@@ -396,21 +399,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TM, HID);
-      const uint32_t da = smem_u32(s_da), wb = smem_u32(s_w);
-      int n = 0;
-      for (int step = T - 1; step >= 1; --step, ++n) {
-        if (!mbar_wait(BAR_DA, (uint32_t)(n & 1), s_abort, gerr, 31)) break;
-        tc_fence_after();
-#pragma unroll 4
-        for (int j = 0; j < N4 / 8; ++j) {
-          const uint64_t ad = make_desc(da + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
-          const uint64_t bd = make_desc(wb + j * 2 * WT_CHUNK_BYTES, WT_CHUNK_BYTES, 128);
-          mma_tf32_ss(tmem_base, ad, bd, idesc, j ? 1u : 0u);
-        }
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t idesc = make_idesc(TM, HID);
+    const uint64_t ad0 = make_desc(smem_u32(s_da), CHUNK_BYTES_A, 128), bd0 = make_desc(smem_u32(s_w), WT_CHUNK_BYTES, 128);
+    int n = 0;
+    for (int step = T - 1; step >= 1; --step, ++n) {
+      if (!mbar_wait(BAR_DA, (uint32_t)(n & 1), s_abort, gerr, 31)) break;
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < N4 / 8; ++j)
+          mma_tf32_ss(tmem_base, ad0 + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bd0 + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
+                      idesc, j ? 1u : 0u);
         mma_commit(BAR_ACC);
       }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -567,24 +570,25 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TM, HID);
-      const uint32_t a0 = smem_u32(s_a), w0 = smem_u32(s_w);
-      int n = 0, np = 0;
-      for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++np) {
-        if (!mbar_wait(BAR_ACC_EMPTY, (uint32_t)((np & 1) ^ 1), s_abort, gerr, 42)) return;
-        for (int d = 0; d < 2; ++d, ++n) {
-          if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 43)) return;
-          tc_fence_after();
-#pragma unroll 4
-          for (int j = 0; j < N4 / 8; ++j) {
-            const uint64_t ad = make_desc(a0 + j * 2 * CHUNK_BYTES_A, CHUNK_BYTES_A, 128);
-            const uint64_t bd = make_desc(w0 + d * HID * WT_CHUNK_BYTES + j * 2 * WT_CHUNK_BYTES, WT_CHUNK_BYTES, 128);
-            mma_tf32_ss(tmem_base, ad, bd, idesc, (d | j) ? 1u : 0u);
-          }
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t idesc = make_idesc(TM, HID);
+    const uint64_t ad0 = make_desc(smem_u32(s_a), CHUNK_BYTES_A, 128), bd0 = make_desc(smem_u32(s_w), WT_CHUNK_BYTES, 128);
+    int n = 0, np = 0;
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++np) {
+      if (!mbar_wait(BAR_ACC_EMPTY, (uint32_t)((np & 1) ^ 1), s_abort, gerr, 42)) return;
+      for (int d = 0; d < 2; ++d, ++n) {
+        if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 43)) return;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bdd = bd0 + (uint64_t)(d * ((HID * WT_CHUNK_BYTES) >> 4));
+#pragma unroll
+          for (int j = 0; j < N4 / 8; ++j)
+            mma_tf32_ss(tmem_base, ad0 + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bdd + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
+                        idesc, (d | j) ? 1u : 0u);
           mma_commit(BAR_EMPTY);
+          if (d == 1) mma_commit(BAR_ACC_FULL);
         }
-        mma_commit(BAR_ACC_FULL);
+        __syncwarp();
       }
     }
   } else {
@@ -688,29 +692,31 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
   const int64_t npairs = (int64_t)T * ntiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t id_main = make_idesc(64, 160, 1, 1), id_one = make_idesc(64, 8, 1, 1);
-      const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b), o0 = smem_u32(s_one);
-      int n = 0;
-      bool ok = true;
-      for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
-        if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 51)) { ok = false; break; }
-        tc_fence_after();
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t id_main = make_idesc(64, 160, 1, 1), id_one = make_idesc(64, 8, 1, 1);
+    const uint64_t ad0 = make_desc_mn_dw(smem_u32(s_a)), bd0 = make_desc_mn_dw(smem_u32(s_b)), od0 = make_desc_mn_dw(smem_u32(s_one));
+    int n = 0;
+    bool ok = true;
+    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
+      if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 51)) { ok = false; break; }
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll 2
         for (int ks = 0; ks < TM / 8; ++ks) {
           const uint32_t acc = (n | ks) ? 1u : 0u;
-          const uint64_t bd = make_desc_mn_dw(b0 + ks * 1024);
-          const uint64_t od = make_desc_mn_dw(o0 + ks * 1024);
+          const uint64_t bd = bd0 + (uint64_t)(ks * 64), od = od0 + (uint64_t)(ks * 64);
 #pragma unroll
           for (int mg = 0; mg < 3; ++mg) {
-            const uint64_t ad = make_desc_mn_dw(a0 + 2 * mg * DW_BLK + ks * 1024);
+            const uint64_t ad = ad0 + (uint64_t)((2 * mg * DW_BLK) >> 4) + (uint64_t)(ks * 64);
             mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS), ad, bd, id_main, acc);
             mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS + 160), ad, od, id_one, acc);
           }
         }
         mma_commit(BAR_EMPTY);
       }
-      if (ok) mma_commit(BAR_DONE);
+      __syncwarp();
     }
+    if (ok && elect_one()) mma_commit(BAR_DONE);
   } else {
     const int ptid = tid - 32;  // 0..255
     int n = 0;

@@ -78,6 +78,14 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// true in exactly one (converged) lane of the warp.  MMA-issuing warps run their loops warp-uniformly and predicate
+// only the tcgen05 instructions with this: inside an `if (lane == 0)` region the compiler has to treat every operand
+// as divergent and wraps each tcgen05.mma in a register -> uniform-register "waterfall" loop (~20 extra instructions).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
