@@ -268,9 +268,7 @@ def main():
     samples_per_s = world * B * 10 / (ms_s / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return finish(world, dev)
     peaks = load_peaks()
     ms_step = ms / args.steps
     value = world * B / (ms_step / 1e3)
@@ -311,9 +309,23 @@ def main():
         "sampling": {"value": samples_per_s, "unit": "samples/s", "batch_per_gpu": B,
                      "roofline_frac": 50.6e6 * samples_per_s / world / 1e12 / peaks["tf32_tflops"]},
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    finish(world, dev)
+
+
+def finish(world, dev):
+    """Multi-rank exit: tearing an NCCL communicator down while captured graphs still reference it can block, so
+    ranks meet at a barrier and leave without the teardown (the process is ending anyway)."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
