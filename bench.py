@@ -275,9 +275,33 @@ def main():
     e2e_value = world * B / (ms_e2e / args.steps / 1e3)
     k_ms = prof["ms"] / max(prof["launches"], 1)
     k_tflops = prof["flops"] / max(prof["ms"], 1e-9) / 1e9
-    roof = {"bound": "tensor", "kernel": prof_kernel, "achieved": k_tflops, "peak": peaks["tf32_tflops"],
-            "unit": "TFLOP/s", "frac": k_tflops / peaks["tf32_tflops"], "traffic": None,
+    k_gbs = prof["bytes"] / max(prof["ms"], 1e-9) / 1e6
+    # which roof bounds the dominant kernel: its arithmetic intensity against the ridge of the two measured peaks
+    ai = prof["flops"] / max(prof["bytes"], 1.0)
+    ridge = peaks["tf32_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    hbm_bound = ai < ridge
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_lstm_tc_fwd_B4096.json")
+    if prof_kernel == "lstm_tc_fwd_kernel" and os.path.exists(tpath):
+        try:
+            caps = json.load(open(tpath))
+            def gb(c, key):
+                return float(next(v for k, v in c.items() if k.startswith(key)).replace(",", ""))
+            traffic = sum(gb(c, "dram__bytes_read.sum") + gb(c, "dram__bytes_write.sum") for c in caps) / len(caps) * 1e9
+            traffic_src = ("profiles/r01_ncu_full_lstm_tc_fwd_B4096.json: mean DRAM read+write bytes of the captured launches "
+                           "(the three 40960-gesture critic-phase layer launches, B=4096; algorithmic 3.6 / 6.0 / 6.0 GB)")
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm" if hbm_bound else "tensor", "kernel": prof_kernel,
+            "achieved": k_gbs if hbm_bound else k_tflops, "peak": peaks["hbm_gbs"] if hbm_bound else peaks["tf32_tflops"],
+            "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": (k_gbs / peaks["hbm_gbs"]) if hbm_bound else (k_tflops / peaks["tf32_tflops"]),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+            "tensor": {"achieved": k_tflops, "peak": peaks["tf32_tflops"], "unit": "TFLOP/s", "frac": k_tflops / peaks["tf32_tflops"]},
+            "hbm": {"achieved": k_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": k_gbs / peaks["hbm_gbs"]},
             "launches_per_step": prof["launches"] / prof_steps, "avg_launch_ms": k_ms,
+            "algorithmic_bytes_per_launch": prof["bytes"] / max(prof["launches"], 1),
             "share_of_step": prof["ms"] / max(ms_prof, 1e-9), "peak_source": peaks["source"],
             "kernel_share_ms_per_step": shares,
             "whole_step": {"achieved": FLOP_PER_GESTURE_STEP * value / world / 1e12, "unit": "TFLOP/s",
