@@ -218,7 +218,8 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
 int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* dparams,
                                  const int64_t* layer_off, const int64_t* dir_stride, const int64_t* off_whh,
                                  const int64_t* off_bih, const int64_t* off_bhh, int64_t B, const float* stash,
-                                 const float* dh_rm, float* dz, float* ws, int64_t ws_floats, cudaStream_t st);
+                                 const float* out, const float* dout, int64_t off_wo, int64_t off_bo, float* dz,
+                                 float* ws, int64_t ws_floats, cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05 conv1d layers of the TemporalDiscriminator (conv_tc.cu)

@@ -507,19 +507,33 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
 }
 
 // G[co][(tap,ci)] = sum_cta partial[cta][co][tap*Cin4 + ci];  db[co] += sum_cta partial[cta][co][Ktot]
-__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int nparts, int ncols, int Cout, int Cin,
-                                      int Cin4, int taps, int Ktot, float* __restrict__ G, float* __restrict__ db) {
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ partial, int nparts, int ncols,
+                                                             int Cout, int Cin, int Cin4, int taps, int Ktot,
+                                                             float* __restrict__ G, float* __restrict__ db) {
+  // block = 64 outputs x 4 partial groups (group g sums partials g, g+4, ...; groups are combined in fixed order)
+  __shared__ float s_part[4][64];
   const int n = Cout * taps * Cin + Cout;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    int co, col;
-    const bool isb = idx >= Cout * taps * Cin;
+  const int lane_o = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + lane_o;
+  int co = 0, col = 0;
+  const bool valid = idx < n;
+  const bool isb = idx >= Cout * taps * Cin;
+  if (valid) {
     if (isb) { co = idx - Cout * taps * Cin; col = Ktot; }
     else { co = idx / (taps * Cin); const int r = idx % (taps * Cin); col = (r / Cin) * Cin4 + (r % Cin); }
-    float s = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < nparts; ++p) s += __ldg(partial + ((int64_t)p * 64 + co) * ncols + col);
-    if (isb) db[co] += s;
-    else G[idx] = s;
+  }
+  float s = 0.f;
+  if (valid) {
+    const float* base = partial + (int64_t)co * ncols + col;
+#pragma unroll 10
+    for (int p = grp; p < nparts; p += 4) s += __ldg(base + (int64_t)p * 64 * ncols);
+  }
+  s_part[grp][lane_o] = s;
+  __syncthreads();
+  if (grp == 0 && valid) {
+    const float tot = ((s_part[0][lane_o] + s_part[1][lane_o]) + s_part[2][lane_o]) + s_part[3][lane_o];
+    if (isb) db[co] += tot;
+    else G[idx] = tot;
   }
 }
 
@@ -552,16 +566,26 @@ __global__ void pool_fwd_chunk_kernel(const float* __restrict__ a, float* __rest
 // dpre3[b][c/4][t][c%4] = LeakyReLU'(a3) * (dpool[b][c*8 + t/16] / 16 + dfeat)     (un-pool + LeakyReLU backward)
 __global__ void unpool_leaky_chunk_kernel(const float* __restrict__ dpool, const float* __restrict__ a3,
                                           const float* __restrict__ dfeat, float* __restrict__ dpre, int64_t B, int C) {
-  const int64_t n = B * C * T;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i & 3);
-    const int t = (int)((i >> 2) % T);
-    const int q = (int)((i / (4 * T)) % (C / 4));
-    const int64_t b = i / ((int64_t)C * T);
-    const int c = q * 4 + c4;
-    float g = __ldg(dpool + b * C * 8 + c * 8 + (t >> 4)) * (1.f / 16.f);
-    if (dfeat) g += __ldg(dfeat + i);
-    dpre[i] = rna_tf32(__ldg(a3 + i) > 0.f ? g : kLeak * g);
+  // one thread = one 16-byte group (4 channels of one time step)
+  const int Cc = C / 4;
+  const int64_t n4 = B * Cc * T;
+  const float4* a4 = reinterpret_cast<const float4*>(a3);
+  const float4* f4 = reinterpret_cast<const float4*>(dfeat);
+  float4* o4 = reinterpret_cast<float4*>(dpre);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i & (T - 1));
+    const uint32_t rest = (uint32_t)(i >> 7);          // b * Cc + q
+    const uint32_t q = rest % (uint32_t)Cc, b = rest / (uint32_t)Cc;
+    const float* dp = dpool + (int64_t)b * C * 8 + (q * 4) * 8 + (t >> 4);
+    float4 g = make_float4(__ldg(dp) * (1.f / 16.f), __ldg(dp + 8) * (1.f / 16.f), __ldg(dp + 16) * (1.f / 16.f),
+                           __ldg(dp + 24) * (1.f / 16.f));
+    if (dfeat) {
+      const float4 f = __ldg(f4 + i);
+      g.x += f.x; g.y += f.y; g.z += f.z; g.w += f.w;
+    }
+    const float4 a = __ldg(a4 + i);
+    o4[i] = make_float4(rna_tf32(a.x > 0.f ? g.x : kLeak * g.x), rna_tf32(a.y > 0.f ? g.y : kLeak * g.y),
+                        rna_tf32(a.z > 0.f ? g.z : kLeak * g.z), rna_tf32(a.w > 0.f ? g.w : kLeak * g.w));
   }
 }
 
@@ -652,7 +676,7 @@ int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64
     }
     WGG_CHECK_LAUNCH(ctx, "conv_tc_wgrad_kernel");
   }
-  ctc::wgrad_finalize_kernel<<<96, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);
+  ctc::wgrad_finalize_kernel<<<(Cout * taps * Cin + Cout + 63) / 64, 256, 0, st>>>(ws, grid, a.ncols, Cout, Cin, Cin4, taps, Ktot, G, db);
   WGG_CHECK_LAUNCH(ctx, "wgrad_finalize_kernel");
   return WGG_OK;
 }
@@ -671,7 +695,7 @@ int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B
 
 int unpool_leaky_chunk_launch(wgg_ctx* ctx, const float* dpool, const float* a3, const float* dfeat, float* dpre,
                               int64_t B, int C, cudaStream_t st) {
-  ctc::unpool_leaky_chunk_kernel<<<ew_blocks(B * C * ctc::T), 256, 0, st>>>(dpool, a3, dfeat, dpre, B, C);
+  ctc::unpool_leaky_chunk_kernel<<<ew_blocks(B * (C / 4) * ctc::T), 256, 0, st>>>(dpool, a3, dfeat, dpre, B, C);
   WGG_CHECK_LAUNCH(ctx, "unpool_leaky_chunk_kernel");
   return WGG_OK;
 }

@@ -473,9 +473,15 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
   float* tcws = csws + colsum_ws_floats(H4, 2);
 
+  if (tcp) {
+    // head and LSTM stack backward run entirely on the tcgen05 path (fused head, BPTT, dx and dW/db kernels)
+    return generator_backward_tc_layers(ctx, cfg, params, dparams, g.layer_off, g.dir_stride, g.off_whh, g.off_bih,
+                                        g.off_bhh, B, stash, out, dout, g.off_wo, g.off_bo, dz, tcws,
+                                        generator_tc_bwd_workspace_floats(cfg, B), st);
+  }
   head_bwd_kernel<<<ew_grid(TB * g.C), 256, 0, st>>>(out, dout, dpre, g.T, B, g.C);
   WGG_CHECK_LAUNCH(ctx, "head_bwd_kernel");
-  const float* hL = tcp ? generator_tc_stash_hrm(cfg, B, stash) : sv.hseq[g.L - 1];
+  const float* hL = sv.hseq[g.L - 1];
   {
     GemmP p;  // dWo (C x 2H) += dpre^T * hL
     p.tag = "gemm_kernel/head_wgrad";
@@ -491,11 +497,6 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     q.B = params + g.off_wo; q.N = 2 * H; q.sbk = 2 * H; q.sbn = 1;
     q.C = dh; q.scm = 2 * H; q.scn = 1; q.force_fp32 = 1;
     WGG_TRY(gemm_launch(ctx, q, st));
-  }
-  if (tcp) {
-    // the LSTM stack's backward runs entirely on the tcgen05 path (BPTT, dx and dW/db kernels, chunk layouts)
-    return generator_backward_tc_layers(ctx, cfg, params, dparams, g.layer_off, g.dir_stride, g.off_whh, g.off_bih,
-                                        g.off_bhh, B, stash, dh, dz, tcws, generator_tc_bwd_workspace_floats(cfg, B), st);
   }
   for (int l = g.L - 1; l >= 0; --l) {
     const int I = g.in_dim(l);

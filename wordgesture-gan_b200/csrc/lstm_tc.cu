@@ -80,24 +80,27 @@ __global__ void prep_weights_kernel(const float* __restrict__ lp, int64_t dir_st
 // layer-0 input in tc layout, K padded to KX0 (zero fill), rows padded to the tile: (models.py:147-157)
 __global__ void build_x0_tc_kernel(const float* __restrict__ proto, const float* __restrict__ z, float* __restrict__ x0,
                                    int T, int64_t B, int ntiles, int C, int pd, int Z, int KX0) {
-  const int64_t per_t = (int64_t)ntiles * TM * KX0;
-  const int64_t n = (int64_t)T * per_t;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    // enumerate in storage order so that writes are coalesced
-    const int t = (int)(i / per_t);
-    int64_t r = i % per_t;
-    const int tile = (int)(r / ((int64_t)TM * KX0));
-    r %= (int64_t)TM * KX0;
-    const int chunk = (int)(r / (TM * 4));
-    const int row = (int)((r % (TM * 4)) / 4);
-    const int k = chunk * 4 + (int)(r & 3);
+  // one thread = one 16-byte group (row, K chunk) in storage order: coalesced 16-byte stores
+  const int KC = KX0 / 4;
+  const int64_t n4 = (int64_t)T * ntiles * KC * TM;
+  float4* o4 = reinterpret_cast<float4*>(x0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i & (TM - 1));
+    const int64_t r1 = i >> 7;
+    const int chunk = (int)(r1 % KC);
+    const uint32_t pr = (uint32_t)(r1 / KC);
+    const int tile = (int)(pr % (uint32_t)ntiles), t = (int)(pr / (uint32_t)ntiles);
     const int64_t b = (int64_t)tile * TM + row;
-    float v = 0.f;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (b < B) {
-      if (k < pd) v = __ldg(proto + (b * T + t) * C + k);
-      else if (k < pd + Z) v = __ldg(z + b * Z + (k - pd));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = chunk * 4 + j;
+        if (k < pd) v[j] = __ldg(proto + (b * T + t) * C + k);
+        else if (k < pd + Z) v[j] = __ldg(z + b * Z + (k - pd));
+      }
     }
-    x0[i] = rna_tf32(v);
+    o4[i] = make_float4(rna_tf32(v[0]), rna_tf32(v[1]), rna_tf32(v[2]), rna_tf32(v[3]));
   }
 }
 
@@ -803,6 +806,100 @@ __global__ void rows_to_chunk_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+// Output head backward, fused (models.py:160-163): per (timestep, 128-gesture tile)
+//   dpre = dy * (1 - y^2);   dh = dpre * Wo  -> chunk layout (the top LSTM layer's dh);
+//   dWo += dpre^T * h,  dbo += sum dpre      -> per-CTA partials, reduced in fixed order by head_bwd_finalize_kernel.
+// Phase A: thread = gesture row (dpre to smem, 24 coalesced 16-byte stores of dh).  Phase B: thread = feature
+// (coalesced reads of the un-rounded h rows, three running sums).  HBM-bound: h read once, dh written once.
+constexpr int HEAD_MAXC = 4;
+__global__ void __launch_bounds__(128) head_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                          const float* __restrict__ h_rm, const float* __restrict__ wo,
+                                                          float* __restrict__ dh, float* __restrict__ part, int T,
+                                                          int64_t B, int ntiles, int C) {
+  __shared__ float s_wo[HEAD_MAXC * 96];
+  __shared__ float s_dp[TM * HEAD_MAXC];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < HEAD_MAXC * 96; i += 128) s_wo[i] = i < C * 96 ? __ldg(wo + i) : 0.f;
+  float accw[HEAD_MAXC] = {0.f, 0.f, 0.f, 0.f};
+  float accb = 0.f;  // thread c < C sums dpre[:, c]
+  const int64_t npairs = (int64_t)T * ntiles;
+  __syncthreads();
+  for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+    const int t = (int)(pr / ntiles), tile = (int)(pr % ntiles);
+    const int64_t b = (int64_t)tile * TM + tid;
+    float dp[HEAD_MAXC] = {0.f, 0.f, 0.f, 0.f};
+    if (b < B) {
+      const int64_t src = (b * T + t) * C;
+      for (int c = 0; c < C; ++c) {
+        const float yy = __ldg(y + src + c);
+        dp[c] = __ldg(dy + src + c) * (1.f - yy * yy);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) s_dp[tid * HEAD_MAXC + c] = dp[c];
+    float4* o4 = reinterpret_cast<float4*>(dh) + pr * 24 * TM + tid;
+#pragma unroll 4
+    for (int q = 0; q < 24; ++q) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXC; ++c) a = fmaf(dp[c], s_wo[c * 96 + q * 4 + i], a);
+        v[i] = a;
+      }
+      o4[(int64_t)q * TM] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    const int64_t b0 = (int64_t)tile * TM;
+    const int nrow = (int)((B - b0) < TM ? (B - b0) : TM);
+    if (tid < 96) {
+      const float* hp = h_rm + ((int64_t)t * B + b0) * 96 + tid;
+#pragma unroll 8
+      for (int r = 0; r < nrow; ++r) {
+        const float hv = __ldg(hp + (int64_t)r * 96);
+        const float4 d = *reinterpret_cast<const float4*>(s_dp + r * HEAD_MAXC);
+        accw[0] = fmaf(d.x, hv, accw[0]);
+        accw[1] = fmaf(d.y, hv, accw[1]);
+        accw[2] = fmaf(d.z, hv, accw[2]);
+        accw[3] = fmaf(d.w, hv, accw[3]);
+      }
+    } else if (tid - 96 < C) {
+      for (int r = 0; r < nrow; ++r) accb += s_dp[r * HEAD_MAXC + (tid - 96)];
+    }
+    __syncthreads();
+  }
+  // partial layout per CTA: [C][96] weights then [C] bias
+  float* pp = part + (int64_t)blockIdx.x * (HEAD_MAXC * 96 + HEAD_MAXC);
+  if (tid < 96) {
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) pp[c * 96 + tid] = accw[c];
+  } else if (tid - 96 < HEAD_MAXC) {
+    pp[HEAD_MAXC * 96 + (tid - 96)] = accb;
+  }
+}
+
+// one block per output element (C*96 weights + C biases): fixed-order tree sum over the CTA partials, accumulated
+// into the gradient buffer
+__global__ void __launch_bounds__(128) head_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C,
+                                                                float* __restrict__ dwo, float* __restrict__ dbo) {
+  __shared__ float s[128];
+  const int o = blockIdx.x;  // < C*96: weight (c = o / 96, f = o % 96); else bias c = o - C*96
+  const int idx = o < C * 96 ? o : HEAD_MAXC * 96 + (o - C * 96);
+  float a = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 128) a += part[(int64_t)i * (HEAD_MAXC * 96 + HEAD_MAXC) + idx];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (o < C * 96) dwo[o] += s[0];
+    else dbo[o - C * 96] += s[0];
+  }
+}
+
 // dz[b][j] = sum_t dx0[t][tile][chunk][row][.] at feature pd + j     (backward of repeat + cat, models.py:154-157)
 __global__ void dz_chunk_kernel(const float* __restrict__ dx0, float* __restrict__ dz, int T, int64_t B, int ntiles,
                                 int chunks, int pd, int Z) {
@@ -982,7 +1079,7 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
                                                          off_bhh[l], I, KX, ws + p.img_off[l], p.img_floats[l]);
     WGG_CHECK_LAUNCH(ctx, "prep_weights_kernel");
   }
-  tc::build_x0_tc_kernel<<<ew_blocks(p.x0_floats), 256, 0, st>>>(proto, z, x0, p.T, B, p.ntiles, p.C, p.pd, p.Z, kKX0);
+  tc::build_x0_tc_kernel<<<ew_blocks(p.x0_floats / 4), 256, 0, st>>>(proto, z, x0, p.T, B, p.ntiles, p.C, p.pd, p.Z, kKX0);
   WGG_CHECK_LAUNCH(ctx, "build_x0_tc_kernel");
   const float* in = x0;
   for (int l = 0; l < p.L; ++l) {
@@ -1010,7 +1107,8 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
 int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, float* dparams,
                                  const int64_t* layer_off, const int64_t* dir_stride, const int64_t* off_whh,
                                  const int64_t* off_bih, const int64_t* off_bhh, int64_t B, const float* stash,
-                                 const float* dh_rm, float* dz, float* ws, int64_t ws_floats, cudaStream_t st) {
+                                 const float* out, const float* dout, int64_t off_wo, int64_t off_bo, float* dz,
+                                 float* ws, int64_t ws_floats, cudaStream_t st) {
   TcPlan p;
   if (!tc_plan(cfg, B, &p)) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_backward_tc: unsupported configuration%s");
   if (!ws || ws_floats < generator_tc_bwd_workspace_floats(cfg, B))
@@ -1022,8 +1120,19 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   float* whhT = da + (int64_t)2 * p.T * p.rows * tc::N4;
   float* wihT = whhT + 2 * tc::HID * tc::N4;
   float* part = wihT + 4 * tc::HID * tc::N4;
-  tc::rows_to_chunk_kernel<<<ew_blocks(p.h_floats), 256, 0, st>>>(dh_rm, dh[0], p.T, B, p.ntiles, 96);
-  WGG_CHECK_LAUNCH(ctx, "rows_to_chunk_kernel");
+  {
+    // output head backward: dh of the top layer straight into the chunk layout, dWo/dbo through per-CTA partials
+    if (cfg->input_dim > tc::HEAD_MAXC) return wgg_fail(ctx, WGG_EUNSUPPORTED, "generator_backward_tc: input_dim > 4%s");
+    const int64_t npairs0 = (int64_t)p.T * p.ntiles;
+    const int hgrid = (int)(npairs0 < 8 * (int64_t)ctx->sm_count ? npairs0 : 8 * (int64_t)ctx->sm_count);
+    ProfScope prof(ctx, "head_bwd_tc_kernel", st, 4.0 * p.T * (double)B * 96 * cfg->input_dim, p.T * (double)B * 4.0 * (96 + 96));
+    tc::head_bwd_tc_kernel<<<hgrid, 128, 0, st>>>(out, dout, stash + sl.hrm, params + off_wo, dh[0], part, p.T, B, p.ntiles,
+                                                  cfg->input_dim);
+    WGG_CHECK_LAUNCH(ctx, "head_bwd_tc_kernel");
+    tc::head_bwd_finalize_kernel<<<cfg->input_dim * 96 + cfg->input_dim, 128, 0, st>>>(part, hgrid, cfg->input_dim,
+                                                                                      dparams + off_wo, dparams + off_bo);
+    WGG_CHECK_LAUNCH(ctx, "head_bwd_finalize_kernel");
+  }
   int cur = 0;
   constexpr size_t smem_bwd = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
   constexpr size_t smem_dx = (size_t)tc::HID * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
