@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
 //   dh_out : [T][ntiles][24][128][4]      d(layer output), chunk layout (chunks dir*12.. belong to this direction)
 //   da_out : [2][T][ntiles][48][128][4]   chunk u = (da_i, da_f, da_g, da_o) of hidden unit u - exactly the A tile
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 288;  // warp 0: MMA issuer; warps 1..8: epilogue (TMEM quarter = warp % 4)
+constexpr int BWD_THREADS = 256;  // 8 epilogue warps (TMEM quarter = warp % 4); warp 0 also issues the MMAs
 constexpr int WT_CHUNK_BYTES = (HID / 8) * 128;  // 768: one K chunk of the [48 x 192] W_hh^T image
 
 // B operand of dh_rec = da * W_hh:  img[u'][n'] = W_hh[(g*H + u)][u'] with n' = 4u + g   ([N=48][K=192], K-major)
@@ -401,90 +401,79 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    // MMA issuer: warp-uniform loop, one elected lane issues
+  {
     const uint32_t idesc = make_idesc(TM, HID);
     const uint64_t ad0 = make_desc(smem_u32(s_da), CHUNK_BYTES_A, 128), bd0 = make_desc(smem_u32(s_w), WT_CHUNK_BYTES, 128);
-    int n = 0;
-    for (int step = T - 1; step >= 1; --step, ++n) {
-      if (!mbar_wait(BAR_DA, (uint32_t)(n & 1), s_abort, gerr, 31)) break;
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int j = 0; j < N4 / 8; ++j)
-          mma_tf32_ss(tmem_base, ad0 + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bd0 + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
-                      idesc, j ? 1u : 0u);
-        mma_commit(BAR_ACC);
-      }
-      __syncwarp();
-    }
-  } else {
     const int quarter = warp & 3;
-    const int half = (warp - 1) >> 2;
+    const int half = warp >> 2;
     const int row = quarter * 32 + lane;
     const int64_t bidx = (int64_t)tile * TM + row;
     const bool valid = bidx < B;
-    float dc[24];
+    float dc[24], cc[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) dc[i] = 0.f;
     float4* da4 = reinterpret_cast<float4*>(s_da);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 24);
+    const float4* gc4 = reinterpret_cast<const float4*>(gc) + row;
+    auto gc_tile = [&](int tt) { return gc4 + ((((int64_t)dir * T + tt) * ntiles + tile) * GC_CHUNKS) * TM; };
+    {
+      // cell state of the first step of the reverse scan; afterwards it is carried over from the c_prev loads
+      const float4* g0 = gc_tile(dir ? 0 : T - 1);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float4 c4 = __ldg(g0 + (int64_t)(HID + half * 6 + k) * TM);
+        cc[4 * k] = c4.x; cc[4 * k + 1] = c4.y; cc[4 * k + 2] = c4.z; cc[4 * k + 3] = c4.w;
+      }
+    }
     int n = 0;
     for (int step = T - 1; step >= 0; --step, ++n) {
       const int t = dir ? T - 1 - step : step;
       const int tp = dir ? t + 1 : t - 1;
-      const float4* g4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
-      const float4* gp4 = reinterpret_cast<const float4*>(gc) + ((((int64_t)dir * T + tp) * ntiles + tile) * GC_CHUNKS) * TM + row;
+      const float4* g4 = gc_tile(t);
       const float4* dh4 = reinterpret_cast<const float4*>(dh_out) + (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS + half * 6) * TM + row;
       float4* dao4 = reinterpret_cast<float4*>(da_out) + ((((int64_t)dir * T + t) * ntiles + tile) * HID + half * 24) * TM + row;
+      // Every global operand of this step is independent of the recurrence: issue all loads BEFORE waiting for the
+      // dh_rec accumulator, so the memory round trip overlaps the tensor-core latency of the previous step.
+      float4 gts[24];
+      float dho[24], cp[24];
+#pragma unroll
+      for (int u = 0; u < 24; ++u) gts[u] = __ldg(g4 + (int64_t)(half * 24 + u) * TM);  // (i, f, g, o)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a0 = valid ? __ldg(dh4 + (int64_t)k * TM) : z4;
+        dho[4 * k] = a0.x; dho[4 * k + 1] = a0.y; dho[4 * k + 2] = a0.z; dho[4 * k + 3] = a0.w;
+        float4 p0 = z4;
+        if (step > 0) p0 = __ldg(gc_tile(tp) + (int64_t)(HID + half * 6 + k) * TM);
+        cp[4 * k] = p0.x; cp[4 * k + 1] = p0.y; cp[4 * k + 2] = p0.z; cp[4 * k + 3] = p0.w;
+      }
       if (step < T - 1) {
         if (!mbar_wait(BAR_ACC, (uint32_t)((n - 1) & 1), s_abort, gerr, 32)) break;
         tc_fence_after();
       }
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float dho[8], cc[8], cp[8];
-        {
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 a0 = valid ? __ldg(dh4 + (int64_t)(ch * 2) * TM) : z4;
-          const float4 a1 = valid ? __ldg(dh4 + (int64_t)(ch * 2 + 1) * TM) : z4;
-          dho[0] = a0.x; dho[1] = a0.y; dho[2] = a0.z; dho[3] = a0.w; dho[4] = a1.x; dho[5] = a1.y; dho[6] = a1.z; dho[7] = a1.w;
-          const int cchunk = HID + half * 6 + ch * 2;
-          const float4 c0 = __ldg(g4 + (int64_t)cchunk * TM), c1 = __ldg(g4 + (int64_t)(cchunk + 1) * TM);
-          cc[0] = c0.x; cc[1] = c0.y; cc[2] = c0.z; cc[3] = c0.w; cc[4] = c1.x; cc[5] = c1.y; cc[6] = c1.z; cc[7] = c1.w;
-          if (step > 0) {
-            const float4 p0 = __ldg(gp4 + (int64_t)cchunk * TM), p1 = __ldg(gp4 + (int64_t)(cchunk + 1) * TM);
-            cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cp[i] = 0.f;
-          }
-        }
-        // all global loads of this 8-unit chunk are issued before any dependent math (one memory round trip per chunk)
-        float4 gts[8];
-#pragma unroll
-        for (int uu = 0; uu < 8; ++uu) gts[uu] = __ldg(g4 + (int64_t)(half * 24 + ch * 8 + uu) * TM);  // (i, f, g, o)
         float rec[8];
         if (step < T - 1) tmem_ld8(taddr + ch * 8, rec);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) rec[i] = 0.f;
         }
-        float dai[8], daf[8], dag[8], dao[8];
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
           const int ul = ch * 8 + uu;
-          const float4 gt = gts[uu];
-          const float tch = tanh_fast(cc[uu]);
-          const float dh = dho[uu] + rec[uu];
+          const float4 gt = gts[ul];
+          const float tch = tanh_fast(cc[ul]);
+          const float dh = dho[ul] + rec[uu];
           const float d_o = dh * tch;
           const float dct = dc[ul] + dh * gt.w * (1.f - tch * tch);
-          dai[uu] = dct * gt.z * gt.x * (1.f - gt.x);
-          daf[uu] = dct * cp[uu] * gt.y * (1.f - gt.y);
-          dag[uu] = dct * gt.x * (1.f - gt.z * gt.z);
-          dao[uu] = d_o * gt.w * (1.f - gt.w);
+          const float dai = dct * gt.z * gt.x * (1.f - gt.x);
+          const float daf = dct * cp[ul] * gt.y * (1.f - gt.y);
+          const float dag = dct * gt.x * (1.f - gt.z * gt.z);
+          const float dao = d_o * gt.w * (1.f - gt.w);
           dc[ul] = dct * gt.y;
-          const float4 dq = make_float4(rna_tf32(dai[uu]), rna_tf32(daf[uu]), rna_tf32(dag[uu]), rna_tf32(dao[uu]));
+          cc[ul] = cp[ul];
+          const float4 dq = make_float4(rna_tf32(dai), rna_tf32(daf), rna_tf32(dag), rna_tf32(dao));
           da4[(half * 24 + ul) * TM + row] = dq;       // A operand of dh_rec = da * W_hh
           dao4[(int64_t)ul * TM] = dq;                 // HBM copy for the dx / dW kernels (coalesced: lane = row)
         }
@@ -493,6 +482,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) lstm_tc_bwd_kernel(const float
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_DA);
+      if (warp == 0 && step >= 1) {
+        // dh_rec = da * W_hh for the next (earlier) step: warp-uniform, one elected lane issues
+        if (!mbar_wait(BAR_DA, (uint32_t)(n & 1), s_abort, gerr, 31)) break;
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < N4 / 8; ++j)
+            mma_tf32_ss(tmem_base, ad0 + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bd0 + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
+                        idesc, j ? 1u : 0u);
+          mma_commit(BAR_ACC);
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
