@@ -28,7 +28,8 @@ constexpr int ROWS_S = 136;            // rows per chunk in shared memory: 2 pad
 constexpr int CS = ROWS_S * 16;        // chunk stride in shared memory (bytes)
 constexpr int PAD_ROWS = 2;
 constexpr int CHUNK_G = T * 16;        // chunk size in HBM (bytes): 128 rows x 16 B
-constexpr int NTHREADS = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 epilogue (TMEM quarter = warp % 4)
+constexpr int NTHREADS = 320;          // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (TMEM quarter = warp % 4, column half)
+constexpr int NST = 3;                 // input ring depth (two gestures' loads in flight behind the one being multiplied)
 
 struct FwdArgs {
   const float* in;        // [B][CinC][T][4]
@@ -54,28 +55,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
   uint8_t* s_w = smem;
   uint8_t* s_in = s_w + ((Kchunks * WCS + 1023) / 1024) * 1024;
   const int in_bytes = a.CinC * CS;
-  float* s_bias = reinterpret_cast<float*>(s_in + 2 * in_bytes);
+  float* s_bias = reinterpret_cast<float*>(s_in + NST * in_bytes);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 2);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(s_bar);
   auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };
-  const uint32_t BAR_ACC_FULL = bar0 + 8u * 4, BAR_ACC_EMPTY = bar0 + 8u * 5;
+  auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+  const uint32_t BAR_ACC_FULL = bar0 + 8u * (2 * NST), BAR_ACC_EMPTY = bar0 + 8u * (2 * NST + 1);
 
   {
     const float4* src = reinterpret_cast<const float4*>(a.wimg);
     float4* dst = reinterpret_cast<float4*>(s_w);
     for (int i = tid; i < Kchunks * WCS / 16; i += NTHREADS) dst[i] = __ldg(src + i);
     float4* zin = reinterpret_cast<float4*>(s_in);
-    for (int i = tid; i < 2 * in_bytes / 16; i += NTHREADS) zin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < NST * in_bytes / 16; i += NTHREADS) zin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < 64; i += NTHREADS) s_bias[i] = (a.bias && i < a.N) ? __ldg(a.bias + i) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
     mbar_init(BAR_ACC_FULL, 1);
-    mbar_init(BAR_ACC_EMPTY, 4);
+    mbar_init(BAR_ACC_EMPTY, 8);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
     if (lane == 0) {
       int n = 0;
       for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-        const int st = n & 1;
-        if (!mbar_wait(BAR_EMPTY(st), ((n >> 1) & 1) ^ 1, s_abort, a.gerr, 11)) break;
+        const int st = n % NST;
+        if (!mbar_wait(BAR_EMPTY(st), ((n / NST) & 1) ^ 1, s_abort, a.gerr, 11)) break;
         mbar_expect_tx(BAR_FULL(st), a.CinC * CHUNK_G);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in) + b * (int64_t)a.CinC * CHUNK_G;
         for (int q = 0; q < a.CinC; ++q)
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
     const uint32_t wb = smem_u32(s_w);
     const uint64_t bd0 = make_desc(wb, WCS, 128);
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-      const int st = n & 1;
-      if (!mbar_wait(BAR_FULL(st), (n >> 1) & 1, s_abort, a.gerr, 12)) break;
+      const int st = n % NST;
+      if (!mbar_wait(BAR_FULL(st), (n / NST) & 1, s_abort, a.gerr, 12)) break;
       if (!mbar_wait(BAR_ACC_EMPTY, (n & 1) ^ 1, s_abort, a.gerr, 13)) break;
       tc_fence_after();
       const uint32_t ab = smem_u32(s_in + st * in_bytes);
@@ -136,54 +137,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_fwd_kernel(FwdArgs a) {
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3;
+    // epilogue: 8 warps; TMEM quarter = warp % 4 (rows = time), the two warps of a quarter split the output channels
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int t = quarter * 32 + lane;
+    const bool split = a.N >= 32;
+    const int ncol = split ? a.N / 2 : a.N;             // columns handled by this warp (0 work for half 1 if !split)
+    const int c0 = split ? half * ncol : 0;
+    const bool active = split || half == 0;
     int n = 0;
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
       if (!mbar_wait(BAR_ACC_FULL, n & 1, s_abort, a.gerr, 14)) break;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      float v[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      float v[32];
+      if (active) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (cc * 16 < a.N) {  // warp-uniform
-          float r[16];
-          tmem_ld16(taddr + cc * 16, r);
+        for (int cc = 0; cc < 2; ++cc) {
+          if (cc * 16 < ncol) {  // warp-uniform
+            float r[16];
+            tmem_ld16(taddr + cc * 16, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[cc * 16 + i] = r[i];
+            for (int i = 0; i < 16; ++i) v[cc * 16 + i] = r[i];
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_ACC_EMPTY);
+      if (!active) continue;
       if (a.mode == 2) {
         float* o = a.out + (b * T + t) * 3;
         o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
       } else {
-        float4* o4 = reinterpret_cast<float4*>(a.out) + (b * (a.N / 4)) * T + t;
-        const float4* y4 = a.mode == 1 ? reinterpret_cast<const float4*>(a.act_lower) + (b * (a.N / 4)) * T + t : nullptr;
-        const float4* f4 = (a.mode == 1 && a.dfeat) ? reinterpret_cast<const float4*>(a.dfeat) + (b * (a.N / 4)) * T + t : nullptr;
+        const int64_t cbase = (b * (a.N / 4) + c0 / 4) * T + t;
+        float4* o4 = reinterpret_cast<float4*>(a.out) + cbase;
+        const float4* y4 = a.mode == 1 ? reinterpret_cast<const float4*>(a.act_lower) + cbase : nullptr;
+        const float4* f4 = (a.mode == 1 && a.dfeat) ? reinterpret_cast<const float4*>(a.dfeat) + cbase : nullptr;
         if (a.mode == 0) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (q >= a.N / 4) break;
+          for (int q = 0; q < 8; ++q) {
+            if (q >= ncol / 4) break;
             float x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = leaky_f(v[4 * q + i] + s_bias[4 * q + i]);
+            for (int i = 0; i < 4; ++i) x[i] = leaky_f(v[4 * q + i] + s_bias[c0 + 4 * q + i]);
             o4[(int64_t)q * T] = make_float4(rna_tf32(x[0]), rna_tf32(x[1]), rna_tf32(x[2]), rna_tf32(x[3]));
           }
         } else {
           // LeakyReLU backward (+ feature-matching gradient injection): issue all loads first, then the math
-          float4 ys[16], fs[16];
+          float4 ys[8], fs[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (q < a.N / 4) {
+          for (int q = 0; q < 8; ++q)
+            if (q < ncol / 4) {
               ys[q] = __ldg(y4 + (int64_t)q * T);
               fs[q] = f4 ? __ldg(f4 + (int64_t)q * T) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (q >= a.N / 4) break;
+          for (int q = 0; q < 8; ++q) {
+            if (q >= ncol / 4) break;
             float x[4] = {v[4 * q] + fs[q].x, v[4 * q + 1] + fs[q].y, v[4 * q + 2] + fs[q].z, v[4 * q + 3] + fs[q].w};
             x[0] = ys[q].x > 0.f ? x[0] : kLeak * x[0];
             x[1] = ys[q].y > 0.f ? x[1] : kLeak * x[1];
@@ -623,7 +633,7 @@ int conv_tc_fwd_launch(wgg_ctx* ctx, const float* in, const float* wimg, const f
   a.tap_row0 = ctc::PAD_ROWS - pad; a.N = N; a.mode = mode; a.gerr = ctx->async_err;
   const int Kchunks = CinC == 1 ? a.taps_p : taps * CinC;
   const int WCS = (N / 8) * 128;
-  const size_t smem = (size_t)((Kchunks * WCS + 1023) / 1024) * 1024 + 2 * (size_t)CinC * ctc::CS + 64 * 4 + 8 * 8 + 16;
+  const size_t smem = (size_t)((Kchunks * WCS + 1023) / 1024) * 1024 + ctc::NST * (size_t)CinC * ctc::CS + 64 * 4 + (2 * ctc::NST + 2) * 8 + 16;
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(ctc::conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

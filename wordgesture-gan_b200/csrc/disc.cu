@@ -199,6 +199,19 @@ __global__ void __launch_bounds__(1024) sn_kernel(SnArgs a, const float* __restr
   for (int r = tid; r < rows; r += NT) sn[a.sn_u[l] + r] = u_s[r];
   for (int c = tid; c < cols; c += NT) sn[a.sn_v[l] + c] = v_s[c];
   if (tid == 0) sn[a.sn_sigma[l]] = sigma;
+}
+
+// W / sigma in the layouts the compute kernels read (second launch: wide, so that the single-CTA power iteration
+// above stays short).  grid (layers, kSnImageSplit)
+constexpr int kSnImageSplit = 16;
+__global__ void __launch_bounds__(256) sn_images_kernel(SnArgs a, const float* __restrict__ params, float* __restrict__ sn,
+                                                        int with_output) {
+  const int l = blockIdx.x;
+  if (l == a.nl - 1 && !with_output) return;
+  const int rows = a.rows[l], cols = a.cols[l];
+  const float* __restrict__ W = params + a.off_w[l];
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, NT = blockDim.x * gridDim.y;
+  const float sigma = sn[a.sn_sigma[l]];
   float* wf = sn + a.sn_wf[l];
   float* wb = sn + a.sn_wb[l];
   const int n = rows * cols;
@@ -239,34 +252,50 @@ __global__ void __launch_bounds__(1024) sn_kernel(SnArgs a, const float* __restr
 }
 
 // dW_orig += G/sigma - (<G, W_orig>/sigma^2) u v^T, G given in the forward layout of that layer.
-__global__ void __launch_bounds__(1024) sn_grad_kernel(SnArgs a, const float* __restrict__ params,
-                                                      const float* __restrict__ sn, const float* __restrict__ G,
-                                                      float* __restrict__ dparams, int with_output) {
+// Two wide launches, grid (layers, kSnGradSplit): partial inner products <G, W_orig>, then the update (the partials
+// are combined in fixed order by every block, so the result is deterministic).
+constexpr int kSnGradSplit = 16;
+__device__ __forceinline__ int sn_gidx(int idx, int cols, int ks, int Cin, int conv) {
+  if (!conv) return idx;
+  const int r = idx / cols, c = idx % cols;
+  return r * cols + (c % ks) * Cin + c / ks;
+}
+__global__ void __launch_bounds__(256) sn_inner_kernel(SnArgs a, const float* __restrict__ params,
+                                                       const float* __restrict__ G, float* __restrict__ partial,
+                                                       int with_output) {
   __shared__ float red[33];
   const int l = blockIdx.x;
   if (l == a.nl - 1 && !with_output) return;  // features-only call: the output layer never ran
   const int rows = a.rows[l], cols = a.cols[l], n = rows * cols;
   const float* __restrict__ W = params + a.off_w[l];
   const float* __restrict__ g = G + a.g_off[l];
-  const int tid = threadIdx.x, NT = blockDim.x;
   const int ks = a.ks[l], Cin = a.Cin[l], conv = a.is_conv[l];
-  auto gidx = [&](int idx) {
-    if (!conv) return idx;
-    const int r = idx / cols, c = idx % cols;
-    return r * cols + (c % ks) * Cin + c / ks;
-  };
   float ip = 0.f;
 #pragma unroll 4
-  for (int idx = tid; idx < n; idx += NT) ip = fmaf(__ldg(g + gidx(idx)), __ldg(W + idx), ip);
+  for (int idx = blockIdx.y * 256 + threadIdx.x; idx < n; idx += 256 * kSnGradSplit)
+    ip = fmaf(__ldg(g + sn_gidx(idx, cols, ks, Cin, conv)), __ldg(W + idx), ip);
   const float inner = block_sum(ip, red);
+  if (threadIdx.x == 0) partial[l * kSnGradSplit + blockIdx.y] = inner;
+}
+__global__ void __launch_bounds__(256) sn_grad_kernel(SnArgs a, const float* __restrict__ sn, const float* __restrict__ G,
+                                                      const float* __restrict__ partial, float* __restrict__ dparams,
+                                                      int with_output) {
+  const int l = blockIdx.x;
+  if (l == a.nl - 1 && !with_output) return;
+  const int rows = a.rows[l], cols = a.cols[l], n = rows * cols;
+  const float* __restrict__ g = G + a.g_off[l];
+  const int ks = a.ks[l], Cin = a.Cin[l], conv = a.is_conv[l];
+  float inner = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSnGradSplit; ++i) inner += partial[l * kSnGradSplit + i];
   const float sigma = sn[a.sn_sigma[l]];
   const float k2 = inner / (sigma * sigma);
   const float* u = sn + a.sn_u[l];
   const float* v = sn + a.sn_v[l];
   float* dW = dparams + a.off_w[l];
-  for (int idx = tid; idx < n; idx += NT) {
+  for (int idx = blockIdx.y * 256 + threadIdx.x; idx < n; idx += 256 * kSnGradSplit) {
     const int r = idx / cols, c = idx % cols;
-    dW[idx] += g[gidx(idx)] / sigma - k2 * u[r] * v[c];
+    dW[idx] += g[sn_gidx(idx, cols, ks, Cin, conv)] / sigma - k2 * u[r] * v[c];
   }
 }
 
@@ -403,6 +432,8 @@ extern "C" int wgg_disc_spectral(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   if (smem > 48 * 1024) return wgg_fail(ctx, WGG_EUNSUPPORTED, "disc_spectral: layer too wide for the SN kernel%s");
   sn_kernel<<<d.nl, 1024, smem, (cudaStream_t)stream>>>(a, params, uv, sn, training, with_output_layer);
   WGG_CHECK_LAUNCH(ctx, "sn_kernel");
+  sn_images_kernel<<<dim3(d.nl, kSnImageSplit), 256, 0, (cudaStream_t)stream>>>(a, params, sn, with_output_layer);
+  WGG_CHECK_LAUNCH(ctx, "sn_images_kernel");
   return WGG_OK;
 }
 
@@ -572,7 +603,10 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   if (dparams) {
     SnArgs a;
     fill_sn_args(d, &a);
-    sn_grad_kernel<<<d.nl, 1024, 0, st>>>(a, params, sn, G, dparams, dscore ? 1 : 0);
+    float* ipart = wgg_next_partial(ctx);
+    sn_inner_kernel<<<dim3(d.nl, kSnGradSplit), 256, 0, st>>>(a, params, G, ipart, dscore ? 1 : 0);
+    WGG_CHECK_LAUNCH(ctx, "sn_inner_kernel");
+    sn_grad_kernel<<<dim3(d.nl, kSnGradSplit), 256, 0, st>>>(a, sn, G, ipart, dparams, dscore ? 1 : 0);
     WGG_CHECK_LAUNCH(ctx, "sn_grad_kernel");
   }
   return WGG_OK;
