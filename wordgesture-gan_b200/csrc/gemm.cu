@@ -115,8 +115,117 @@ __device__ __forceinline__ void store_out(const GemmP& p, float* C, const float*
 // ---------------------------------------------------------------------------------------------
 // fp32 FMA kernel: 64x64x16 tile, 256 threads, 4x4 register tile
 // ---------------------------------------------------------------------------------------------
-template <int CONV>
-__global__ void __launch_bounds__(256, 2) gemm_kernel(GemmP p) {
+template <int CONV, int BM_>
+__global__ void __launch_bounds__(256, BM_ == 64 ? 2 : 4) gemm_kernel(GemmP p) {
+  constexpr int RM = BM_ / 16;  // rows per thread (4, or 2 for the small-problem tile that doubles the CTA count)
+  __shared__ __align__(16) float As[BK][BM_ + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+  const float* __restrict__ A = p.A + (int64_t)batch * p.bsA;
+  const float* __restrict__ B = p.B + (int64_t)batch * p.bsB;
+  const int64_t m0 = (int64_t)blockIdx.x * BM_;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  const int64_t ktiles = (p.K + BK - 1) / BK;
+  const int64_t per = (ktiles + p.splitk - 1) / p.splitk;
+  const int64_t kt_begin = (int64_t)split * per;
+  const int64_t kt_end = min(ktiles, kt_begin + per);
+
+  ALoader<RM, BM_, BK, CONV> la;
+  BLoader<4, BN, BK, CONV> lb;
+  la.init(p, m0, kt_begin * BK, tid);
+  lb.init(p, n0, kt_begin * BK, tid);
+
+  float acc[RM][4];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int tx = tid % 16, ty = tid / 16;
+  float ra[RM], rb[4];
+  if (kt_begin < kt_end) {
+    la.load(p, A, m0, kt_begin * BK, ra);
+    lb.load(p, B, n0, kt_begin * BK, rb);
+  }
+  for (int64_t kt = kt_begin; kt < kt_end; ++kt) {
+#pragma unroll
+    for (int i = 0; i < RM; ++i) As[la.kk(i)][la.mm(i)] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[lb.kk(i)][lb.nn(i)] = rb[i];
+    __syncthreads();
+    if (kt + 1 < kt_end) {
+      la.load(p, A, m0, (kt + 1) * BK, ra);
+      lb.load(p, B, n0, (kt + 1) * BK, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[RM];
+      if (RM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[RM - 2] = a.z; av[RM - 1] = a.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+        av[0] = a.x; av[1] = a.y;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
+  float* C = p.C + (int64_t)batch * p.bsC;
+  const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
+  const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int64_t m = m0 + ty * RM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      if (P) P[m * p.N + n] = acc[i][j];
+      else store_out(p, C, bias, bias2, m, n, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 FMA kernel with 16-byte global loads: the nn.Linear shapes (forward x W^T, backward-data dY W, weight
+// gradient dY^T X with split-K).  Each operand is contiguous either along k or along its tile direction; a thread
+// loads ONE float4 per operand and k-tile (instead of four predicated scalars) and the k-contiguous case is
+// transposed on its way into shared memory.  Same 64x64x16 tile / 4x4 register tile / epilogue as gemm_kernel.
+// Requires: dimensions along the vector direction multiples of 4, 16-byte aligned bases and leading dimensions.
+// ---------------------------------------------------------------------------------------------
+template <int KFAST>
+__device__ __forceinline__ float4 vec_tile_load(const float* __restrict__ X, int64_t ld, int64_t mn0, int64_t k0, int64_t MN,
+                                                int64_t K, int tid) {
+  // KFAST: X[(mn) * ld + k], thread -> (row = tid / 4, kq = tid % 4);  else X[k * ld + mn], thread -> (k = tid / 16, q = tid % 16)
+  int64_t mn, k;
+  if (KFAST) { mn = mn0 + (tid >> 2); k = k0 + 4 * (tid & 3); }
+  else { k = k0 + (tid >> 4); mn = mn0 + 4 * (tid & 15); }
+  if (mn >= MN || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return __ldg(reinterpret_cast<const float4*>(X + (KFAST ? mn * ld + k : k * ld + mn)));
+}
+template <int KFAST>
+__device__ __forceinline__ void vec_tile_store(float (*S)[BM + PAD], const float4& v, int tid) {
+  if (KFAST) {
+    const int row = tid >> 2, kq = 4 * (tid & 3);
+    S[kq][row] = v.x; S[kq + 1][row] = v.y; S[kq + 2][row] = v.z; S[kq + 3][row] = v.w;
+  } else {
+    *reinterpret_cast<float4*>(&S[tid >> 4][4 * (tid & 15)]) = v;
+  }
+}
+
+template <int A_KF, int B_KF>
+__global__ void __launch_bounds__(256, 3) gemm_fp32_vec_kernel(GemmP p) {
+  static_assert(BM == BN, "shared tile helper assumes square tiles");
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -129,34 +238,26 @@ __global__ void __launch_bounds__(256, 2) gemm_kernel(GemmP p) {
   const int64_t per = (ktiles + p.splitk - 1) / p.splitk;
   const int64_t kt_begin = (int64_t)split * per;
   const int64_t kt_end = min(ktiles, kt_begin + per);
-
-  ALoader<4, BM, BK, CONV> la;
-  BLoader<4, BN, BK, CONV> lb;
-  la.init(p, m0, kt_begin * BK, tid);
-  lb.init(p, n0, kt_begin * BK, tid);
+  const int64_t lda = A_KF ? p.sam : p.sak, ldb = B_KF ? p.sbn : p.sbk;
 
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
   const int tx = tid % 16, ty = tid / 16;
-  float ra[4], rb[4];
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
   if (kt_begin < kt_end) {
-    la.load(p, A, m0, kt_begin * BK, ra);
-    lb.load(p, B, n0, kt_begin * BK, rb);
+    ra = vec_tile_load<A_KF>(A, lda, m0, kt_begin * BK, p.M, p.K, tid);
+    rb = vec_tile_load<B_KF>(B, ldb, n0, kt_begin * BK, p.N, p.K, tid);
   }
   for (int64_t kt = kt_begin; kt < kt_end; ++kt) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      As[la.kk(i)][la.mm(i)] = ra[i];
-      Bs[lb.kk(i)][lb.nn(i)] = rb[i];
-    }
+    vec_tile_store<A_KF>(As, ra, tid);
+    vec_tile_store<B_KF>(Bs, rb, tid);
     __syncthreads();
     if (kt + 1 < kt_end) {
-      la.load(p, A, m0, (kt + 1) * BK, ra);
-      lb.load(p, B, n0, (kt + 1) * BK, rb);
+      ra = vec_tile_load<A_KF>(A, lda, m0, (kt + 1) * BK, p.M, p.K, tid);
+      rb = vec_tile_load<B_KF>(B, ldb, n0, (kt + 1) * BK, p.N, p.K, tid);
     }
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
@@ -171,7 +272,6 @@ __global__ void __launch_bounds__(256, 2) gemm_kernel(GemmP p) {
     }
     __syncthreads();
   }
-
   float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
   float* C = p.C + (int64_t)batch * p.bsC;
   const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
@@ -554,7 +654,16 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.splitk > 1 && (!p.partial || p.act != ACT_NONE || p.bias || p.bias2))
     return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K needs a partial buffer and a plain epilogue%s");
   const bool tf32 = ctx->math_mode >= 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
-  const int bm = tf32 ? TBM : BM, bn = tf32 ? TBN : BN;
+  // fp32 with 16-byte loads: every operand contiguous along k or along its tile direction, vector direction % 4
+  const bool fa_kf = p.sak == 1, fa_mf = p.sam == 1, fb_kf = p.sbk == 1, fb_nf = p.sbn == 1;
+  const bool fvec = !tf32 && p.conv_mode == 0 && (fa_kf || fa_mf) && (fb_kf || fb_nf) &&
+                    (fa_kf ? (p.K % 4 == 0 && p.sam % 4 == 0) : (p.M % 4 == 0 && p.sak % 4 == 0)) &&
+                    (fb_kf ? (p.K % 4 == 0 && p.sbn % 4 == 0) : (p.N % 4 == 0 && p.sbk % 4 == 0)) &&
+                    p.bsA % 4 == 0 && p.bsB % 4 == 0 && (((uintptr_t)p.A | (uintptr_t)p.B) % 16 == 0);
+  // small fp32 problems (the Linear layers): halve the M tile when the 64-row tiling would leave SMs idle
+  const bool small = !tf32 && !fvec && p.conv_mode == 0 &&
+                     cdiv64(p.M, BM) * cdiv64(p.N, BN) * p.nbatch * p.splitk < 2 * (int64_t)ctx->sm_count;
+  const int bm = tf32 ? TBM : (small ? 32 : BM), bn = tf32 ? TBN : BN;
   dim3 grid((unsigned)cdiv64(p.M, bm), (unsigned)cdiv64(p.N, bn), (unsigned)(p.nbatch * p.splitk));
   if (grid.y > 65535 || grid.z > 65535) return wgg_fail(ctx, WGG_EINVAL, "gemm: grid too large%s");
   ProfScope prof(ctx, "gemm_kernel", st, 2.0 * (double)p.M * (double)p.N * (double)p.K * p.nbatch,
@@ -586,9 +695,15 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
     else if (p.conv_mode == 2) gemm_mma_kernel<2, 0><<<grid, 256, 0, st>>>(p);
     else if (x3) gemm_mma_kernel<0, 1><<<grid, 256, 0, st>>>(p);
     else gemm_mma_kernel<0, 0><<<grid, 256, 0, st>>>(p);
-  } else if (p.conv_mode == 1) gemm_kernel<1><<<grid, 256, 0, st>>>(p);
-  else if (p.conv_mode == 2) gemm_kernel<2><<<grid, 256, 0, st>>>(p);
-  else gemm_kernel<0><<<grid, 256, 0, st>>>(p);
+  } else if (fvec) {
+    if (a_kf && b_kf) gemm_fp32_vec_kernel<1, 1><<<grid, 256, 0, st>>>(p);
+    else if (a_kf) gemm_fp32_vec_kernel<1, 0><<<grid, 256, 0, st>>>(p);
+    else if (b_kf) gemm_fp32_vec_kernel<0, 1><<<grid, 256, 0, st>>>(p);
+    else gemm_fp32_vec_kernel<0, 0><<<grid, 256, 0, st>>>(p);
+  } else if (p.conv_mode == 1) gemm_kernel<1, 64><<<grid, 256, 0, st>>>(p);
+  else if (p.conv_mode == 2) gemm_kernel<2, 64><<<grid, 256, 0, st>>>(p);
+  else if (small) gemm_kernel<0, 32><<<grid, 256, 0, st>>>(p);
+  else gemm_kernel<0, 64><<<grid, 256, 0, st>>>(p);
   WGG_CHECK_LAUNCH(ctx, "gemm_kernel");
   if (p.splitk > 1) {
     if (p.scn != 1 || p.scm != p.N)
