@@ -638,25 +638,39 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
 // pairs of the persistent CTA (3 x 168 = 504 columns); each CTA writes one partial block.
 //   grid (ctas_per_dir, 2 dirs); 288 threads: warp 0 MMA, warps 1..8 producers then read-out.
 // ---------------------------------------------------------------------------------------------
-constexpr int DW_THREADS = 288;
-constexpr int DW_BLK = TM * 128;      // 16384 B: one 32-wide block of 128 rows
-constexpr int DW_NB = 5;              // B operand blocks (160 features)
-constexpr int DW_COLS = 168;          // 160 + 8 (bias) columns per M group
+// K-major formulation (K = the gestures of a tile): both operands must hold FOUR CONSECUTIVE GESTURES of one
+// gate / feature row in 16 bytes, i.e. the transpose of the HBM chunk layout (four gates / features of one gesture).
+// MN-major TF32 operands (which would read the HBM layout as is) run at about a quarter of the K-major MMA rate
+// (DESIGN.md section 4), so sixteen producer warps transpose on the fly instead: coalesced 16-byte loads (lane =
+// gesture), a 4x4 transpose inside each lane quad (4 SHFL), conflict-free 16-byte shared stores into the canonical
+// no-swizzle K-major layout (k-chunk stride padded by 64 B).  A = da^T (192 gate rows: one M = 128 and one M = 64
+// MMA per k-step), B = [x | h_prev | 1 | 0]^T (N = 160: x 0..95, h 96..143, ones row 144 -> bias column).
+// Half tiles (64 gestures) double-buffered; accumulators stay in TMEM over all (t, tile) pairs of the persistent CTA.
+constexpr int DW_THREADS = 672;                 // warp 0: MMA issuer; warps 1..4: cp.async loaders; warps 5..20: transposers, then read-out
+constexpr int DW_LOADERS = 4;
+constexpr int DW_N = 160;                       // B rows = columns of the accumulators
+constexpr int DW_BIAS_COL = 144;
+constexpr int DW_Q = 32;                        // gestures per stage (a quarter tile)
+constexpr int DW_KC = DW_Q / 4;                 // k-chunks per stage
+constexpr int DW_LBO_A = N4 * 16 + 64;          // 3136 B between k-chunks of the A tile
+constexpr int DW_LBO_B = DW_N * 16 + 64;        // 2624 B
+constexpr int DW_STAGE = DW_KC * (DW_LBO_A + DW_LBO_B);  // 46080 B
+constexpr int DW_RAW_CHUNKS = HID + 24 + KH_CHUNKS;      // 84: da | x | h_prev chunks of one pair
+constexpr int DW_RAW_SLOT = DW_RAW_CHUNKS * DW_Q * 16;   // 43008 B: a quarter tile in HBM order
+constexpr int DW_NRAW = 3;
 
-__device__ __forceinline__ uint64_t make_desc_mn_dw(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((DW_BLK >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
-  return d;
-}
-__device__ __forceinline__ uint32_t dw_off(int r, int q) {  // 16-byte group (row r, 4-wide chunk q) inside a tile
-  return (uint32_t)((q >> 3) * DW_BLK + r * 128 + ((((q & 7) >> 1) ^ (r & 3)) << 5) + ((q & 1) << 4));
-}
-__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ float4 quad_transpose(float4 v, int lane) {
+  // lanes 4q..4q+3 hold rows r0..r3 of a 4x4 block; afterwards lane 4q+j holds column j
+  const bool odd = lane & 1, hi = lane & 2;
+  float s0 = odd ? v.x : v.y, s1 = odd ? v.z : v.w;
+  s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+  s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  if (odd) { v.x = s0; v.z = s1; } else { v.y = s0; v.w = s1; }
+  float t0 = hi ? v.x : v.z, t1 = hi ? v.y : v.w;
+  t0 = __shfl_xor_sync(0xffffffffu, t0, 2);
+  t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+  if (hi) { v.x = t0; v.y = t1; } else { v.z = t0; v.w = t1; }
+  return v;
 }
 
 __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* __restrict__ da,
@@ -665,25 +679,32 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
                                                                    float* __restrict__ partial, int T, int ntiles,
                                                                    int* __restrict__ gerr) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_a = smem;                         // 6 blocks: da (192 gates, unit-major n')
-  uint8_t* s_b = s_a + 6 * DW_BLK;             // 5 blocks: [x (96) | h_prev (48) | 0 (16)]
-  uint8_t* s_one = s_b + DW_NB * DW_BLK;       // 1 block of ones
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + DW_BLK);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  uint8_t* s_raw = smem + 2 * DW_STAGE;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_raw + DW_NRAW * DW_RAW_SLOT);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 12);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
   const uint32_t bar0 = smem_u32(s_bar);
-  const uint32_t BAR_FULL = bar0, BAR_EMPTY = bar0 + 8, BAR_DONE = bar0 + 16;
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };            // operand stage filled (16 transposer warps)
+  auto BAR_EMPTY = [&](int s) { return bar0 + 16u + 8u * s; };     // operand stage consumed (MMA commit)
+  auto BAR_RAW_FULL = [&](int s) { return bar0 + 32u + 8u * s; };  // raw slot landed (bulk-copy bytes)
+  auto BAR_RAW_EMPTY = [&](int s) { return bar0 + 56u + 8u * s; }; // raw slot read by all transposer warps
+  const uint32_t BAR_DONE = bar0 + 80u;
   {
     float4* z = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < 11 * DW_BLK / 16; i += DW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* o = reinterpret_cast<float4*>(s_one);
-    for (int i = tid; i < DW_BLK / 16; i += DW_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = tid; i < 2 * DW_STAGE / 16; i += DW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    // the ones row of B (bias column of the accumulators): never overwritten by the transposers
+    for (int i = tid; i < 2 * DW_KC; i += DW_THREADS) {
+      const int st = i / DW_KC, kc = i % DW_KC;
+      *reinterpret_cast<float4*>(smem + st * DW_STAGE + DW_KC * DW_LBO_A + kc * DW_LBO_B + (DW_BIAS_COL / 8) * 128 +
+                                 (DW_BIAS_COL % 8) * 16) = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
   }
   if (tid == 0) {
-    mbar_init(BAR_FULL, 256);
-    mbar_init(BAR_EMPTY, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(BAR_FULL(st), 16); mbar_init(BAR_EMPTY(st), 1); }
+    for (int st = 0; st < DW_NRAW; ++st) { mbar_init(BAR_RAW_FULL(st), DW_LOADERS * 32); mbar_init(BAR_RAW_EMPTY(st), 16); }
     mbar_init(BAR_DONE, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -695,72 +716,126 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const int64_t npairs = (int64_t)T * ntiles;
+  const int nchunks = HID + xin_chunks + KH_CHUNKS;
+  const bool ts_on = g_fwd_ts_on && blockIdx.x == 0 && blockIdx.y == 0;
+#define TSD(k) do { if (ts_on && lane == 0) g_fwd_ts[(n & 127) * 8 + (k)] = clock64(); } while (0)
 
   if (warp == 0) {
     // MMA issuer: warp-uniform loop, one elected lane issues
-    const uint32_t id_main = make_idesc(64, 160, 1, 1), id_one = make_idesc(64, 8, 1, 1);
-    const uint64_t ad0 = make_desc_mn_dw(smem_u32(s_a)), bd0 = make_desc_mn_dw(smem_u32(s_b)), od0 = make_desc_mn_dw(smem_u32(s_one));
+    const uint32_t id128 = make_idesc(128, DW_N), id64 = make_idesc(64, DW_N);
     int n = 0;
     bool ok = true;
-    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
-      if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 51)) { ok = false; break; }
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll 2
-        for (int ks = 0; ks < TM / 8; ++ks) {
-          const uint32_t acc = (n | ks) ? 1u : 0u;
-          const uint64_t bd = bd0 + (uint64_t)(ks * 64), od = od0 + (uint64_t)(ks * 64);
+    for (int64_t pr = blockIdx.x; pr < npairs && ok; pr += gridDim.x) {
+      for (int q = 0; q < TM / DW_Q; ++q, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, gerr, 51)) { ok = false; break; }
+        tc_fence_after();
+        TSD(0);
+        const uint32_t a0 = smem_u32(smem) + st * DW_STAGE, b0 = a0 + DW_KC * DW_LBO_A;
+        const uint64_t ad0 = make_desc(a0, DW_LBO_A, 128), ad1 = make_desc(a0 + 16 * 128, DW_LBO_A, 128);
+        const uint64_t bd0 = make_desc(b0, DW_LBO_B, 128);
+        if (elect_one()) {
 #pragma unroll
-          for (int mg = 0; mg < 3; ++mg) {
-            const uint64_t ad = ad0 + (uint64_t)((2 * mg * DW_BLK) >> 4) + (uint64_t)(ks * 64);
-            mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS), ad, bd, id_main, acc);
-            mma_tf32_ss(tmem_base + (uint32_t)(mg * DW_COLS + 160), ad, od, id_one, acc);
+          for (int ks = 0; ks < DW_Q / 8; ++ks) {
+            const uint32_t acc = (n | ks) ? 1u : 0u;
+            const uint64_t astep = (uint64_t)(ks * ((2 * DW_LBO_A) >> 4)), bstep = (uint64_t)(ks * ((2 * DW_LBO_B) >> 4));
+            mma_tf32_ss(tmem_base, ad0 + astep, bd0 + bstep, id128, acc);
+            mma_tf32_ss(tmem_base + (uint32_t)DW_N, ad1 + astep, bd0 + bstep, id64, acc);
           }
+          mma_commit(BAR_EMPTY(st));
         }
-        mma_commit(BAR_EMPTY);
+        __syncwarp();
+        TSD(1);
       }
-      __syncwarp();
     }
     if (ok && elect_one()) mma_commit(BAR_DONE);
-  } else {
-    const int ptid = tid - 32;  // 0..255
+  } else if (warp <= DW_LOADERS) {
+    // loaders: 16-byte cp.async copies in HBM order (one warp instruction = the 32 gestures of one chunk), completion
+    // signalled on the slot's mbarrier by every thread; never blocks on data, so up to three quarter tiles are in
+    // flight.  (512-byte bulk copies were issue-bound here: ~57 clk each from a single warp.)
+    const int lw = warp - 1;
     int n = 0;
     bool ok = true;
-    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++n) {
-      if (!mbar_wait(BAR_EMPTY, (uint32_t)((n & 1) ^ 1), s_abort, gerr, 52)) { ok = false; break; }
+    for (int64_t pr = blockIdx.x; pr < npairs && ok; pr += gridDim.x) {
       const int t = (int)(pr / ntiles), tile = (int)(pr % ntiles);
       const int tp = dir ? t + 1 : t - 1;  // timestep whose h fed the recurrence at t
-      const uint32_t a0 = smem_u32(s_a), b0 = smem_u32(s_b);
-      const float4* sd = reinterpret_cast<const float4*>(da) + ((int64_t)dir * npairs + pr) * HID * TM;
-      for (int i = ptid; i < HID * TM; i += 256) cp16(a0 + dw_off(i % TM, i / TM), sd + i);
-      const float4* sx = reinterpret_cast<const float4*>(xin) + pr * xin_chunks * TM;
-      for (int i = ptid; i < xin_chunks * TM; i += 256) cp16(b0 + dw_off(i % TM, i / TM), sx + i);
-      if (tp >= 0 && tp < T) {
-        const float4* sh = reinterpret_cast<const float4*>(hself) + (((int64_t)tp * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * TM;
-        for (int i = ptid; i < KH_CHUNKS * TM; i += 256) cp16(b0 + dw_off(i % TM, 24 + i / TM), sh + i);
-      } else {
-        for (int i = ptid; i < KH_CHUNKS * TM; i += 256)
-          *reinterpret_cast<float4*>(s_b + dw_off(i % TM, 24 + i / TM)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool has_prev = tp >= 0 && tp < T;
+      const float4* sd = reinterpret_cast<const float4*>(da) + ((int64_t)dir * npairs + pr) * HID * TM + lane;
+      const float4* sx = reinterpret_cast<const float4*>(xin) + pr * xin_chunks * TM + lane;
+      const float4* sh = reinterpret_cast<const float4*>(hself) +
+                         (((int64_t)(has_prev ? tp : 0) * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * TM + lane;
+      const int nload = has_prev ? nchunks : nchunks - KH_CHUNKS;
+      for (int q = 0; q < TM / DW_Q; ++q, ++n) {
+        const int slot = n % DW_NRAW;
+        if (!mbar_wait(BAR_RAW_EMPTY(slot), (uint32_t)(((n / DW_NRAW) & 1) ^ 1), s_abort, gerr, 54)) { ok = false; break; }
+        if (lw == 0) TSD(6);
+        const uint32_t dst0 = smem_u32(s_raw) + slot * DW_RAW_SLOT + lane * 16;
+        for (int c = lw; c < nload; c += DW_LOADERS) {
+          const float4* src = c < HID ? sd + c * TM : (c < HID + xin_chunks ? sx + (c - HID) * TM : sh + (c - HID - xin_chunks) * TM);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + c * (DW_Q * 16)), "l"(src + q * DW_Q) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(BAR_RAW_FULL(slot)) : "memory");
+        if (lw == 0) TSD(7);
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_async_smem();
-      mbar_arrive(BAR_FULL);
+    }
+  } else {
+    const int tw = warp - 1 - DW_LOADERS;  // 0..15
+    int n = 0;
+    bool ok = true;
+    for (int64_t pr = blockIdx.x; pr < npairs && ok; pr += gridDim.x) {
+      const int t = (int)(pr / ntiles);
+      const int tp = dir ? t + 1 : t - 1;
+      const bool has_prev = tp >= 0 && tp < T;
+      for (int q = 0; q < TM / DW_Q; ++q, ++n) {
+        const int st = n & 1, slot = n % DW_NRAW;
+        if (!mbar_wait(BAR_RAW_FULL(slot), (uint32_t)((n / DW_NRAW) & 1), s_abort, gerr, 55)) { ok = false; break; }
+        if (tw == 0) TSD(2);
+        if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, gerr, 52)) { ok = false; break; }
+        if (tw == 0) TSD(3);
+        uint8_t* sa = smem + st * DW_STAGE;
+        uint8_t* sb = sa + DW_KC * DW_LBO_A;
+        const float4* raw = reinterpret_cast<const float4*>(s_raw + slot * DW_RAW_SLOT) + lane;
+        const int kc = lane >> 2, j = lane & 3;
+#pragma unroll 2
+        for (int c = tw; c < nchunks; c += 16) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < HID + xin_chunks || has_prev) v = raw[c * DW_Q];
+          const float4 w = quad_transpose(v, lane);
+          int row;
+          uint8_t* dst;
+          if (c < HID) { row = 4 * c + j; dst = sa + kc * DW_LBO_A; }
+          else if (c < HID + xin_chunks) { row = 4 * (c - HID) + j; dst = sb + kc * DW_LBO_B; }
+          else { row = 96 + 4 * (c - HID - xin_chunks) + j; dst = sb + kc * DW_LBO_B; }
+          *reinterpret_cast<float4*>(dst + (row >> 3) * 128 + (row & 7) * 16) = w;
+        }
+        if (tw == 0) TSD(4);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR_FULL(st));
+          mbar_arrive(BAR_RAW_EMPTY(slot));
+        }
+        if (tw == 0) TSD(5);
+      }
     }
     if (ok && mbar_wait(BAR_DONE, 0, s_abort, gerr, 53)) {
       tc_fence_after();
-      // M = 64 accumulators: rows in lanes 0..15 of each TMEM quarter; 8 producer warps = 2 per quarter split the columns
-      const int quarter = warp & 3, colhalf = (warp - 1) >> 2;
+      // accumulators: gates 0..127 in TMEM lanes 0..127 (cols 0..159); gates 128..191 as an M = 64 tile (lanes 0..15
+      // of each quarter, cols 160..319).  Four warps per quarter split the 160 columns.
+      const int quarter = warp & 3, cpart = tw >> 2;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      for (int mg = 0; mg < 3; ++mg) {
-        float* dst = partial + ((((int64_t)dir * gridDim.x + blockIdx.x) * 3 + mg) * 64 + quarter * 16 + lane) * DW_COLS;
-        for (int c0 = colhalf * 16; c0 < DW_COLS; c0 += 32) {
-          float r[16];
-          tmem_ld16(taddr + mg * DW_COLS + c0, r);
-          if (lane < 16) {
+      float* pbase = partial + ((int64_t)dir * gridDim.x + blockIdx.x) * N4 * DW_N;
+      for (int c0 = cpart * 40; c0 < cpart * 40 + 40; c0 += 8) {
+        float r[8];
+        tmem_ld8(taddr + c0, r);
+        float* d0 = pbase + (int64_t)(quarter * 32 + lane) * DW_N + c0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < DW_COLS) dst[c0 + i] = r[i];
-          }
+        for (int i = 0; i < 8; ++i) d0[i] = r[i];
+        tmem_ld8(taddr + DW_N + c0, r);
+        if (lane < 16) {
+          float* d1 = pbase + (int64_t)(128 + quarter * 16 + lane) * DW_N + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d1[i] = r[i];
         }
       }
     }
@@ -782,11 +857,10 @@ __global__ void dw_finalize_kernel(const float* __restrict__ partial, int nparts
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N4 * per_row; idx += gridDim.x * blockDim.x) {
     const int np = idx / per_row, c = idx % per_row;
     const int u = np >> 2, g = np & 3, prow = g * HID + u;
-    const int col = c < I ? c : (c < I + HID ? 96 + (c - I) : 160);
-    const int mg = np >> 6, r = np & 63;
+    const int col = c < I ? c : (c < I + HID ? 96 + (c - I) : DW_BIAS_COL);
     float s = 0.f;
 #pragma unroll 8
-    for (int p = 0; p < nparts; ++p) s += __ldg(partial + ((((int64_t)dir * nparts + p) * 3 + mg) * 64 + r) * DW_COLS + col);
+    for (int p = 0; p < nparts; ++p) s += __ldg(partial + (((int64_t)dir * nparts + p) * N4 + np) * DW_N + col);
     if (c < I) o[(int64_t)prow * I + c] += s;
     else if (c < I + HID) o[off_whh + (int64_t)prow * HID + (c - I)] += s;
     else { o[off_bih + prow] += s; o[off_bhh + prow] += s; }
@@ -1053,7 +1127,7 @@ int64_t generator_tc_bwd_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
   TcPlan p;
   if (!tc_plan(cfg, B, &p)) return 0;
   return 2 * p.h_floats + (int64_t)2 * p.T * p.rows * tc::N4 + 2 * tc::HID * tc::N4 + 4 * tc::HID * tc::N4 +
-         (int64_t)2 * kDwCtasPerDir * 3 * 64 * tc::DW_COLS;
+         (int64_t)2 * kDwCtasPerDir * tc::N4 * tc::DW_N;
 }
 
 bool generator_tc_supported(const wgg_model_cfg* cfg) {
@@ -1138,7 +1212,7 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   int cur = 0;
   constexpr size_t smem_bwd = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
   constexpr size_t smem_dx = (size_t)tc::HID * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
-  constexpr size_t smem_dw = (size_t)12 * tc::DW_BLK + 4 * 8 + 16;
+  constexpr size_t smem_dw = (size_t)2 * tc::DW_STAGE + tc::DW_NRAW * tc::DW_RAW_SLOT + 12 * 8 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tc::lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd) != cudaSuccess ||
