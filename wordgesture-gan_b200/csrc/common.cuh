@@ -125,6 +125,9 @@ struct GemmP {
   int force_fp32 = 0;
   const char* tag = nullptr;  // call-site label for the profiler
   int x3 = 0;  // tensor-core mode: error-compensated 3xTF32 (always on for conv windows)
+  // fp32 kernels only (nbatch == 1): rowsum[m] += sum_k A(m,k) in the same pass (bias gradient of a Linear layer's
+  // weight-gradient GEMM); with split-K the partial buffer holds M extra floats per split.
+  float* rowsum = nullptr;
 };
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
@@ -186,7 +189,7 @@ inline int ew_blocks(int64_t n) {
 // ----------------------------------------------------------------------------------------------
 int wgg_linear_fwd(wgg_ctx* ctx, const float* A, int64_t lda, const float* W, const float* bias, float* C,
                    int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t st);
-int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A, int64_t lda, float* dW, int64_t M,
+int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A, int64_t lda, float* dW, float* db, int64_t M,
                      int N, int K, int accumulate, float* part, cudaStream_t st);
 int wgg_linear_dgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* W, float* dA, int64_t lda, int64_t M,
                      int N, int K, int accumulate, cudaStream_t st);

@@ -512,8 +512,7 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
     const float* in = stash + l.in_off * B;
     if (dscore) {
       if (dparams) {
-        WGG_TRY(wgg_linear_wgrad(ctx, dscore, 1, in, l.cols, G + l.g_off, B, 1, l.cols, 0, part, st));
-        WGG_TRY(colsum_launch(ctx, dscore, B, 1, 1, 1, 0, dparams + l.off_b, nullptr, 0, 1, csws, st));
+        WGG_TRY(wgg_linear_wgrad(ctx, dscore, 1, in, l.cols, G + l.g_off, dparams + l.off_b, B, 1, l.cols, 0, part, st));
       }
       WGG_TRY(wgg_linear_dgrad(ctx, dscore, 1, sn + l.sn_wf, dcur, l.cols, B, 1, l.cols, 0, st));
     } else {
@@ -553,8 +552,7 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
       }
     } else {
       if (dparams) {
-        WGG_TRY(wgg_linear_wgrad(ctx, dcur, l.rows, in, l.cols, G + l.g_off, B, l.rows, l.cols, 0, part, st));
-        WGG_TRY(colsum_launch(ctx, dcur, B, l.rows, l.rows, 1, 0, dparams + l.off_b, nullptr, 0, 1, csws, st));
+        WGG_TRY(wgg_linear_wgrad(ctx, dcur, l.rows, in, l.cols, G + l.g_off, dparams + l.off_b, B, l.rows, l.cols, 0, part, st));
       }
       if (need_dgrad) {
         float* dst = (i == 0) ? dx : dnext;

@@ -75,9 +75,11 @@ int wgg_linear_fwd(wgg_ctx* ctx, const float* A, int64_t lda, const float* W, co
 }
 
 // dW (N x K) (+)= dY^T (M x N)^T * A (M x K), deterministic split over M
-int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A, int64_t lda, float* dW, int64_t M,
+int wgg_linear_wgrad(wgg_ctx* ctx, const float* dY, int64_t ldy, const float* A, int64_t lda, float* dW, float* db, int64_t M,
                      int N, int K, int accumulate, float* part, cudaStream_t st) {
+  // db (optional): bias gradient += column sums of dY, carried by the same GEMM (row sums of its A operand dY^T)
   GemmP p;
+  p.rowsum = db;
   p.A = dY; p.M = N; p.K = M; p.sam = 1; p.sak = ldy;
   p.B = A; p.N = K; p.sbk = lda; p.sbn = 1;
   p.C = dW; p.scm = K; p.scn = 1; p.accumulate = accumulate;
@@ -172,10 +174,8 @@ extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, cons
   WGG_CHECK_LAUNCH(ctx, "enc_head_bwd_kernel");
   const int last = e.dims[e.n];
   const float* hl = stash + e.act_off[e.n - 1] * B;
-  WGG_TRY(wgg_linear_wgrad(ctx, dmu_t, e.Z, hl, last, dparams + e.off_wmu, B, e.Z, last, 1, part, st));
-  WGG_TRY(colsum_launch(ctx, dmu_t, B, e.Z, e.Z, 1, 0, dparams + e.off_bmu, nullptr, 0, 1, csws, st));
-  WGG_TRY(wgg_linear_wgrad(ctx, dlv_t, e.Z, hl, last, dparams + e.off_wlv, B, e.Z, last, 1, part, st));
-  WGG_TRY(colsum_launch(ctx, dlv_t, B, e.Z, e.Z, 1, 0, dparams + e.off_blv, nullptr, 0, 1, csws, st));
+  WGG_TRY(wgg_linear_wgrad(ctx, dmu_t, e.Z, hl, last, dparams + e.off_wmu, dparams + e.off_bmu, B, e.Z, last, 1, part, st));
+  WGG_TRY(wgg_linear_wgrad(ctx, dlv_t, e.Z, hl, last, dparams + e.off_wlv, dparams + e.off_blv, B, e.Z, last, 1, part, st));
   WGG_TRY(wgg_linear_dgrad(ctx, dmu_t, e.Z, params + e.off_wmu, dh, last, B, e.Z, last, 0, st));
   WGG_TRY(wgg_linear_dgrad(ctx, dlv_t, e.Z, params + e.off_wlv, dh, last, B, e.Z, last, 1, st));
   for (int i = e.n - 1; i >= 0; --i) {
@@ -183,8 +183,7 @@ extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, cons
     const float* act = stash + e.act_off[i] * B;
     const float* in = i == 0 ? x : stash + e.act_off[i - 1] * B;
     WGG_TRY(leaky_bwd_launch(ctx, act, dh, nullptr, B * N, st));
-    WGG_TRY(wgg_linear_wgrad(ctx, dh, N, in, K, dparams + e.off_w[i], B, N, K, 1, part, st));
-    WGG_TRY(colsum_launch(ctx, dh, B, N, N, 1, 0, dparams + e.off_b[i], nullptr, 0, 1, csws, st));
+    WGG_TRY(wgg_linear_wgrad(ctx, dh, N, in, K, dparams + e.off_w[i], dparams + e.off_b[i], B, N, K, 1, part, st));
     if (i > 0) {
       WGG_TRY(wgg_linear_dgrad(ctx, dh, N, params + e.off_w[i], dh2, K, B, N, K, 0, st));
       float* t = dh; dh = dh2; dh2 = t;

@@ -136,11 +136,13 @@ __global__ void __launch_bounds__(256, BM_ == 64 ? 2 : 4) gemm_kernel(GemmP p) {
   la.init(p, m0, kt_begin * BK, tid);
   lb.init(p, n0, kt_begin * BK, tid);
 
-  float acc[RM][4];
+  float acc[RM][4], rs[RM];
 #pragma unroll
-  for (int i = 0; i < RM; ++i)
+  for (int i = 0; i < RM; ++i) {
+    rs[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
 
   const int tx = tid % 16, ty = tid / 16;
   float ra[RM], rb[4];
@@ -171,14 +173,27 @@ __global__ void __launch_bounds__(256, BM_ == 64 ? 2 : 4) gemm_kernel(GemmP p) {
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < RM; ++i)
+      for (int i = 0; i < RM; ++i) {
+        rs[i] += av[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
 
-  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
+  const int64_t pstride = p.M * p.N + (p.rowsum ? p.M : 0);
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * pstride : nullptr;
+  if (p.rowsum && blockIdx.y == 0 && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int64_t m = m0 + ty * RM + i;
+      if (m < p.M) {
+        if (P) P[p.M * p.N + m] = rs[i];
+        else p.rowsum[m] += rs[i];
+      }
+    }
+  }
   float* C = p.C + (int64_t)batch * p.bsC;
   const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
   const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(256, 3) gemm_fp32_vec_kernel(GemmP p) {
   const int64_t kt_end = min(ktiles, kt_begin + per);
   const int64_t lda = A_KF ? p.sam : p.sak, ldb = B_KF ? p.sbn : p.sbk;
 
-  float acc[4][4];
+  float acc[4][4], rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -266,13 +281,26 @@ __global__ void __launch_bounds__(256, 3) gemm_fp32_vec_kernel(GemmP p) {
       const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        rs[i] += av[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
-  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * p.M * p.N : nullptr;
+  const int64_t pstride = p.M * p.N + (p.rowsum ? p.M : 0);
+  float* P = p.splitk > 1 ? p.partial + (int64_t)blockIdx.z * pstride : nullptr;
+  if (p.rowsum && blockIdx.y == 0 && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + ty * 4 + i;
+      if (m < p.M) {
+        if (P) P[p.M * p.N + m] = rs[i];
+        else p.rowsum[m] += rs[i];
+      }
+    }
+  }
   float* C = p.C + (int64_t)batch * p.bsC;
   const float* bias = p.bias ? p.bias + (int64_t)batch * p.bsBias : nullptr;
   const float* bias2 = p.bias2 ? p.bias2 + (int64_t)batch * p.bsBias : nullptr;
@@ -607,6 +635,19 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   }
 }
 
+// split-K reduction of a GEMM that also carried row sums: partial = [S][MN + M]
+__global__ void __launch_bounds__(256) reduce_partials_rs_kernel(const float* __restrict__ P, int S, int64_t MN, int64_t M,
+                                                                 float* __restrict__ out, int accumulate,
+                                                                 float* __restrict__ rowsum) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = MN + M;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += P[(int64_t)k * n + i];
+  if (i < MN) out[i] = accumulate ? out[i] + s : s;
+  else rowsum[i - MN] += s;
+}
+
 // stage 1 of the column sum: block (32 cols, 8 row-lanes); grid (ceil(N/32), S, nbatch)
 __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ X, int64_t M, int64_t N, int64_t ldx,
                                                      int64_t bsX, int S, float* __restrict__ P) {
@@ -646,7 +687,8 @@ int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch
   return (int)want;
 }
 
-int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch) { return (int64_t)kMaxSplit * M * N * nbatch; }
+// + 2048 floats per split: room for the row sums a weight-gradient GEMM may carry (GemmP::rowsum, M <= 2048)
+int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch) { return (int64_t)kMaxSplit * (M * N + 2048) * nbatch; }
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return WGG_OK;
@@ -654,6 +696,8 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.splitk > 1 && (!p.partial || p.act != ACT_NONE || p.bias || p.bias2))
     return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K needs a partial buffer and a plain epilogue%s");
   const bool tf32 = ctx->math_mode >= 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
+  if (p.rowsum && (tf32 || p.nbatch != 1 || p.conv_mode != 0 || p.M > 2048))
+    return wgg_fail(ctx, WGG_EINVAL, "gemm: row sums are only carried by the plain fp32 kernels%s");
   // fp32 with 16-byte loads: every operand contiguous along k or along its tile direction, vector direction % 4
   const bool fa_kf = p.sak == 1, fa_mf = p.sam == 1, fb_kf = p.sbk == 1, fb_nf = p.sbn == 1;
   const bool fvec = !tf32 && p.conv_mode == 0 && (fa_kf || fa_mf) && (fb_kf || fb_nf) &&
@@ -708,6 +752,13 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   if (p.splitk > 1) {
     if (p.scn != 1 || p.scm != p.N)
       return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K output must be dense row-major%s");
+    if (p.rowsum) {
+      const int64_t n = p.M * p.N + p.M;
+      reduce_partials_rs_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(p.partial, p.splitk, p.M * p.N, p.M, p.C, p.accumulate,
+                                                                           p.rowsum);
+      WGG_CHECK_LAUNCH(ctx, "reduce_partials_rs_kernel");
+      return WGG_OK;
+    }
     WGG_TRY(reduce_partials_launch(ctx, p.partial, p.splitk, p.M * p.N, p.nbatch, (int64_t)p.splitk * p.M * p.N, p.C,
                                    nullptr, p.bsC, p.accumulate, st));
   }

@@ -78,29 +78,37 @@ __global__ void prep_weights_kernel(const float* __restrict__ lp, int64_t dir_st
 }
 
 // layer-0 input in tc layout, K padded to KX0 (zero fill), rows padded to the tile: (models.py:147-157)
-__global__ void build_x0_tc_kernel(const float* __restrict__ proto, const float* __restrict__ z, float* __restrict__ x0,
-                                   int T, int64_t B, int ntiles, int C, int pd, int Z, int KX0) {
-  // one thread = one 16-byte group (row, K chunk) in storage order: coalesced 16-byte stores
-  const int KC = KX0 / 4;
-  const int64_t n4 = (int64_t)T * ntiles * KC * TM;
-  float4* o4 = reinterpret_cast<float4*>(x0);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int row = (int)(i & (TM - 1));
-    const int64_t r1 = i >> 7;
-    const int chunk = (int)(r1 % KC);
-    const uint32_t pr = (uint32_t)(r1 / KC);
-    const int tile = (int)(pr % (uint32_t)ntiles), t = (int)(pr / (uint32_t)ntiles);
+__global__ void __launch_bounds__(256) build_x0_tc_kernel(const float* __restrict__ proto, const float* __restrict__ z,
+                                                          float* __restrict__ x0, int T, int64_t B, int ntiles, int C,
+                                                          int pd, int Z, int KX0) {
+  // block = (tile, 8 timesteps): the latent part of x0 is the same for every timestep, so the tile's z rows are
+  // staged once in shared memory (coalesced) and re-used; every store is a coalesced 16-byte group.
+  extern __shared__ float s_z[];  // [TM][Z + 1]
+  const int tile = blockIdx.x, t0 = blockIdx.y * 8;
+  const int KC = KX0 / 4, ZP = Z + 1;
+  for (int i = threadIdx.x; i < TM * Z; i += 256) {
+    const int row = i / Z, j = i % Z;
     const int64_t b = (int64_t)tile * TM + row;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (b < B) {
+    s_z[row * ZP + j] = b < B ? __ldg(z + b * Z + j) : 0.f;
+  }
+  __syncthreads();
+  float4* o4 = reinterpret_cast<float4*>(x0);
+  for (int tt = 0; tt < 8 && t0 + tt < T; ++tt) {
+    const int t = t0 + tt;
+    for (int i = threadIdx.x; i < KC * TM; i += 256) {
+      const int chunk = i >> 7, row = i & (TM - 1);
+      const int64_t b = (int64_t)tile * TM + row;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b < B) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = chunk * 4 + j;
-        if (k < pd) v[j] = __ldg(proto + (b * T + t) * C + k);
-        else if (k < pd + Z) v[j] = __ldg(z + b * Z + (k - pd));
+        for (int j = 0; j < 4; ++j) {
+          const int k = chunk * 4 + j;
+          if (k < pd) v[j] = __ldg(proto + (b * T + t) * C + k);
+          else if (k < pd + Z) v[j] = s_z[row * ZP + (k - pd)];
+        }
       }
+      o4[((int64_t)t * ntiles + tile) * KC * TM + i] = make_float4(rna_tf32(v[0]), rna_tf32(v[1]), rna_tf32(v[2]), rna_tf32(v[3]));
     }
-    o4[i] = make_float4(rna_tf32(v[0]), rna_tf32(v[1]), rna_tf32(v[2]), rna_tf32(v[3]));
   }
 }
 
@@ -1155,7 +1163,8 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
                                                          off_bhh[l], I, KX, ws + p.img_off[l], p.img_floats[l]);
     WGG_CHECK_LAUNCH(ctx, "prep_weights_kernel");
   }
-  tc::build_x0_tc_kernel<<<ew_blocks(p.x0_floats / 4), 256, 0, st>>>(proto, z, x0, p.T, B, p.ntiles, p.C, p.pd, p.Z, kKX0);
+  tc::build_x0_tc_kernel<<<dim3((unsigned)p.ntiles, (unsigned)((p.T + 7) / 8)), 256, (size_t)tc::TM * (p.Z + 1) * sizeof(float), st>>>(
+      proto, z, x0, p.T, B, p.ntiles, p.C, p.pd, p.Z, kKX0);
   WGG_CHECK_LAUNCH(ctx, "build_x0_tc_kernel");
   const float* in = x0;
   for (int l = 0; l < p.L; ++l) {
