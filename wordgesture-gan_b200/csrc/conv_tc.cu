@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a
 // row earlier, so that one start address reads tap j from the first copy and tap j+1 from the second; B = dpre
 // (N = co).  The bias gradient is one M = 64 MMA per k-step with A = ones.  Single-stage tiles (139 KB).
 // ---------------------------------------------------------------------------------------------
-constexpr int W2_THREADS = 288;  // warp 0: MMA issuer; warps 1..8: producers, then TMEM read-out
+constexpr int W2_THREADS = 320;  // warp 0: MMA issuer; warps 1..8: producers, then TMEM read-out; warp 9: bias column sums
 
 __device__ __forceinline__ uint64_t make_desc_mn_lbo(uint32_t saddr, uint32_t lbo) {
   uint64_t d = 0;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR_FULL(s), 128);
-      mbar_init(BAR_EMPTY(s), 1);
+      mbar_init(BAR_EMPTY(s), 2);  // MMA commit + the bias warp
     }
     mbar_init(BAR_DONE, 1);
     *s_abort = 0;
@@ -428,8 +428,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
 
   if (warp == 0) {
     // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues
-    const uint32_t id_main = make_idesc(128, Cout, 1, 1), id_bias = make_idesc(64, Cout, 1, 1);
-    const uint64_t od = make_desc_mn_lbo(smem_u32(s_one), 1024);
+    const uint32_t id_main = make_idesc(128, Cout, 1, 1);
     int n = 0;
     bool ok = true;
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
@@ -447,13 +446,39 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
           const uint64_t bd = bd0 + (uint64_t)(ks * 64);
           for (int p = 0; p < npairs; ++p)
             mma_tf32_ss(tmem_base + (uint32_t)(p * Cout), ad0 + (uint64_t)(ks * 64 + p * 16), bd, id_main, acc);
-          mma_tf32_ss(tmem_base + (uint32_t)(npairs * Cout), od, bd, id_bias, acc);
         }
         mma_commit(BAR_EMPTY(st));
       }
       __syncwarp();
     }
     if (ok && elect_one()) mma_commit(BAR_DONE);
+  } else if (warp == 9) {
+    // bias gradient db[co] = sum_t dpre[t][co]: one warp sums the dpre tile of every stage with plain FP32 adds (an
+    // MN-major ones-MMA for it cost a quarter of the kernel's tensor time); lane = channels 2*lane, 2*lane + 1
+    float b0 = 0.f, b1 = 0.f;
+    int n = 0;
+    bool ok = true;
+    const int q = lane >> 1;
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
+      const int st = n & 1;
+      if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 29)) { ok = false; break; }
+      if (q < a.CoutC) {
+        const uint8_t* d0 = smem + st * W2_STAGE + 4 * W_BLK + (lane & 1) * 8;
+#pragma unroll 8
+        for (int t = 0; t < T; ++t) {
+          const float2 v = *reinterpret_cast<const float2*>(d0 + w_off(t + PAD_ROWS, q));
+          b0 += v.x;
+          b1 += v.y;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_EMPTY(st));
+    }
+    if (ok && q < a.CoutC) {
+      float* prow = a.partial + (int64_t)blockIdx.x * 64 * a.ncols;
+      prow[(int64_t)(2 * lane) * a.ncols + a.taps * 64] = b0;
+      prow[(int64_t)(2 * lane + 1) * a.ncols + a.taps * 64] = b1;
+    }
   } else {
     // two producer groups (4 warps each); group g owns stage g and the samples g, g + 2, ... so that two samples'
     // loads are always in flight (a group blocks on its own copies only)
@@ -495,15 +520,6 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
 #pragma unroll
             for (int i = 0; i < 16; ++i) prow[(int64_t)(c0 + i) * a.ncols + tap * 64 + ci] = r[i];
           }
-        }
-      }
-      // bias: every row of the M = 64 accumulator holds db[co]; rows < 16 of quarter 0 are lanes 0..15
-      for (int c0 = chalf * 16; c0 < Cout; c0 += 32) {
-        float r[16];
-        tmem_ld16(taddr + npairs * Cout + c0, r);
-        if (quarter == 0 && lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) prow[(int64_t)(c0 + i) * a.ncols + a.taps * 64] = r[i];
         }
       }
     }
