@@ -34,3 +34,4 @@ for (Cout, Cin, taps, pad) in [(64, 64, 5, 2), (32, 64, 3, 1), (64, 3, 5, 2)]:
     nbytes = B * T * 4 * (Cout + Cin4)
     print(f"wgrad Cout={Cout} Cin={Cin} taps={taps}: wgrad+finalize {tot:7.1f} us; kernel {k_us:7.1f} us -> {nbytes / k_us / 1e3:7.1f} GB/s "
           f"(floor {nbytes / 6.55e3 / 1e3:5.1f} us), async_err {_lib.async_error(dev)}")
+

@@ -370,48 +370,43 @@ __global__ void __launch_bounds__(W_THREADS, 1) conv_tc_wgrad_kernel(WgradArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weight gradient, 64-input-channel layers, full-rate formulation: the transposed problem
-//     G^T[(tap, ci)][co] = sum_t in[t + tap - pad][ci] * dpre[t][co]
-// with M = 128 = TWO taps x 64 input channels per MMA (M = 64 MMAs run far below the M = 128 rate).  The A operand
-// is a 4-block MN-major tile [x_b0, x_b1, x'_b0, x'_b1] where x' is a second copy of the input tile stored one
-// row earlier, so that one start address reads tap j from the first copy and tap j+1 from the second; B = dpre
-// (N = co).  The bias gradient is one M = 64 MMA per k-step with A = ones.  Single-stage tiles (139 KB).
+// Weight gradient, 64-input-channel layers, K-MAJOR formulation (an earlier MN-major version of this kernel - operands
+// read in HBM order - was bound by the MN-major TF32 operand fetch, roughly a quarter of the K-major rate: ~180 clk per
+// M128 x N64 x K8 MMA).  Gt[(tap, ci)][co] = sum_t x[t + tap - pad][ci] * dpre[t][co] with K = time: a K-major operand row must hold
+// four consecutive time steps in 16 bytes - the transpose of the HBM layout - and a tap is a shift along K that is not
+// a multiple of the 16-byte chunk.  So the operand tile holds four alignment variants X_a[ci][k] = x[k + a - pad][ci]
+// (a = 0..3; tap s' uses variant s' % 4 at chunk offset s' / 4), stacked as rows: [X_0; X_1] and [X_2; X_3] are M = 128
+// operands that each produce two taps per MMA.  Per gesture: one loader warp bulk-copies the two HBM tiles (2 KB per
+// channel chunk, chunk stride padded to 2064 B so that the gathers below are bank-conflict-free), sixteen transposer
+// warps build the K-major tiles quarter by quarter (each 16-byte group = four conflict-free 4-byte shared loads +
+// one 16-byte store; the bias gradient is summed on the way), one warp issues the MMAs; accumulators stay in TMEM.
 // ---------------------------------------------------------------------------------------------
-constexpr int W2_THREADS = 320;  // warp 0: MMA issuer; warps 1..8: producers, then TMEM read-out; warp 9: bias column sums
+constexpr int W3_THREADS = 576;        // warp 0: MMA issuer; warp 1: loader; warps 2..17: transposers, then read-out
+constexpr int W3_RCS = 2064;           // raw chunk stride (2048 + 16)
+constexpr int W3_RAW_T = 16 * W3_RCS;  // one raw tensor tile (16 chunks)
+constexpr int W3_RAW_SLOT = 2 * W3_RAW_T;
+constexpr int W3_LBO_A = 256 * 16, W3_LBO_B = 64 * 16;
+constexpr int W3_KCH = 8;              // k-chunks (32 time steps) per operand stage, + 1 halo chunk for chunk offset 1
+constexpr int W3_STAGE_A = (W3_KCH + 1) * W3_LBO_A, W3_STAGE = W3_STAGE_A + W3_KCH * W3_LBO_B;  // 45056 B
 
-__device__ __forceinline__ uint64_t make_desc_mn_lbo(uint32_t saddr, uint32_t lbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
-  return d;
-}
-
-constexpr int W2_STAGE = 6 * W_BLK;  // x (4 blocks: two copies) + dpre (2 blocks)
-
-__global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(W3_THREADS, 1) conv_tc_wgrad3_kernel(WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_one = smem + 2 * W2_STAGE;   // 2 blocks x 8 rows of ones (every k-step reads the same 8 rows)
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_one + 2048);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  uint8_t* s_raw = smem + 2 * W3_STAGE;
+  float* s_bias = reinterpret_cast<float*>(s_raw + 2 * W3_RAW_SLOT);  // [16 warps][64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 16 * 64);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 10);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(s_bar);
-  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };
-  auto BAR_EMPTY = [&](int s) { return bar0 + 16u + 8u * s; };
-  const uint32_t BAR_DONE = bar0 + 32u;
-  {
-    float4* z = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < 2 * W2_STAGE / 16; i += W2_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* o = reinterpret_cast<float4*>(s_one);
-    for (int i = tid; i < 2048 / 16; i += W2_THREADS) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-  }
+  auto BAR_FULL = [&](int s) { return bar0 + 8u * s; };             // operand stage built (16 transposer warps)
+  auto BAR_EMPTY = [&](int s) { return bar0 + 16u + 8u * s; };      // operand stage consumed (MMA commit)
+  auto BAR_RAW_FULL = [&](int s) { return bar0 + 32u + 8u * s; };   // raw tiles landed
+  auto BAR_RAW_EMPTY = [&](int s) { return bar0 + 48u + 8u * s; };  // raw tiles read by all transposer warps
+  const uint32_t BAR_DONE = bar0 + 64u;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR_FULL(s), 128);
-      mbar_init(BAR_EMPTY(s), 2);  // MMA commit + the bias warp
+      mbar_init(BAR_FULL(s), 16); mbar_init(BAR_EMPTY(s), 1);
+      mbar_init(BAR_RAW_FULL(s), 1); mbar_init(BAR_RAW_EMPTY(s), 16);
     }
     mbar_init(BAR_DONE, 1);
     *s_abort = 0;
@@ -425,100 +420,143 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_tc_wgrad2_kernel(WgradArgs
   const uint32_t tmem_base = *s_tmem;
   const int Cout = a.CoutC * 4;
   const int npairs = (a.taps + 1) / 2;
+  const bool halo = a.taps > 4;  // taps 4, 5 read their variant one chunk further
 
   if (warp == 0) {
-    // MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues
-    const uint32_t id_main = make_idesc(128, Cout, 1, 1);
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t idesc = make_idesc(128, Cout);
     int n = 0;
     bool ok = true;
-    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-      const int st = n & 1;
-      if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 26)) { ok = false; break; }
-      tc_fence_after();
-      const uint32_t x0 = smem_u32(smem) + st * W2_STAGE, d0 = x0 + 4 * W_BLK;
-      // descriptors advance by 8 rows (1024 B -> 64 in the 16-byte address field) per k-step
-      const uint64_t bd0 = make_desc_mn(d0 + PAD_ROWS * 128);
-      const uint64_t ad0 = make_desc_mn(x0 + (PAD_ROWS - a.pad) * 128);
-      if (elect_one()) {
-#pragma unroll 4
-        for (int ks = 0; ks < T / 8; ++ks) {
-          const uint32_t acc = (n | ks) ? 1u : 0u;
-          const uint64_t bd = bd0 + (uint64_t)(ks * 64);
-          for (int p = 0; p < npairs; ++p)
-            mma_tf32_ss(tmem_base + (uint32_t)(p * Cout), ad0 + (uint64_t)(ks * 64 + p * 16), bd, id_main, acc);
+    for (int64_t b = blockIdx.x; b < a.B && ok; b += gridDim.x) {
+      for (int qd = 0; qd < T / 32; ++qd, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 61)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem) + st * W3_STAGE;
+        const uint64_t ad0 = make_desc(a0, W3_LBO_A, 128), bd0 = make_desc(a0 + W3_STAGE_A, W3_LBO_B, 128);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < W3_KCH / 2; ++ks) {
+            const uint32_t acc = (n | ks) ? 1u : 0u;
+            const uint64_t bd = bd0 + (uint64_t)(ks * ((2 * W3_LBO_B) >> 4));
+            for (int p = 0; p < npairs; ++p) {
+              const int av = (2 * p) & 3, o = (2 * p) >> 2;  // variant pair [X_av; X_av+1] at chunk offset o
+              mma_tf32_ss(tmem_base + (uint32_t)(p * Cout),
+                          ad0 + (uint64_t)((av * 1024 + (2 * ks + o) * W3_LBO_A) >> 4), bd, idesc, acc);
+            }
+          }
+          mma_commit(BAR_EMPTY(st));
         }
-        mma_commit(BAR_EMPTY(st));
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (ok && elect_one()) mma_commit(BAR_DONE);
-  } else if (warp == 9) {
-    // bias gradient db[co] = sum_t dpre[t][co]: one warp sums the dpre tile of every stage with plain FP32 adds (an
-    // MN-major ones-MMA for it cost a quarter of the kernel's tensor time); lane = channels 2*lane, 2*lane + 1
-    float b0 = 0.f, b1 = 0.f;
+  } else if (warp == 1) {
+    // loader: one 2 KB bulk copy per channel chunk (lanes 0..15: x, lanes 16..31: dpre)
     int n = 0;
-    bool ok = true;
-    const int q = lane >> 1;
     for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x, ++n) {
-      const int st = n & 1;
-      if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, a.gerr, 29)) { ok = false; break; }
-      if (q < a.CoutC) {
-        const uint8_t* d0 = smem + st * W2_STAGE + 4 * W_BLK + (lane & 1) * 8;
-#pragma unroll 8
-        for (int t = 0; t < T; ++t) {
-          const float2 v = *reinterpret_cast<const float2*>(d0 + w_off(t + PAD_ROWS, q));
-          b0 += v.x;
-          b1 += v.y;
-        }
-      }
+      const int slot = n & 1;
+      if (!mbar_wait(BAR_RAW_EMPTY(slot), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, a.gerr, 62)) break;
+      if (lane == 0) mbar_expect_tx(BAR_RAW_FULL(slot), (uint32_t)(16 + a.CoutC) * (T * 16));
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR_EMPTY(st));
-    }
-    if (ok && q < a.CoutC) {
-      float* prow = a.partial + (int64_t)blockIdx.x * 64 * a.ncols;
-      prow[(int64_t)(2 * lane) * a.ncols + a.taps * 64] = b0;
-      prow[(int64_t)(2 * lane + 1) * a.ncols + a.taps * 64] = b1;
+      const uint32_t dst = smem_u32(s_raw) + slot * W3_RAW_SLOT;
+      if (lane < 16) {
+        bulk_g2s(dst + lane * W3_RCS, reinterpret_cast<const uint8_t*>(a.in) + (b * 16 + lane) * (int64_t)(T * 16), T * 16,
+                 BAR_RAW_FULL(slot));
+      } else if (lane - 16 < a.CoutC) {
+        bulk_g2s(dst + W3_RAW_T + (lane - 16) * W3_RCS,
+                 reinterpret_cast<const uint8_t*>(a.dpre) + (b * a.CoutC + (lane - 16)) * (int64_t)(T * 16), T * 16,
+                 BAR_RAW_FULL(slot));
+      }
     }
   } else {
-    // two producer groups (4 warps each); group g owns stage g and the samples g, g + 2, ... so that two samples'
-    // loads are always in flight (a group blocks on its own copies only)
-    const int ptid = (tid - 32) & 127, g = (tid - 32) >> 7;
-    int k = 0;
+    const int tw = warp - 2;                 // 0..15
+    const int comp = lane & 3, cl = lane >> 2;
+    // static work split (no per-item decoding): warp tw builds variant av = tw / 4 for channel group cg = (tw / 2) % 2,
+    // k-chunks [j0, j1) of every stage, plus ONE dpre chunk (channel group tw / 8, k-chunk tw % 8)
+    const int av = tw >> 2, cg = (tw >> 1) & 1;
+    const int j0 = (tw & 1) ? 4 : 0;
+    const int j1 = (tw & 1) ? ((halo && av < 2) ? W3_KCH + 1 : W3_KCH) : 4;  // halo chunk only feeds [X_0; X_1] at offset 1
+    const int ca = cg * 8 + cl;                         // channel chunk of the A rows; channel = 4 ca + comp
+    const int ra = av * 64 + 4 * ca + comp;
+    const uint32_t a_src = ca * W3_RCS + comp * 4, a_dst = (ra >> 3) * 128 + (ra & 7) * 16;
+    const int bcg = tw >> 3, bj = tw & 7;
+    const bool b_on = bcg * 8 < a.CoutC;
+    const int cb = bcg * 8 + cl, rb = 4 * cb + comp;
+    const uint32_t b_src = cb * W3_RCS + comp * 4 + 4 * bj * 16, b_dst = bj * W3_LBO_B + (rb >> 3) * 128 + (rb & 7) * 16;
+    float bsum = 0.f;                        // bias partial of channel bcg*32 + lane (this warp's share of the time steps)
+    int n = 0, ns = 0;
     bool ok = true;
-    const uint32_t x0 = smem_u32(smem) + g * W2_STAGE, d0 = x0 + 4 * W_BLK;
-    for (int64_t b = blockIdx.x + (int64_t)g * gridDim.x; b < a.B; b += 2 * (int64_t)gridDim.x, ++k) {
-      if (!mbar_wait(BAR_EMPTY(g), (uint32_t)((k & 1) ^ 1), s_abort, a.gerr, 27)) { ok = false; break; }
-      // lane -> (4 consecutive rows) x (8 consecutive chunks): 64-byte global segments, conflict-free 512-byte smem rows
-      const float4* sd = reinterpret_cast<const float4*>(a.dpre) + b * (int64_t)a.CoutC * T;
-      for (int i = ptid; i < a.CoutC * T; i += 128) {
-        const int q = ((i >> 3) / T) * 8 + (i & 7), t = (i >> 3) % T;
-        cp_async16(d0 + w_off(t + PAD_ROWS, q), sd + q * T + t);
+    for (int64_t b = blockIdx.x; b < a.B && ok; b += gridDim.x, ++ns) {
+      const int slot = ns & 1;
+      if (!mbar_wait(BAR_RAW_FULL(slot), (uint32_t)((ns >> 1) & 1), s_abort, a.gerr, 63)) { ok = false; break; }
+      const uint8_t* rx = s_raw + slot * W3_RAW_SLOT;
+      const uint8_t* rd = rx + W3_RAW_T;
+      for (int qd = 0; qd < T / 32; ++qd, ++n) {
+        const int st = n & 1;
+        if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, a.gerr, 64)) { ok = false; break; }
+        uint8_t* sa = smem + st * W3_STAGE;
+        uint8_t* sb = sa + W3_STAGE_A;
+        {
+          int t0 = 4 * (W3_KCH * qd + j0) + av - a.pad;
+          const uint8_t* src = rx + a_src;
+          uint8_t* dst = sa + a_dst + j0 * W3_LBO_A;
+#pragma unroll
+          for (int jj = 0; jj < 5; ++jj) {
+            if (j0 + jj < j1) {  // warp-uniform
+              float v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i;
+                v[i] = (unsigned)t < (unsigned)T ? *reinterpret_cast<const float*>(src + t * 16) : 0.f;
+              }
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+              t0 += 4;
+              dst += W3_LBO_A;
+            }
+          }
+        }
+        if (b_on) {
+          const uint8_t* src = rd + b_src + qd * (W3_KCH * 4 * 16);
+          const float v0 = *reinterpret_cast<const float*>(src), v1 = *reinterpret_cast<const float*>(src + 16);
+          const float v2 = *reinterpret_cast<const float*>(src + 32), v3 = *reinterpret_cast<const float*>(src + 48);
+          bsum += (v0 + v1) + (v2 + v3);
+          *reinterpret_cast<float4*>(sb + b_dst) = make_float4(v0, v1, v2, v3);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR_FULL(st));
       }
-      const float4* si = reinterpret_cast<const float4*>(a.in) + b * (int64_t)16 * T;
-      for (int i = ptid; i < 16 * T; i += 128) {
-        const int q = ((i >> 3) / T) * 8 + (i & 7), t = (i >> 3) % T;
-        cp_async16(x0 + w_off(t + PAD_ROWS, q), si + q * T + t);                   // copy 1: row t + 2
-        cp_async16(x0 + 2 * W_BLK + w_off(t + PAD_ROWS - 1, q), si + q * T + t);   // copy 2: one row earlier (= tap + 1)
-      }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_async_smem();
-      mbar_arrive(BAR_FULL(g));
+      if (!ok) break;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_RAW_EMPTY(slot));
     }
-    if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 28)) {
+    // bias: warp tw summed channels (tw/8)*32 + lane over k-chunks = tw%8 (mod 8): combine the eight partials of each
+    // channel group in fixed order
+    s_bias[tw * 32 + lane] = bsum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    float* prow = a.partial + (int64_t)blockIdx.x * 64 * a.ncols;
+    if (ok && tw < 2 && tw * 32 + lane < Cout) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += s_bias[(tw * 8 + w) * 32 + lane];
+      prow[(int64_t)(tw * 32 + lane) * a.ncols + a.taps * 64] = sum;
+    }
+    if (ok && mbar_wait(BAR_DONE, 0, s_abort, a.gerr, 65)) {
       tc_fence_after();
-      // D_p[m = tapbit*64 + ci][co] (M = 128: lane = m).  Two warps per TMEM quarter split the co columns.
-      const int quarter = warp & 3, chalf = (warp - 1) >> 2;
+      // D_p[m = tapbit*64 + ci][co] (M = 128: TMEM lane = m).  Four warps per TMEM quarter split the co columns.
+      const int quarter = warp & 3, cpart = tw >> 2;
       const int m = quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      float* prow = a.partial + (int64_t)blockIdx.x * 64 * a.ncols;
+      const int cw = Cout / 4;  // columns per warp (16 or 8)
       for (int p = 0; p < npairs; ++p) {
         const int tap = 2 * p + (m >> 6), ci = m & 63;
-        for (int c0 = chalf * 16; c0 < Cout; c0 += 32) {
-          float r[16];
-          tmem_ld16(taddr + p * Cout + c0, r);
+        for (int c0 = cpart * cw; c0 < cpart * cw + cw; c0 += 8) {
+          float r[8];
+          tmem_ld8(taddr + p * Cout + c0, r);
           if (tap < a.taps) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) prow[(int64_t)(c0 + i) * a.ncols + tap * 64 + ci] = r[i];
+            for (int i = 0; i < 8; ++i) prow[(int64_t)(c0 + i) * a.ncols + tap * 64 + ci] = r[i];
           }
         }
       }
@@ -689,14 +727,14 @@ int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64
     ProfScope prof(ctx, "conv_tc_wgrad_kernel", st, 2.0 * (double)B * ctc::T * Cout * (double)(taps * Cin),
                    (double)B * ctc::T * 4.0 * (Cout + CinC * 4), "conv_tc_wgrad_kernel");
     if (CinC == 16) {
-      const size_t smem2 = (size_t)2 * ctc::W2_STAGE + 2048 + 8 * 8 + 16;
-      static bool configured2 = false;
-      if (!configured2) {
-        if (cudaFuncSetAttribute(ctc::conv_tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
-          return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad2_kernel: cannot reserve shared memory%s");
-        configured2 = true;
+      const size_t smem3 = (size_t)2 * ctc::W3_STAGE + 2 * ctc::W3_RAW_SLOT + 16 * 64 * 4 + 10 * 8 + 16;
+      static bool configured3 = false;
+      if (!configured3) {
+        if (cudaFuncSetAttribute(ctc::conv_tc_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) != cudaSuccess)
+          return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad3_kernel: cannot reserve shared memory%s");
+        configured3 = true;
       }
-      ctc::conv_tc_wgrad2_kernel<<<grid, ctc::W2_THREADS, smem2, st>>>(a);
+      ctc::conv_tc_wgrad3_kernel<<<grid, ctc::W3_THREADS, smem3, st>>>(a);
     } else {
       ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);
     }
@@ -750,3 +788,4 @@ int chunk_to_rows_launch(wgg_ctx* ctx, const float* in, float* out, int64_t B, i
   WGG_CHECK_LAUNCH(ctx, "chunk_to_rows_kernel");
   return WGG_OK;
 }
+

@@ -725,8 +725,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
   const uint32_t tmem_base = *s_tmem;
   const int64_t npairs = (int64_t)T * ntiles;
   const int nchunks = HID + xin_chunks + KH_CHUNKS;
-  const bool ts_on = g_fwd_ts_on && blockIdx.x == 0 && blockIdx.y == 0;
-#define TSD(k) do { if (ts_on && lane == 0) g_fwd_ts[(n & 127) * 8 + (k)] = clock64(); } while (0)
 
   if (warp == 0) {
     // MMA issuer: warp-uniform loop, one elected lane issues
@@ -738,7 +736,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
         const int st = n & 1;
         if (!mbar_wait(BAR_FULL(st), (uint32_t)((n >> 1) & 1), s_abort, gerr, 51)) { ok = false; break; }
         tc_fence_after();
-        TSD(0);
         const uint32_t a0 = smem_u32(smem) + st * DW_STAGE, b0 = a0 + DW_KC * DW_LBO_A;
         const uint64_t ad0 = make_desc(a0, DW_LBO_A, 128), ad1 = make_desc(a0 + 16 * 128, DW_LBO_A, 128);
         const uint64_t bd0 = make_desc(b0, DW_LBO_B, 128);
@@ -753,7 +750,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
           mma_commit(BAR_EMPTY(st));
         }
         __syncwarp();
-        TSD(1);
       }
     }
     if (ok && elect_one()) mma_commit(BAR_DONE);
@@ -776,14 +772,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
       for (int q = 0; q < TM / DW_Q; ++q, ++n) {
         const int slot = n % DW_NRAW;
         if (!mbar_wait(BAR_RAW_EMPTY(slot), (uint32_t)(((n / DW_NRAW) & 1) ^ 1), s_abort, gerr, 54)) { ok = false; break; }
-        if (lw == 0) TSD(6);
         const uint32_t dst0 = smem_u32(s_raw) + slot * DW_RAW_SLOT + lane * 16;
         for (int c = lw; c < nload; c += DW_LOADERS) {
           const float4* src = c < HID ? sd + c * TM : (c < HID + xin_chunks ? sx + (c - HID) * TM : sh + (c - HID - xin_chunks) * TM);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + c * (DW_Q * 16)), "l"(src + q * DW_Q) : "memory");
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(BAR_RAW_FULL(slot)) : "memory");
-        if (lw == 0) TSD(7);
       }
     }
   } else {
@@ -797,9 +791,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
       for (int q = 0; q < TM / DW_Q; ++q, ++n) {
         const int st = n & 1, slot = n % DW_NRAW;
         if (!mbar_wait(BAR_RAW_FULL(slot), (uint32_t)((n / DW_NRAW) & 1), s_abort, gerr, 55)) { ok = false; break; }
-        if (tw == 0) TSD(2);
         if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n >> 1) & 1) ^ 1), s_abort, gerr, 52)) { ok = false; break; }
-        if (tw == 0) TSD(3);
         uint8_t* sa = smem + st * DW_STAGE;
         uint8_t* sb = sa + DW_KC * DW_LBO_A;
         const float4* raw = reinterpret_cast<const float4*>(s_raw + slot * DW_RAW_SLOT) + lane;
@@ -816,14 +808,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) lstm_tc_dw_kernel(const float* 
           else { row = 96 + 4 * (c - HID - xin_chunks) + j; dst = sb + kc * DW_LBO_B; }
           *reinterpret_cast<float4*>(dst + (row >> 3) * 128 + (row & 7) * 16) = w;
         }
-        if (tw == 0) TSD(4);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(BAR_FULL(st));
           mbar_arrive(BAR_RAW_EMPTY(slot));
         }
-        if (tw == 0) TSD(5);
       }
     }
     if (ok && mbar_wait(BAR_DONE, 0, s_abort, gerr, 53)) {
