@@ -1074,9 +1074,11 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
     configured = true;
   }
   dim3 grid((unsigned)ntiles, 2);
-  // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out
+  // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out, and for the
+  // grad-carrying forward the stash it has to write (gates + c: 960 B per gesture-step-direction, + h_rm rows)
   ProfScope prof(ctx, "lstm_tc_fwd_kernel", st, 2.0 * T * (double)B * 2.0 * tc::N4 * (KXC * 4 + tc::HID),
-                 (double)T * B * 4.0 * (2.0 * KXC * 4 + 96));
+                 (double)T * B * 4.0 * (2.0 * KXC * 4 + 96) +
+                     (STASH ? (double)T * B * (2.0 * tc::GC_CHUNKS * 16 + (h_rm ? 96 * 4.0 : 0.0)) : 0.0));
   tc::lstm_tc_fwd_kernel<KXC, STASH><<<grid, tc::NTHREADS, smem, st>>>(xin, img, img_stride, hout, T, ntiles, gc, h_rm, B,
                                                                          ctx->async_err);
   WGG_CHECK_LAUNCH(ctx, "lstm_tc_fwd_kernel");
