@@ -88,6 +88,11 @@ WGG_API int wgg_async_error(wgg_ctx* ctx, int* code);
  *     own CUDA path, cuDNN TF32), nn.Linear layers stay fp32;
  * 2 = "tf32x3": LSTM as in 1, conv contractions in error-compensated 3xTF32 (fp32-grade gradients). */
 WGG_API int wgg_set_math_mode(wgg_ctx* ctx, int mode);
+/* A context may be driven from two CUDA streams at once (the two independent critic chains of the training step,
+ * src/shared/utils.py:68-109, run concurrently).  Calls issued for the second stream are bracketed with
+ * wgg_set_lane(ctx, 1) ... wgg_set_lane(ctx, 0) so that the library's internal reduction scratch of the two chains
+ * never aliases (host-side state; no device work).  lane is 0 or 1. */
+WGG_API int wgg_set_lane(wgg_ctx* ctx, int lane);
 
 /* ---- Generator: replaces Generator.forward, src/gan/models.py:125-165 (+ its autograd) --------
  * params layout: nn.LSTM order - per layer, per direction: weight_ih (4H,I), weight_hh (4H,H),

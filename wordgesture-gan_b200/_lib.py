@@ -39,6 +39,7 @@ _SIG = {
     "wgg_last_error": (c_char_p, [_P]),
     "wgg_launch_count": (c_int64, [_P]),
     "wgg_set_math_mode": (c_int, [_P, c_int]),
+    "wgg_set_lane": (c_int, [_P, c_int]),
     "wgg_async_error": (c_int, [_P, POINTER(c_int)]),
     "wgg_profile_report": (c_int, [_P, c_char_p, c_int64]),
     "wgg_profile_enable": (c_int, [_P, c_char_p]),
@@ -171,15 +172,43 @@ def stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_lane = 0
+
+
+class lane:
+    """Context manager for calls issued on the SECOND of two concurrently driven streams (train_step runs the two
+    critic chains side by side): they get their own scratch workspace and their own half of the library's
+    reduction-scratch ring (wgg_set_lane)."""
+
+    def __init__(self, device, k: int = 1):
+        self.device, self.k = device, k
+
+    def __enter__(self):
+        global _lane
+        self.prev = _lane
+        _lane = self.k
+        c = ctx(self.device)
+        check(lib().wgg_set_lane(c, self.k), c)
+        return self
+
+    def __exit__(self, *exc):
+        global _lane
+        _lane = self.prev
+        c = ctx(self.device)
+        check(lib().wgg_set_lane(c, self.prev), c)
+        return False
+
+
 def workspace(device, nfloats: int) -> torch.Tensor:
-    """Grow-only per-device scratch buffer.  All calls of a process are issued on one stream at a time,
-    so a single buffer is shared by every entry point."""
+    """Grow-only scratch buffer per (device, lane).  All calls of one lane are issued on one stream at a time, so a
+    single buffer is shared by every entry point of that lane."""
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    w = _ws.get(idx)
+    key = (idx, _lane)
+    w = _ws.get(key)
     if w is None or w.numel() < nfloats:
-        _ws[idx] = None
-        w = _ws[idx] = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
+        _ws[key] = None
+        w = _ws[key] = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
     return w
 
 

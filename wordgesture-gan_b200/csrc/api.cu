@@ -49,6 +49,12 @@ extern "C" int wgg_set_math_mode(wgg_ctx* ctx, int mode) {
   return WGG_OK;
 }
 
+extern "C" int wgg_set_lane(wgg_ctx* ctx, int lane) {
+  if (!ctx || lane < 0 || lane > 1) return WGG_EINVAL;
+  ctx->lane = lane;
+  return WGG_OK;
+}
+
 extern "C" int wgg_profile_enable(wgg_ctx* ctx, const char* kernel_substr) {
   if (!ctx) return WGG_EINVAL;
   ctx->prof_n = 0;

@@ -15,7 +15,8 @@ struct wgg_ctx {
   // device scratch for reduction partials (allocated once in wgg_create): a ring of slots so that
   // consecutive reductions queued on one stream never share a slot with a finalize still in flight.
   float* red_scratch = nullptr;
-  int red_slot = 0;
+  int red_slot[2] = {0, 0};
+  int lane = 0;  // which of the two concurrently driven streams the next calls belong to (wgg_set_lane)
   // device word set by a persistent kernel whose pipeline wedged (bounded mbarrier waits); see wgg_async_error
   int* async_err = nullptr;
   // optional per-kernel-class CUDA-event timing (bench.py's roofline): see wgg_profile_enable
@@ -52,8 +53,10 @@ struct ProfScope {
 constexpr int kRedBlocks = 296;  // 2 x 148 SMs
 constexpr int kRedSlots = 64;
 inline float* wgg_next_partial(wgg_ctx* ctx) {
-  float* p = ctx->red_scratch + (size_t)ctx->red_slot * kRedBlocks;
-  ctx->red_slot = (ctx->red_slot + 1) % kRedSlots;
+  // each lane rotates through its own half of the ring
+  const int half = kRedSlots / 2;
+  float* p = ctx->red_scratch + (size_t)(ctx->lane * half + ctx->red_slot[ctx->lane]) * kRedBlocks;
+  ctx->red_slot[ctx->lane] = (ctx->red_slot[ctx->lane] + 1) % half;
   return p;
 }
 

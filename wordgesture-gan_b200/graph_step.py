@@ -36,9 +36,15 @@ class GraphedTrainStep:
         self.proto.copy_(torch.rand(self.proto.shape, device=dev, generator=gen) * 2 - 1)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                train_batch(trainer, self.real, self.proto, max_norm)
+        prev_par = getattr(trainer, "parallel_critics", "auto")
+        if prev_par == "auto":
+            trainer.parallel_critics = True   # warm up the two-stream critic phase the capture will use
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    train_batch(trainer, self.real, self.proto, max_norm)
+        finally:
+            trainer.parallel_critics = prev_par
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._restore(snap)

@@ -65,6 +65,11 @@ class DataParallelGAN:
         for opt in (trainer.optimizer_G, trainer.optimizer_E, trainer.optimizer_D1, trainer.optimizer_D2):
             opt.process_group = group if group is not None else dist.group.WORLD
             opt.world_size = self.world_size
+        # the D2 chain of the critic phase runs on its own stream next to the D1 chain (train_step.train_batch):
+        # give its all-reduces their own communicator so that collectives of the two chains never share one
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+        self.group_d2 = dist.new_group(ranks=ranks)
+        trainer.optimizer_D2.process_group = self.group_d2
         self.sync_state()
 
     def sync_state(self):

@@ -35,6 +35,13 @@ def n_noise_draws(training_config) -> int:
     return 2 * training_config.n_critic + 3
 
 
+def _critic_side_stream(trainer, dev):
+    st = getattr(trainer, "_critic_stream", None)
+    if st is None:
+        st = trainer._critic_stream = torch.cuda.Stream(device=dev)
+    return st
+
+
 def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, max_norm: float,
                 noise: Optional[List[torch.Tensor]] = None, on_step=None) -> Dict[str, torch.Tensor]:
     """One batch of the step.  ``noise`` optionally injects the 2*n_critic+3 (B, Z) normal draws in consumption
@@ -74,19 +81,39 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
                 fake_all = trainer.generator(prototype.repeat(2, 1, 1), torch.cat([zs[0], z_enc], 0))
         fakes_1 = fake_all[:n * B].view(n, B, *fake_all.shape[1:])
         fakes_2 = fake_all[n * B:].view(n, B, *fake_all.shape[1:])
+    # The D1 chain and the D2 chain are independent (different networks, optimisers and fake batches; they only read
+    # `real`), so D2's steps are issued on a second stream: its many small launches (Linear layers, spectral norm,
+    # reductions) overlap D1's bandwidth-bound conv kernels and vice versa.  Inside a captured CUDA graph the two
+    # chains become parallel branches.  Results are identical to the sequential order.
+    # Eager execution is bound by host launch issue, where a second stream only adds synchronisation calls, so the
+    # side stream is used under graph capture (and by the capture's warm-up) only.
+    main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+    par = getattr(trainer, "parallel_critics", "auto")
+    use_side = main is not None and n > 0 and (par is True or (par == "auto" and torch.cuda.is_current_stream_capturing()))
+    side = _critic_side_stream(trainer, dev) if use_side else None
+    if side is not None:
+        side.wait_stream(main)
+
+    def d_step(name, disc, opt, fake, critic_it):
+        opt.zero_grad()
+        real_scores = disc(real_gesture)
+        fake_scores = disc(fake)
+        loss = WassersteinLoss.discriminator_loss(real_scores, fake_scores)
+        loss.backward()
+        if on_step is not None:
+            on_step(f"{name[:2].upper()}_grads_{critic_it}", opt)
+        opt.step(max_norm=max_norm)
+        out[name] = loss.detach()
+
     for critic_it in range(n):
-        for name, disc, opt, fakes in (("d1_loss", trainer.discriminator_1, trainer.optimizer_D1, fakes_1),
-                                       ("d2_loss", trainer.discriminator_2, trainer.optimizer_D2, fakes_2)):
-            fake = fakes[critic_it]
-            opt.zero_grad()
-            real_scores = disc(real_gesture)
-            fake_scores = disc(fake)
-            loss = WassersteinLoss.discriminator_loss(real_scores, fake_scores)
-            loss.backward()
-            if on_step is not None:
-                on_step(f"{name[:2].upper()}_grads_{critic_it}", opt)
-            opt.step(max_norm=max_norm)
-            out[name] = loss.detach()
+        d_step("d1_loss", trainer.discriminator_1, trainer.optimizer_D1, fakes_1[critic_it], critic_it)
+        if side is not None:
+            with torch.cuda.stream(side), _lib.lane(dev, 1):
+                d_step("d2_loss", trainer.discriminator_2, trainer.optimizer_D2, fakes_2[critic_it], critic_it)
+        else:
+            d_step("d2_loss", trainer.discriminator_2, trainer.optimizer_D2, fakes_2[critic_it], critic_it)
+    if side is not None:
+        main.wait_stream(side)
 
     trainer.optimizer_G.zero_grad()
     trainer.optimizer_E.zero_grad()
