@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   uint8_t* s_h = s_x + NSTAGE * SB_BYTES;
   float* s_bias = reinterpret_cast<float*>(s_h + KH_CHUNKS * CHUNK_BYTES_A);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + N4);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 20);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
   auto BAR_ACC_FULL = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
   auto BAR_ACC_EMPTY = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
-  const uint32_t BAR_H = bar0 + 8u * (2 * NSTAGE + 4);
+  auto BAR_H = [&](int ph) { return bar0 + 8u * (2 * NSTAGE + 4 + ph); };  // h chunks {ph, 3+ph, 6+ph, 9+ph} written
 
   // ---- one-time setup -------------------------------------------------------------------------
   {
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       mbar_init(BAR_ACC_FULL(b), 1);
       mbar_init(BAR_ACC_EMPTY(b), EPI_WARPS);
     }
-    mbar_init(BAR_H, EPI_WARPS);
+    for (int ph = 0; ph < 3; ++ph) mbar_init(BAR_H(ph), EPI_WARPS);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
     uint32_t phase = 0;
     bool ok = true;
     const uint32_t wx = smem_u32(s_wx), wh = smem_u32(s_wh), hs = smem_u32(s_h);
-    const uint64_t bdx0 = make_desc(wx, CHUNK_BYTES_W, 128), bdh0 = make_desc(wh, CHUNK_BYTES_W, 128);
-    const uint64_t adh0 = make_desc(hs, CHUNK_BYTES_A, 128);
+    const uint64_t bdx0 = make_desc(wx, CHUNK_BYTES_W, 128);
+    const uint64_t adh3 = make_desc(hs, 3 * CHUNK_BYTES_A, 128), bdh3 = make_desc(wh, 3 * CHUNK_BYTES_W, 128);  // chunk pairs (c, c+3)
     constexpr uint64_t kAStep = (2 * CHUNK_BYTES_A) >> 4, kWStep = (2 * CHUNK_BYTES_W) >> 4;
     for (int step = 0; step < T && ok; ++step) {
       const int b = step & 1;
@@ -242,19 +242,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       }
       if (!ok) break;
       if (lane == 0) TS(1);
+      // recurrent part, pipelined against the gate math of the previous step: every epilogue warp writes its h chunks
+      // in three phases; as soon as phase ph is complete the two MMAs over K chunks (ph, 3+ph) and (6+ph, 9+ph) are
+      // issued (the pair's second chunk is addressed through the descriptor's leading-byte-offset), so only the last
+      // third of W_hh h is exposed after the gate math
       if (step > 0) {
-        if (!mbar_wait(BAR_H, (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) break;
-        tc_fence_after();
-        if (lane == 0) TS(2);
-      }
-      if (elect_one()) {
-        if (step > 0) {
+        for (int ph = 0; ph < 3; ++ph) {
+          if (!mbar_wait(BAR_H(ph), (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) { ok = false; break; }
+          tc_fence_after();
+          if (lane == 0 && ph == 0) TS(2);
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < KH_CHUNKS / 2; ++j)
-            mma_tf32_ss(tacc, adh0 + (uint64_t)j * kAStep, bdh0 + (uint64_t)j * kWStep, kIdesc, 1u);
+            for (int g2 = 0; g2 < 2; ++g2)
+              mma_tf32_ss(tacc, adh3 + (uint64_t)(((6 * g2 + ph) * CHUNK_BYTES_A) >> 4),
+                          bdh3 + (uint64_t)(((6 * g2 + ph) * CHUNK_BYTES_W) >> 4), kIdesc, 1u);
+          }
+          __syncwarp();
         }
-        mma_commit(BAR_ACC_FULL(b));
+        if (!ok) break;
       }
+      if (elect_one()) mma_commit(BAR_ACC_FULL(b));
       __syncwarp();
       if (lane == 0) TS(3);
     }
@@ -337,11 +344,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
             *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
                 make_float4(hraw[0], hraw[1], hraw[2], hraw[3]);
         }
+        if (warp == 2 && lane == 0 && ch == 2) TS(6);
+        fence_async_smem();   // this phase's h chunk is visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR_H(ch));
       }
-      if (warp == 2 && lane == 0) TS(6);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR_H);
       if (warp == 2 && lane == 0) TS(7);
     }
   }
@@ -1066,7 +1073,7 @@ template <int KXC, int STASH>
 int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_stride, float* hout, int T, int ntiles,
                  int64_t B, float* gc, float* h_rm, cudaStream_t st) {
   constexpr size_t smem = (size_t)KXC * tc::CHUNK_BYTES_W + tc::KH_CHUNKS * tc::CHUNK_BYTES_W + tc::NSTAGE * tc::SB_BYTES +
-                          tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 16 * 8 + 16;
+                          tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 20 * 8 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tc::lstm_tc_fwd_kernel<KXC, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
