@@ -547,24 +547,27 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
                                                                    const float* __restrict__ wimg,
                                                                    float* __restrict__ dx, int T, int ntiles,
                                                                    int out_chunks, int* __restrict__ gerr) {
+  constexpr int NSTG = 3;                                 // ring of half da tiles (24 K-chunks = 48 KB each)
+  constexpr int HALF_CHUNKS = HID / 2, HALF_BYTES = HALF_CHUNKS * CHUNK_BYTES_A;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_a = smem;                                  // one da tile: 48 chunks x 2048 B
-  uint8_t* s_w = s_a + HID * CHUNK_BYTES_A;             // 2 dirs x (48 chunks x 768 B)
+  uint8_t* s_a = smem;
+  uint8_t* s_w = s_a + NSTG * HALF_BYTES;               // 2 dirs x (48 chunks x 768 B)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + 2 * HID * WT_CHUNK_BYTES);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NSTG + 2);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.y;
   const uint32_t bar0 = smem_u32(s_bar);
-  const uint32_t BAR_FULL = bar0, BAR_EMPTY = bar0 + 8, BAR_ACC_FULL = bar0 + 16, BAR_ACC_EMPTY = bar0 + 24;
+  auto BAR_FULL = [&](int st) { return bar0 + 8u * st; };
+  auto BAR_EMPTY = [&](int st) { return bar0 + 8u * (NSTG + st); };
+  const uint32_t BAR_ACC_FULL = bar0 + 8u * (2 * NSTG), BAR_ACC_EMPTY = bar0 + 8u * (2 * NSTG + 1);
   {
     const float4* src = reinterpret_cast<const float4*>(wimg + (int64_t)half * 2 * HID * N4);
     float4* dst = reinterpret_cast<float4*>(s_w);
     for (int i = tid; i < 2 * HID * N4 / 4; i += DX_THREADS) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
-    mbar_init(BAR_FULL, 1);
-    mbar_init(BAR_EMPTY, 1);
+    for (int st = 0; st < NSTG; ++st) { mbar_init(BAR_FULL(st), 1); mbar_init(BAR_EMPTY(st), 1); }
     mbar_init(BAR_ACC_FULL, 1);
     mbar_init(BAR_ACC_EMPTY, 4);
     *s_abort = 0;
@@ -583,10 +586,13 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
     if (lane == 0) {
       int n = 0;
       for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x)
-        for (int d = 0; d < 2; ++d, ++n) {
-          if (!mbar_wait(BAR_EMPTY, (uint32_t)((n & 1) ^ 1), s_abort, gerr, 41)) return;
-          mbar_expect_tx(BAR_FULL, HID * CHUNK_BYTES_A);
-          bulk_g2s(smem_u32(s_a), da + ((int64_t)d * npairs + pr) * tile_floats, HID * CHUNK_BYTES_A, BAR_FULL);
+        for (int dh = 0; dh < 4; ++dh, ++n) {   // (direction, K half)
+          const int st = n % NSTG;
+          if (!mbar_wait(BAR_EMPTY(st), (uint32_t)(((n / NSTG) & 1) ^ 1), s_abort, gerr, 41)) return;
+          mbar_expect_tx(BAR_FULL(st), HALF_BYTES);
+          bulk_g2s(smem_u32(s_a) + st * HALF_BYTES,
+                   reinterpret_cast<const uint8_t*>(da + ((int64_t)(dh >> 1) * npairs + pr) * tile_floats) + (dh & 1) * HALF_BYTES,
+                   HALF_BYTES, BAR_FULL(st));
         }
     }
   } else if (warp == 1) {
@@ -596,17 +602,19 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
     int n = 0, np = 0;
     for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x, ++np) {
       if (!mbar_wait(BAR_ACC_EMPTY, (uint32_t)((np & 1) ^ 1), s_abort, gerr, 42)) return;
-      for (int d = 0; d < 2; ++d, ++n) {
-        if (!mbar_wait(BAR_FULL, (uint32_t)(n & 1), s_abort, gerr, 43)) return;
+      for (int dh = 0; dh < 4; ++dh, ++n) {
+        const int st = n % NSTG;
+        if (!mbar_wait(BAR_FULL(st), (uint32_t)((n / NSTG) & 1), s_abort, gerr, 43)) return;
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bdd = bd0 + (uint64_t)(d * ((HID * WT_CHUNK_BYTES) >> 4));
+          const uint64_t ads = ad0 + (uint64_t)((st * HALF_BYTES) >> 4);
+          const uint64_t bdd = bd0 + (uint64_t)(((dh >> 1) * HID + (dh & 1) * HALF_CHUNKS) * (WT_CHUNK_BYTES >> 4));
 #pragma unroll
-          for (int j = 0; j < N4 / 8; ++j)
-            mma_tf32_ss(tmem_base, ad0 + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bdd + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
-                        idesc, (d | j) ? 1u : 0u);
-          mma_commit(BAR_EMPTY);
-          if (d == 1) mma_commit(BAR_ACC_FULL);
+          for (int j = 0; j < HALF_CHUNKS / 2; ++j)
+            mma_tf32_ss(tmem_base, ads + (uint64_t)(j * ((2 * CHUNK_BYTES_A) >> 4)), bdd + (uint64_t)(j * ((2 * WT_CHUNK_BYTES) >> 4)),
+                        idesc, (dh | j) ? 1u : 0u);
+          mma_commit(BAR_EMPTY(st));
+          if (dh == 3) mma_commit(BAR_ACC_FULL);
         }
         __syncwarp();
       }
@@ -647,11 +655,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) lstm_tc_dx_kernel(const float* 
 
 // ---------------------------------------------------------------------------------------------
 // dW_ih, dW_hh, db of one layer: G[n'][feat] = sum_{t, sample} da[n'] * [x_t | h_prev][feat];  db[n'] = sum da[n'].
-// Both operands MN-major (SWIZZLE_128B_BASE32B tiles [32-wide blocks][128 sample rows][128 B], see conv_tc.cu),
-// K = the 128 samples of a (t, tile) pair; M = 192 gates as three M=64 MMAs, N = 160 = 96 input features + 48
-// recurrent features (+16 zero), plus an N=8 MMA against ones for the bias.  Accumulators stay in TMEM across all
-// pairs of the persistent CTA (3 x 168 = 504 columns); each CTA writes one partial block.
-//   grid (ctas_per_dir, 2 dirs); 288 threads: warp 0 MMA, warps 1..8 producers then read-out.
+//   grid (ctas_per_dir, 2 dirs); each CTA writes one partial block [192 gates][160], reduced by dw_finalize_kernel.
 // ---------------------------------------------------------------------------------------------
 // K-major formulation (K = the gestures of a tile): both operands must hold FOUR CONSECUTIVE GESTURES of one
 // gate / feature row in 16 bytes, i.e. the transpose of the HBM chunk layout (four gates / features of one gesture).
@@ -1219,7 +1223,7 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   }
   int cur = 0;
   constexpr size_t smem_bwd = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
-  constexpr size_t smem_dx = (size_t)tc::HID * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
+  constexpr size_t smem_dx = (size_t)3 * (tc::HID / 2) * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 8 * 8 + 16;
   constexpr size_t smem_dw = (size_t)2 * tc::DW_STAGE + tc::DW_NRAW * tc::DW_RAW_SLOT + 12 * 8 + 16;
   static bool configured = false;
   if (!configured) {
