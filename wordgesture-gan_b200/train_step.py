@@ -72,8 +72,11 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
             epss.append(draw())
         with torch.no_grad():
             if n > 1:
-                real_rep = real_gesture.repeat(n, 1, 1)
-                z_enc, _, _ = trainer.encoder(real_rep, torch.cat(epss, 0))
+                # the encoder is deterministic up to the reparameterisation (models.py:80-86): mu / log_var of `real`
+                # are the same in every critic iteration, only eps differs - one encoder pass, n re-parameterisations
+                z0, mu, log_var = trainer.encoder(real_gesture, epss[0])
+                std = torch.exp(0.5 * log_var)
+                z_enc = torch.cat([z0] + [torch.addcmul(mu, e, std) for e in epss[1:]], 0)
                 proto_rep = prototype.repeat(2 * n, 1, 1)
                 fake_all = trainer.generator(proto_rep, torch.cat(zs + [z_enc], 0))
             else:
