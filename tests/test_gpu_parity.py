@@ -573,3 +573,79 @@ def test_multi_step_losses_track_cpu_restatement(case):
             worst = max(worst, dev)
             assert dev <= 1e-2, (case, step, k, out[k].item(), ref[k])
     print(f"multi-step {case}: worst relative loss deviation over {steps} steps = {worst:.2e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,steps,B", [("tiny_temporal", 12, 8), ("default", 3, 16)])
+def test_resynchronised_steps_match_cpu_restatement(case, steps, B):
+    """SURVEY.md 8(c) parity protocol (2): step-level comparison RE-SYNCHRONISED before every step.  The fp64 CPU
+    restatement trains freely; before each step its complete pre-step state (parameters, spectral-norm u/v buffers,
+    Adam moments and step counts) is loaded into the CUDA trainer, both take the step on the same batch and the same
+    13 noise tensors, and the 11 losses and the post-step parameters are compared (fp32 mode)."""
+    from oracle import torch_port
+    wgg.set_math_mode("fp32")
+    g = Golden(case)
+    ocfg = oracle_cfg(g)
+    tr = trainer_from_golden(g)
+    for m in (tr.generator, tr.encoder, tr.discriminator_1, tr.discriminator_2):
+        m.train()
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=ocfg, tc=O.TrainCfg(), dtype=torch.float64)
+    tp.load_state({m: g.init_state(m) for m in MODS})
+    opts = dict(G=tr.optimizer_G, E=tr.optimizer_E, D1=tr.optimizer_D1, D2=tr.optimizer_D2)
+    rng = np.random.default_rng(11)
+    worst_loss = worst_post = 0.0
+    for step in range(steps):
+        pre = tp.state()
+        for m in MODS:
+            load_state(getattr(tr, ATTR[m]), pre[m])
+            sd = tp.opt[m].state_dict()
+            if sd["state"]:
+                opts[m].load_state_dict(sd)
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)
+        real = f32(rng.uniform(-1, 1, (B, ocfg.seq_length, ocfg.input_dim)))
+        proto = f32(rng.uniform(-1, 1, (B, ocfg.seq_length, ocfg.input_dim)))
+        noise = [f32(rng.standard_normal((B, ocfg.latent_dim))) for _ in range(13)]
+        ref = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise)
+        out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise])
+        for k in LOSS_KEYS:
+            # the adversarial terms are means of critic scores that nearly cancel (|loss| ~ 1e-3) after five fp32
+            # Adam updates inside the batch: judge them on the scale of the scores (floor 1e-2), not of the residual
+            dev = abs(out[k].item() - ref[k]) / max(abs(ref[k]), 1e-2)
+            worst_loss = max(worst_loss, dev)
+            assert dev <= 5e-3, (case, step, k, out[k].item(), ref[k])
+        post = tp.state()
+        for m in MODS:
+            mod = getattr(tr, ATTR[m])
+            for k, prm in mod.named_parameters():
+                e = rel_l2(to_np(prm), post[m][k])
+                worst_post = max(worst_post, e)
+                assert e <= 5e-3, (case, step, m, k, e)
+    print(f"resynchronised {case}: {steps} steps, worst loss deviation {worst_loss:.2e}, worst post-step parameter "
+          f"rel-L2 {worst_post:.2e}")
+
+
+@pytest.mark.gpu
+def test_epoch_with_resident_loader_graph_equals_eager():
+    """train_epoch_with_grad_clip fed by the device-resident loader: three full batches of the
+    default model, once launch by launch and once through the captured CUDA graph (two-stream critic phase inside),
+    from the same initial state, shuffle seed and RNG state - same four epoch means."""
+    wgg.set_math_mode("tf32")
+    try:
+        mc, tc = wgg.ModelConfig(), wgg.TrainingConfig(batch_size=64)
+        gen = torch.Generator().manual_seed(9)
+        gest = (torch.rand(192, 128, 3, generator=gen) * 2 - 1).to(DEV)
+        prot = (torch.rand(192, 128, 3, generator=gen) * 2 - 1).to(DEV)
+        res = []
+        for use_graph in (False, True):
+            wgg.seed_everything(42)
+            tr = wgg.WordGestureGANTrainer(mc, tc, DEV)
+            tr.use_cuda_graph = use_graph
+            loader = wgg.DeviceResidentLoader(gest, prot, 64, shuffle=True, drop_last=True,
+                                              generator=torch.Generator(device=DEV).manual_seed(5))
+            torch.manual_seed(123)
+            torch.cuda.manual_seed(123)
+            res.append(wgg.train_epoch_with_grad_clip(tr, loader, 1.0, mc, tc, DEV))
+        for k in ("d1_loss", "d2_loss", "cycle1_total", "cycle2_total"):
+            assert np.isfinite(res[0][k]) and abs(res[0][k] - res[1][k]) <= 1e-5 * max(1.0, abs(res[0][k])), (k, res)
+    finally:
+        wgg.set_math_mode("fp32")

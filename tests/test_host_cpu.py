@@ -182,3 +182,35 @@ def test_ctypes_signatures_match_header_arity_and_types():
                 assert a in (c_int, c_int32), (name, decl, a)
             else:
                 raise AssertionError(f"{name}: unhandled parameter declaration {decl!r}")
+
+
+def test_device_resident_loader_matches_dataloader_contract():
+    """the resident loader yields the reference's batch dicts (data.py:157-164, 526-533) - every
+    sample exactly once per epoch, gesture/prototype rows stay paired, seeded shuffles reproduce, drop_last / ragged
+    last batch follow torch.utils.data.DataLoader."""
+    import torch
+    import wgg_b200 as wgg
+    n, T = 23, 16
+    g = torch.arange(n, dtype=torch.float32).view(n, 1, 1).expand(n, T, 3).contiguous()
+    p = -g
+    words = [f"w{i}" for i in range(n)]
+    ld = wgg.DeviceResidentLoader(g, p, batch_size=8, shuffle=True, generator=torch.Generator().manual_seed(3), words=words)
+    assert len(ld) == 3
+    seen = []
+    for b in ld:
+        assert set(b) == {"gesture", "prototype", "word"}
+        assert b["gesture"].shape[1:] == (T, 3) and torch.equal(b["gesture"], -b["prototype"])
+        ids = b["gesture"][:, 0, 0].long().tolist()
+        assert b["word"] == [f"w{i}" for i in ids]
+        seen += ids
+    assert sorted(seen) == list(range(n)) and seen != list(range(n))
+    again = [i for b in wgg.DeviceResidentLoader(g, p, 8, True, generator=torch.Generator().manual_seed(3)) for i in b["gesture"][:, 0, 0].long().tolist()]
+    assert again == seen
+    ld2 = wgg.DeviceResidentLoader(g, p, batch_size=8, shuffle=False, drop_last=True)
+    sizes = [b["gesture"].size(0) for b in ld2]
+    assert sizes == [8, 8] and len(ld2) == 2
+    first = next(iter(ld2))["gesture"][:, 0, 0].tolist()
+    assert first == list(range(8))
+    import pytest
+    with pytest.raises(ValueError):
+        wgg.DeviceResidentLoader(g, p[:, :8], 4)
