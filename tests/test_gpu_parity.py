@@ -649,3 +649,41 @@ def test_epoch_with_resident_loader_graph_equals_eager():
             assert np.isfinite(res[0][k]) and abs(res[0][k] - res[1][k]) <= 1e-5 * max(1.0, abs(res[0][k])), (k, res)
     finally:
         wgg.set_math_mode("fp32")
+
+
+@pytest.mark.gpu
+def test_local_runner_checkpoints_and_resumes(tmp_path):
+    """run_training (the TRAIN_SCRIPT body, train_gan.py:60-200): 2 epochs -> latest.pt / epoch_2.pt in the reference's
+    checkpoint format; resuming to 3 epochs replays the cosine schedule (LR of epoch 3 equals the closed form) and
+    continues from the saved step counts."""
+    import math
+    wgg.set_math_mode("tf32")
+    try:
+        gen = torch.Generator().manual_seed(4)
+        gest = torch.rand(128, 128, 3, generator=gen) * 2 - 1
+        prot = torch.rand(128, 128, 3, generator=gen) * 2 - 1
+        tc = wgg.TrainingConfig(batch_size=64, num_epochs=3)
+        hist = wgg.run_training(gest, prot, 2, tmp_path, resume=True, training_config=tc, checkpoint_every=10,
+                                device=DEV, verbose=False)
+        assert [h["epoch"] for h in hist] == [1, 2] and all(np.isfinite(h["cycle1_total"]) for h in hist)
+        assert (tmp_path / "latest.pt").exists() and (tmp_path / "epoch_2.pt").exists()
+        ck = torch.load(tmp_path / "latest.pt", map_location="cpu")
+        assert ck["epoch"] == 1
+        for k in ("generator", "encoder", "discriminator_1", "discriminator_2", "optimizer_G", "optimizer_E",
+                  "optimizer_D1", "optimizer_D2"):
+            assert k in ck
+        assert "lstm.weight_ih_l0_reverse" in ck["generator"] and "temporal_conv.0.weight_u" in ck["discriminator_1"]
+        # 2 epochs x 2 batches: G/E stepped 4 times, each D 20 times
+        assert float(ck["optimizer_G"]["state"][0]["step"]) == 4.0 and float(ck["optimizer_D1"]["state"][0]["step"]) == 20.0
+        hist2 = wgg.run_training(gest, prot, 3, tmp_path, resume=True, training_config=tc, checkpoint_every=10,
+                                 device=DEV, verbose=False)
+        assert [h["epoch"] for h in hist2] == [3]
+        # CosineAnnealingLR(T_max=3, eta_min=1e-5) after 3 scheduler steps: eta_min
+        assert abs(hist2[0]["lr"] - 1e-5) < 1e-9
+        # first invocation: T_max = its own num_epochs = 2 (train_gan.py:95-100): half way after epoch 1, eta_min after 2
+        lr1 = 1e-5 + (2e-4 - 1e-5) * (1 + math.cos(math.pi * 1 / 2)) / 2
+        assert abs(hist[0]["lr"] - lr1) < 1e-9 and abs(hist[1]["lr"] - 1e-5) < 1e-9
+        ck3 = torch.load(tmp_path / "latest.pt", map_location="cpu")
+        assert ck3["epoch"] == 2 and float(ck3["optimizer_G"]["state"][0]["step"]) == 6.0
+    finally:
+        wgg.set_math_mode("fp32")

@@ -12,12 +12,13 @@ from .gan_trainer import WordGestureGANTrainer
 from .graph_step import GraphedTrainStep
 from .optim import FusedClipAdam
 from .resident_loader import DeviceResidentLoader
+from .runner import run_training
 from .train_step import log, seed_everything, train_batch, train_epoch_with_grad_clip
 
 __all__ = [
     "ModelConfig", "TrainingConfig", "DEFAULT_MODEL_CONFIG", "DEFAULT_TRAINING_CONFIG",
     "Generator", "VariationalEncoder", "Discriminator", "TemporalDiscriminator",
     "WassersteinLoss", "FeatureMatchingLoss", "ReconstructionLoss", "LatentEncodingLoss", "KLDivergenceLoss",
-    "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam", "GraphedTrainStep", "DeviceResidentLoader",
+    "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam", "GraphedTrainStep", "DeviceResidentLoader", "run_training",
     "set_math_mode", "get_math_mode", "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
 ]
