@@ -216,7 +216,6 @@ bool generator_tc_supported(const wgg_model_cfg* cfg);
 int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
 int64_t generator_tc_bwd_workspace_floats(const wgg_model_cfg* cfg, int64_t B);
 int64_t generator_tc_stash_floats(const wgg_model_cfg* cfg, int64_t B);
-float* generator_tc_stash_hrm(const wgg_model_cfg* cfg, int64_t B, float* stash);
 int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const int64_t* layer_off,
                          const int64_t* dir_stride, const int64_t* off_whh, const int64_t* off_bih,
                          const int64_t* off_bhh, int64_t off_wo, int64_t off_bo, const float* proto, const float* z,

@@ -895,10 +895,11 @@ __global__ void rows_to_chunk_kernel(const float* __restrict__ in, float* __rest
 //   dpre = dy * (1 - y^2);   dh = dpre * Wo  -> chunk layout (the top LSTM layer's dh);
 //   dWo += dpre^T * h,  dbo += sum dpre      -> per-CTA partials, reduced in fixed order by head_bwd_finalize_kernel.
 // Phase A: thread = gesture row (dpre to smem, 24 coalesced 16-byte stores of dh).  Phase B: thread = feature
-// (coalesced reads of the un-rounded h rows, three running sums).  HBM-bound: h read once, dh written once.
+// (reads the top layer's output in its chunk layout - the same TF32-rounded h the forward head multiplied - three
+// running sums).  HBM-bound: h read once, dh written once.
 constexpr int HEAD_MAXC = 4;
 __global__ void __launch_bounds__(128) head_bwd_tc_kernel(const float* __restrict__ y, const float* __restrict__ dy,
-                                                          const float* __restrict__ h_rm, const float* __restrict__ wo,
+                                                          const float* __restrict__ h_tc, const float* __restrict__ wo,
                                                           float* __restrict__ dh, float* __restrict__ part, int T,
                                                           int64_t B, int ntiles, int C) {
   __shared__ float s_wo[HEAD_MAXC * 96];
@@ -939,10 +940,11 @@ __global__ void __launch_bounds__(128) head_bwd_tc_kernel(const float* __restric
     const int64_t b0 = (int64_t)tile * TM;
     const int nrow = (int)((B - b0) < TM ? (B - b0) : TM);
     if (tid < 96) {
-      const float* hp = h_rm + ((int64_t)t * B + b0) * 96 + tid;
+      // feature tid of gesture r: chunk tid / 4, component tid % 4 of the chunk-layout tile [24][128][4]
+      const float* hp = h_tc + (pr * 24 + (tid >> 2)) * (int64_t)(TM * 4) + (tid & 3);
 #pragma unroll 8
       for (int r = 0; r < nrow; ++r) {
-        const float hv = __ldg(hp + (int64_t)r * 96);
+        const float hv = __ldg(hp + r * 4);
         const float4 d = *reinterpret_cast<const float4*>(s_dp + r * HEAD_MAXC);
         accw[0] = fmaf(d.x, hv, accw[0]);
         accw[1] = fmaf(d.y, hv, accw[1]);
@@ -1097,16 +1099,15 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
 }
 }  // namespace
 
-// ---- training stash of the tcgen05 path (floats):  x0_tc | h_tc[0..L-1] | gc[0..L-1] | h_rm (last layer) ----
+// ---- training stash of the tcgen05 path (floats):  x0_tc | h_tc[0..L-1] | gc[0..L-1] ----
 struct TcStash {
-  int64_t x0, h[WGG_MAX_HIDDEN_LAYERS], gc[WGG_MAX_HIDDEN_LAYERS], hrm, total;
+  int64_t x0, h[WGG_MAX_HIDDEN_LAYERS], gc[WGG_MAX_HIDDEN_LAYERS], total;
 };
 static void tc_stash_layout(const TcPlan& p, int64_t B, TcStash* s) {
   int64_t off = 0;
   s->x0 = off; off += p.x0_floats;
   for (int l = 0; l < p.L; ++l) { s->h[l] = off; off += p.h_floats; }
   for (int l = 0; l < p.L; ++l) { s->gc[l] = off; off += (int64_t)2 * p.T * p.rows * (tc::GC_CHUNKS * 4); }
-  s->hrm = off; off += (int64_t)p.T * B * 96;
   s->total = off;
 }
 
@@ -1116,15 +1117,6 @@ int64_t generator_tc_stash_floats(const wgg_model_cfg* cfg, int64_t B) {
   TcStash s;
   tc_stash_layout(p, B, &s);
   return s.total;
-}
-
-// row-major last-layer output inside a tcgen05 training stash (operand of the head's weight gradient)
-float* generator_tc_stash_hrm(const wgg_model_cfg* cfg, int64_t B, float* stash) {
-  TcPlan p;
-  if (!tc_plan(cfg, B, &p)) return nullptr;
-  TcStash s;
-  tc_stash_layout(p, B, &s);
-  return stash + s.hrm;
 }
 
 int64_t generator_tc_workspace_floats(const wgg_model_cfg* cfg, int64_t B) {
@@ -1173,7 +1165,7 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
   for (int l = 0; l < p.L; ++l) {
     float* hout = stash ? stash + sl.h[l] : hbuf[l & 1];
     float* gcl = stash ? stash + sl.gc[l] : nullptr;
-    float* hrm = (stash && l == p.L - 1) ? stash + sl.hrm : nullptr;
+    float* hrm = nullptr;  // the row-major copy of the top layer's output is no longer needed (head backward reads the chunk layout)
     const float* img = ws + p.img_off[l];
     if (l == 0) {
       if (stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
@@ -1214,7 +1206,7 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
     const int64_t npairs0 = (int64_t)p.T * p.ntiles;
     const int hgrid = (int)(npairs0 < 8 * (int64_t)ctx->sm_count ? npairs0 : 8 * (int64_t)ctx->sm_count);
     ProfScope prof(ctx, "head_bwd_tc_kernel", st, 4.0 * p.T * (double)B * 96 * cfg->input_dim, p.T * (double)B * 4.0 * (96 + 96));
-    tc::head_bwd_tc_kernel<<<hgrid, 128, 0, st>>>(out, dout, stash + sl.hrm, params + off_wo, dh[0], part, p.T, B, p.ntiles,
+    tc::head_bwd_tc_kernel<<<hgrid, 128, 0, st>>>(out, dout, stash + sl.h[p.L - 1], params + off_wo, dh[0], part, p.T, B, p.ntiles,
                                                   cfg->input_dim);
     WGG_CHECK_LAUNCH(ctx, "head_bwd_tc_kernel");
     tc::head_bwd_finalize_kernel<<<cfg->input_dim * 96 + cfg->input_dim, 128, 0, st>>>(part, hgrid, cfg->input_dim,
