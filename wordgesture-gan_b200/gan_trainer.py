@@ -46,8 +46,9 @@ class WordGestureGANTrainer:
         self.optimizer_D1 = FusedClipAdam(self.discriminator_1, lr=lr, betas=(0.5, 0.999))
         self.optimizer_D2 = FusedClipAdam(self.discriminator_2, lr=lr, betas=(0.5, 0.999))
         self.current_epoch = 0
-        # opt-in: train_epoch_with_grad_clip replays one captured CUDA graph per full batch (graph_step.py)
-        self.use_cuda_graph = False
+        # train_epoch_with_grad_clip replays one captured CUDA graph per full batch (graph_step.py): True / False force
+        # it on / off; "auto" uses it for epochs long enough to amortise warm-up + capture (>= 8 batches)
+        self.use_cuda_graph = "auto"
 
     # ---- generator-side cycles ------------------------------------------------------------------
     def _adversarial_terms(self, disc, fake, real):

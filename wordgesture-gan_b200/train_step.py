@@ -150,7 +150,13 @@ def train_epoch_with_grad_clip(trainer, dataloader, max_norm, model_config, trai
     keys = ("d1_loss", "d2_loss", "cycle1_total", "cycle2_total")
     sums = None
     num_batches = 0
-    use_graph = bool(getattr(trainer, "use_cuda_graph", False))
+    use_graph = getattr(trainer, "use_cuda_graph", False)
+    if use_graph == "auto":
+        try:
+            use_graph = torch.device(device).type == "cuda" and len(dataloader) >= 8
+        except TypeError:  # an iterable without a length
+            use_graph = False
+    use_graph = bool(use_graph)
     for batch in dataloader:
         real = batch["gesture"].to(device, non_blocking=True)
         proto = batch["prototype"].to(device, non_blocking=True)
