@@ -1,18 +1,21 @@
 // Persistent BiLSTM-layer forward on 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-// Replaces, for the no-grad generator calls (10 of the 12 per training batch: src/shared/utils.py:70-73,91-94;
-// and all of sampling: eval_gan.py:131-135), nn.LSTM's per-layer work of src/gan/models.py:160:
+// Replaces nn.LSTM's per-layer work of src/gan/models.py:160 for every generator call of the step (the no-grad
+// critic-phase calls, src/shared/utils.py:70-73,91-94; the grad-carrying calls of the G/E step, which also stash what
+// BPTT needs; and all of sampling, eval_gan.py:131-135):
 //     gates_t = x_t W_ih^T + h_{t-1} W_hh^T + b ;  c_t = f c_{t-1} + i g ;  h_t = o tanh(c_t)
 // One CTA owns a tile of 128 samples of one direction for all T timesteps:
 //   * W_ih, W_hh (TF32) stay resident in shared memory for the whole sequence;
 //   * x_t tiles stream in through a 5-stage ring of bulk asynchronous copies (cp.async.bulk -> mbarrier tx);
-//   * one elected thread issues tcgen05.mma kind::tf32 (M=128 samples, N=192 gates, K=8 per instruction), the
-//     accumulator lives in TMEM (two 192-column buffers: the x-projection of step t+1 is issued while the
-//     epilogue of step t still runs; only h_{t-1} W_hh^T sits on the recurrent critical path);
-//   * 8 epilogue warps read the accumulator with tcgen05.ld (one thread = one sample row, gates of a hidden
-//     unit are adjacent columns because the weight rows are permuted unit-major), apply the gate
+//   * one warp issues tcgen05.mma kind::tf32 (M=128 samples, N=192 gates, K=8 per instruction; warp-uniform loop,
+//     one elected lane), the accumulator lives in TMEM (two 192-column buffers: the x-projection of step t+1 is
+//     issued while the epilogue of step t still runs; h_{t-1} W_hh^T follows in three phases as the h chunks land);
+//   * 16 epilogue warps read the accumulator with tcgen05.ld (one thread = one sample row and 12 hidden units,
+//     gates of a hidden unit are adjacent columns because the weight rows are permuted unit-major), apply the gate
 //     non-linearities, keep c in registers, and write h_t both to shared memory (the next step's A operand)
 //     and to HBM (the next layer's input).
+// The rest of this file is the backward of the stack on the same layouts: BPTT, input gradient, weight gradient,
+// and the fused output-head backward.
 //
 // Operand layout ("tc layout", no swizzle, K-major core matrices): a [rows x K] fp32 matrix is stored as
 //   [K/4 chunks][rows/8 groups][8 rows][4 floats]   i.e. 128-byte core matrices (8 rows x 16 B);
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) build_x0_tc_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// the persistent layer kernel.  grid (ntiles, 2 directions), 320 threads, 1 CTA / SM.
+// the persistent layer kernel.  grid (ntiles, 2 directions), 576 threads, 1 CTA / SM.
 // xin : [T][ntiles][KXC][16][8][4]   hout : [T][ntiles][24][16][8][4] (this direction fills chunks dir*12..+12)
 // ---------------------------------------------------------------------------------------------
 // STASH = 1 (grad-carrying forward) additionally writes, per step, what BPTT needs:
