@@ -614,16 +614,23 @@ __global__ void pack_x4_kernel(const float* __restrict__ x, float* __restrict__ 
 
 // pooled[b][c*8+bin] = mean_{t in bin} a[b][c/4][t][c%4]     (AdaptiveAvgPool1d(8), models.py:312-315)
 __global__ void pool_fwd_chunk_kernel(const float* __restrict__ a, float* __restrict__ pooled, int64_t B, int C) {
-  const int64_t n = B * C * 8;
+  // one thread = (gesture, channel chunk, bin): sixteen contiguous 16-byte loads, four channel means
+  const int Cc = C / 4;
+  const int64_t n = B * Cc * 8;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int bin = (int)((i / C) % 8);
-    const int64_t b = i / ((int64_t)C * 8);
-    const float* p = a + ((b * (C / 4) + c / 4) * T + bin * 16) * 4 + (c & 3);
-    float s = 0.f;
+    const int bin = (int)(i & 7);
+    const uint32_t rest = (uint32_t)(i >> 3);          // b * Cc + q
+    const uint32_t q = rest % (uint32_t)Cc, b = rest / (uint32_t)Cc;
+    const float4* p = a4 + (int64_t)rest * T + bin * 16;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) s += __ldg(p + t * 4);
-    pooled[b * C * 8 + c * 8 + bin] = s * (1.f / 16.f);
+    for (int t = 0; t < 16; ++t) {
+      const float4 v = __ldg(p + t);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = pooled + (int64_t)b * C * 8 + (q * 4) * 8 + bin;
+    o[0] = s.x * (1.f / 16.f); o[8] = s.y * (1.f / 16.f); o[16] = s.z * (1.f / 16.f); o[24] = s.w * (1.f / 16.f);
   }
 }
 
@@ -752,7 +759,7 @@ int pack_x4_launch(wgg_ctx* ctx, const float* x, float* x4, int64_t B, int C, cu
 }
 
 int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B, int C, cudaStream_t st) {
-  ctc::pool_fwd_chunk_kernel<<<ew_blocks(B * C * 8), 256, 0, st>>>(a, pooled, B, C);
+  ctc::pool_fwd_chunk_kernel<<<ew_blocks(B * (C / 4) * 8), 256, 0, st>>>(a, pooled, B, C);
   WGG_CHECK_LAUNCH(ctx, "pool_fwd_chunk_kernel");
   return WGG_OK;
 }
