@@ -214,3 +214,22 @@ def test_device_resident_loader_matches_dataloader_contract():
     import pytest
     with pytest.raises(ValueError):
         wgg.DeviceResidentLoader(g, p[:, :8], 4)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm of the measurement contract) prints ONE JSON line with the keys the
+    driver reads; it runs entirely on the host (tiny bounded sample here)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-batch", "8"], capture_output=True, text=True, timeout=600, check=True)
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "gestures/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]

@@ -85,3 +85,37 @@ def test_torch_port_matches_reference_golden(case):
     for m in MODS:
         for name, val in st[m].items():
             g.check("post", m, name, val, 1e-7, "torch_port")
+
+
+def test_step_restructurings_are_exact():
+    """The product path restructures the step without changing its numbers (train_step.py / gan_trainer.py):
+    (a) ONE generator call on the stacked critic-phase batch instead of 2*n_critic calls,
+    (b) ONE encoder pass on the real batch + n re-parameterisations (mu / log_var do not depend on eps),
+    (c) cycle-1 and cycle-2 generator passes as one stacked call.
+    Checked here on the CPU restatement of the reference's modules (fp64): no layer mixes samples, so the stacked
+    calls reproduce the separate calls row for row."""
+    import torch
+    from oracle import torch_port
+    g = Golden("tiny_temporal")
+    ocfg = oracle_cfg(g)
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=ocfg, tc=O.TrainCfg(), dtype=torch.float64)
+    tp.load_state({m: g.init_state(m) for m in MODS})
+    gen = torch.Generator().manual_seed(3)
+    B, n = 6, 3
+    real = torch.rand(B, ocfg.seq_length, ocfg.input_dim, generator=gen, dtype=torch.float64) * 2 - 1
+    proto = torch.rand(B, ocfg.seq_length, ocfg.input_dim, generator=gen, dtype=torch.float64) * 2 - 1
+    zs = [torch.randn(B, ocfg.latent_dim, generator=gen, dtype=torch.float64) for _ in range(n)]
+    epss = [torch.randn(B, ocfg.latent_dim, generator=gen, dtype=torch.float64) for _ in range(n)]
+    with torch.no_grad():
+        # (b) encoder: z_i = mu + eps_i * exp(0.5 log_var) with the mu / log_var of a single pass
+        z0, mu, lv = tp.E(real, epss[0])
+        for e in epss:
+            zi, mui, lvi = tp.E(real, e)
+            assert torch.equal(mui, mu) and torch.equal(lvi, lv)
+            assert torch.allclose(zi, torch.addcmul(mu, e, torch.exp(0.5 * lv)), rtol=0, atol=1e-15)
+        # (a) + (c) generator on stacked batches
+        z_enc = [tp.E(real, e)[0] for e in epss]
+        stacked = tp.G(proto.repeat(2 * n, 1, 1), torch.cat(zs + z_enc, 0))
+        for i, z in enumerate(zs + z_enc):
+            single = tp.G(proto, z)
+            assert torch.allclose(stacked[i * B:(i + 1) * B], single, rtol=0, atol=1e-13), i
