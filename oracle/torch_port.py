@@ -117,7 +117,14 @@ class TorchPortTrainer:
     def state(self):
         return {k: {n: v.detach().double().numpy() for n, v in m.state_dict().items()} for k, m in self.mods.items()}
 
-    def train_batch(self, real, proto, noise=None, max_norm: float = 1.0):
+    def _record(self, rec, tag, mod):
+        """Un-clipped gradients of one optimiser step (same tags as wgg_oracle.train_batch / the product's on_step)."""
+        if rec is not None:
+            rec[tag] = {n: p.grad.detach().double().numpy().copy() for n, p in mod.named_parameters()}
+
+    def train_batch(self, real, proto, noise=None, max_norm: float = 1.0, record=None, fakes=None):
+        """One batch of utils.py:62-135.  ``record`` (dict) receives the un-clipped gradients of the 12 optimiser steps
+        (D1_grads_i, D2_grads_i, G_grads, E_grads); ``fakes`` (dict) the two generator-side fake gestures."""
         c, tc = self.cfg, self.tc
         B = real.shape[0]
         real, proto = real.to(self.dtype), proto.to(self.dtype)
@@ -125,7 +132,7 @@ class TorchPortTrainer:
         draw = (lambda: torch.as_tensor(next(it), dtype=self.dtype)) if it is not None else (
             lambda: torch.randn(B, c.latent_dim, dtype=self.dtype))
         out = {}
-        for _ in range(tc.n_critic):
+        for it_c in range(tc.n_critic):
             for key, D in (("D1", self.D1), ("D2", self.D2)):
                 with torch.no_grad():
                     z = draw() if key == "D1" else self.E(real, draw())[0]
@@ -135,6 +142,7 @@ class TorchPortTrainer:
                 fs = D(fake)
                 loss = fs.mean() - rs.mean()
                 loss.backward()
+                self._record(record, f"{key}_grads_{it_c}", D)
                 nn.utils.clip_grad_norm_(D.parameters(), max_norm)
                 self.opt[key].step()
                 out[key.lower() + "_loss"] = loss.item()
@@ -142,6 +150,8 @@ class TorchPortTrainer:
         self.opt["E"].zero_grad()
         z = draw()
         fake = self.G(proto, z)
+        if fakes is not None:
+            fakes["fake1"] = fake.detach().double().numpy()
         wg, ff, rf = -self.D1(fake).mean(), self.D1.feats(fake), self.D1.feats(real)
         with torch.no_grad():
             zr = self.E(fake, draw())[0]
@@ -150,6 +160,8 @@ class TorchPortTrainer:
         out.update(cycle1_wgan=wg.item(), cycle1_feat=feat.item(), cycle1_lat=lat.item(), cycle1_total=l1.item())
         ze, mu, lv = self.E(real, draw())
         fake = self.G(proto, ze)
+        if fakes is not None:
+            fakes["fake2"] = fake.detach().double().numpy()
         wg, ff, rf = -self.D2(fake).mean(), self.D2.feats(fake), self.D2.feats(real)
         feat, rec = _fm(rf, ff), F.l1_loss(fake, real)
         kld = (-0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=1)).mean()
@@ -157,11 +169,40 @@ class TorchPortTrainer:
         out.update(cycle2_wgan=wg.item(), cycle2_feat=feat.item(), cycle2_rec=rec.item(), cycle2_kld=kld.item(),
                    cycle2_total=l2.item())
         (l1 + l2).backward()
+        self._record(record, "G_grads", self.G)
+        self._record(record, "E_grads", self.E)
         nn.utils.clip_grad_norm_(self.G.parameters(), max_norm)
         nn.utils.clip_grad_norm_(self.E.parameters(), max_norm)
         self.opt["G"].step()
         self.opt["E"].step()
         return out
+
+    def cycle1(self, proto, real, z, eps_recover):
+        """trainer.py:84-140 (train_generator_step_cycle1) with the two normal draws injected."""
+        tc = self.tc
+        proto, real = proto.to(self.dtype), real.to(self.dtype)
+        z, eps_recover = torch.as_tensor(z, dtype=self.dtype), torch.as_tensor(eps_recover, dtype=self.dtype)
+        fake = self.G(proto, z)
+        wg, ff, rf = -self.D1(fake).mean(), self.D1.feats(fake), self.D1.feats(real)
+        with torch.no_grad():
+            zr = self.E(fake, eps_recover)[0]
+        feat, lat = _fm(rf, ff), F.l1_loss(zr, z)
+        total = wg + tc.lambda_feat * feat + tc.lambda_lat * lat
+        return fake, total, dict(cycle1_wgan=wg.item(), cycle1_feat=feat.item(), cycle1_lat=lat.item(),
+                                 cycle1_total=total.item())
+
+    def cycle2(self, proto, real, eps):
+        """trainer.py:142-193 (train_generator_step_cycle2) with the reparameterisation noise injected."""
+        tc = self.tc
+        proto, real = proto.to(self.dtype), real.to(self.dtype)
+        ze, mu, lv = self.E(real, torch.as_tensor(eps, dtype=self.dtype))
+        fake = self.G(proto, ze)
+        wg, ff, rf = -self.D2(fake).mean(), self.D2.feats(fake), self.D2.feats(real)
+        feat, rec = _fm(rf, ff), F.l1_loss(fake, real)
+        kld = (-0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=1)).mean()
+        total = wg + tc.lambda_feat * feat + tc.lambda_rec * rec + tc.lambda_kld * kld
+        return fake, total, dict(cycle2_wgan=wg.item(), cycle2_feat=feat.item(), cycle2_rec=rec.item(),
+                                 cycle2_kld=kld.item(), cycle2_total=total.item())
 
     def sample(self, proto, z):
         with torch.no_grad():

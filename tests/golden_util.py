@@ -90,3 +90,33 @@ def summarise(a):
 def oracle_cfg(g):
     from oracle import wgg_oracle as O
     return O.ModelCfg(**g.cfg_kwargs())
+
+
+class CycleGolden:
+    """tests/golden/cycles_<case>.npz: direct calls of the reference's train_generator_step_cycle1/2
+    (oracle/make_golden_cycles.py)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, f"cycles_{name}.npz"), allow_pickle=False)
+
+    cfg_kwargs = Golden.cfg_kwargs
+
+    def init_state(self, mod, dtype=np.float64):
+        return {str(k): self.z[f"init/{mod}/{k}"].astype(dtype) for k in self.z[f"order/{mod}"]}
+
+    def inputs(self):
+        n = self.z["noise"]
+        return self.z["real"], self.z["proto"], n[0], n[1], n[2]
+
+    def losses(self, cyc):
+        pre = f"c{cyc}/dict/"
+        return {k[len(pre):]: float(self.z[k]) for k in self.z.files if k.startswith(pre)}
+
+    def grads(self, cyc, mod):
+        pre = f"c{cyc}/grad/{mod}/"
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
+
+    def uv(self, cyc):
+        pre = f"c{cyc}/uv/"
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}

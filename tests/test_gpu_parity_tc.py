@@ -1,0 +1,445 @@
+"""-m gpu: parity of the BENCHMARKED path - math modes "tf32" and "tf32x3" (tcgen05 LSTM / conv kernels) - against
+the fp64 CPU checkers at the sizes where the tensor-core kernels' tiling actually wraps:
+
+  * generator forward + BPTT + dx + dW at B in {128, 129, 512, 600}: 1, 2, 4 and 5 tiles of 128 gestures, a ragged
+    last tile, multi-(t, tile) loops of the persistent dx / dW kernels;
+  * the whole training batch (5 x (D1, D2) + G/E; the stacked 10*B no-grad generator call and the 2*B grad-carrying
+    one) at the same sizes: 11 losses and the un-clipped gradients of all 12 optimiser steps;
+  * the discriminator's persistent conv kernels at B >= 3 * 148 + 1 so every CTA wraps its 3-stage input ring;
+  * both generator-side cycles at BASELINE configs[1]'s batch of 4096 (forward + 9 losses) and with their generator /
+    encoder gradients at 1024;
+  * the re-synchronised step protocol for 100 steps (tiny model) / 20 steps (default model) in
+    all three math modes;
+  * the public train_generator_step_cycle1/2 methods against fixtures made by calling the reference's own;
+  * a captured graph keeps working after eager calls regrow the process-wide scratch (graph-owned scratch).
+
+Checkers: oracle/wgg_oracle.py (numpy fp64) and oracle/torch_port.py in float64, both pinned to fixtures produced by
+the unmodified reference (tests/test_oracle_golden.py).
+
+Tolerances, per-tensor rel-L2 against fp64 (written here, asserted below):
+  generator (TF32 LSTM in both modes)  : forward 2e-3 max-abs/max-abs, gradients 1e-3 (north star)
+  discriminator, mode tf32             : weights 2e-2, input gradient 4e-2 - the bounds the reference's own
+                                         cuDNN-TF32 path measures on the same GPU (profiles/r01_ref_cuda_precision.json)
+  discriminator, mode tf32x3           : 1e-3 everywhere (north star)
+  G/E gradients of the full step       : they contain d/dx of the conv stack: 4e-2 in tf32, 2e-3 in tf32x3
+Measured values are written to gpurun_out/tc_parity_report.json.
+"""
+import functools
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import wgg_b200 as wgg
+from golden_util import LOSS_KEYS, MODS, CycleGolden, Golden, max_abs_rel, oracle_cfg, rel_l2
+from gpu_util import ATTR, DEV, grads_of, load_state, model_cfg, rand_inputs, state_of, to_np, to_t
+from oracle import torch_port
+from oracle import wgg_oracle as O
+from wgg_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT = O.ModelCfg()
+FWD_TOL = 2e-3
+GEN_GRAD_TOL = 1e-3
+DISC_W_TOL = {"fp32": 1e-3, "tf32": 2e-2, "tf32x3": 1e-3}
+DISC_DX_TOL = {"fp32": 1e-3, "tf32": 4e-2, "tf32x3": 1e-3}
+GE_STEP_TOL = {"fp32": 1e-3, "tf32": 4e-2, "tf32x3": 2e-3}
+LOSS_TOL = {"fp32": 1e-4, "tf32": 5e-3, "tf32x3": 2e-3}
+
+_REPORT = {}
+
+
+def report(key, value):
+    _REPORT[key] = value
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/tc_parity_report.json", "w") as f:
+        json.dump(_REPORT, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(params=["tf32", "tf32x3"])
+def tc_mode(request):
+    wgg.set_math_mode(request.param)
+    yield request.param
+    torch.cuda.synchronize()
+    code = _lib.async_error(DEV)
+    wgg.set_math_mode("fp32")
+    assert code == 0, f"a tcgen05 pipeline timed out (code {code})"
+
+
+@pytest.fixture(params=["fp32", "tf32", "tf32x3"])
+def any_mode(request):
+    wgg.set_math_mode(request.param)
+    yield request.param
+    torch.cuda.synchronize()
+    code = _lib.async_error(DEV)
+    wgg.set_math_mode("fp32")
+    assert code == 0, f"a tcgen05 pipeline timed out (code {code})"
+
+
+def f32(a):
+    return np.asarray(a).astype(np.float32).astype(np.float64)
+
+
+def seed42_states():
+    """fp32-representable seed-42 initial state of the default model (the reference's, bit for bit)."""
+    g = Golden("default")
+    return {m: g.init_state(m) for m in MODS}
+
+
+def trainer_with(states, ocfg=DEFAULT, **tc_kwargs):
+    tr = wgg.WordGestureGANTrainer(model_cfg(ocfg), wgg.TrainingConfig(**tc_kwargs), DEV)
+    for m in MODS:
+        load_state(getattr(tr, ATTR[m]), states[m])
+        getattr(tr, ATTR[m]).train()
+    return tr
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (i) generator forward + backward over several 128-gesture tiles
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def gen_reference(B):
+    p = seed42_states()["G"]
+    _, proto, z = rand_inputs(DEFAULT, B, 40 + B)
+    dy = f32(np.random.default_rng(B).standard_normal((B, 128, 3)))
+    y, stash = O.generator_fwd(p, DEFAULT, proto, z)
+    g, dz = O.generator_bwd(p, DEFAULT, stash, dy)
+    return p, proto, z, dy, y, g, dz
+
+
+@pytest.mark.parametrize("B", [128, 129, 512, 600])
+def test_tc_generator_multi_tile(tc_mode, B):
+    p, proto, z, dy, y_ref, g_ref, dz_ref = gen_reference(B)
+    G = wgg.Generator(model_cfg(DEFAULT)).to(DEV)
+    load_state(G, p)
+    zt = to_t(z).requires_grad_(True)
+    y = G(to_t(proto), zt)
+    e_fwd = max_abs_rel(to_np(y), y_ref)
+    y.backward(to_t(dy))
+    per = {k: rel_l2(v, g_ref[k]) for k, v in grads_of(G).items()}
+    e_dz = rel_l2(to_np(zt.grad), dz_ref)
+    with torch.no_grad():
+        y_ng = G(to_t(proto), to_t(z))   # the no-grad (critic phase / sampling) kernel variant
+    e_ng = max_abs_rel(to_np(y_ng), y_ref)
+    worst = max(per, key=per.get)
+    report(f"generator/{tc_mode}/B{B}", dict(fwd=e_fwd, fwd_nograd=e_ng, grad_worst=per[worst], grad_worst_tensor=worst,
+                                             dz=e_dz))
+    assert e_fwd <= FWD_TOL and e_ng <= FWD_TOL, (e_fwd, e_ng)
+    assert per[worst] <= GEN_GRAD_TOL, (worst, per[worst])
+    assert e_dz <= GEN_GRAD_TOL, e_dz
+    # rows of a ragged last tile must not leak into each other: row 0 of the batch alone gives the same output
+    with torch.no_grad():
+        y1 = G(to_t(proto[:1]), to_t(z[:1]))
+    assert torch.equal(y1[0], y_ng[0])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (ii) the whole training batch at multi-tile sizes.  Learning rate 0 on both sides: the Adam updates inside the
+# batch vanish, so every one of the 12 gradient sets is a clean function of the initial weights, the spectral-norm
+# schedule (u / v still advance at every discriminator call) and the data - nothing amplifies rounding noise between
+# critic iterations and all 12 can be held to the per-mode bound.
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def batch_reference(B, lr):
+    states = seed42_states()
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=DEFAULT, tc=O.TrainCfg(learning_rate=lr), dtype=torch.float64)
+    tp.load_state(states)
+    rng = np.random.default_rng(1000 + B)
+    real = f32(rng.uniform(-1, 1, (B, 128, 3)))
+    proto = f32(rng.uniform(-1, 1, (B, 128, 3)))
+    noise = [f32(rng.standard_normal((B, 32))) for _ in range(13)]
+    rec, fakes = {}, {}
+    losses = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise, record=rec, fakes=fakes)
+    return states, real, proto, noise, losses, rec, fakes
+
+
+def run_batch(tr, real, proto, noise):
+    rec = {}
+
+    def on_step(tag, opt):
+        flat = opt.flat_grad().detach().double().cpu().numpy()
+        off, d = 0, {}
+        for k, prm in opt.module.named_parameters():
+            d[k] = flat[off:off + prm.numel()].reshape(tuple(prm.shape))
+            off += prm.numel()
+        rec[tag] = d
+
+    out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise], on_step=on_step)
+    return {k: v.item() for k, v in out.items()}, rec
+
+
+@pytest.mark.parametrize("B", [128, 129, 512, 600])
+def test_tc_train_batch_multi_tile(tc_mode, B):
+    states, real, proto, noise, ref_losses, ref_rec, _ = batch_reference(B, 0.0)
+    tr = trainer_with(states, learning_rate=0.0)
+    losses, rec = run_batch(tr, real, proto, noise)
+    worst_loss = max(abs(losses[k] - ref_losses[k]) / max(abs(ref_losses[k]), 1e-2) for k in LOSS_KEYS)
+    assert set(rec) == set(ref_rec) and len(rec) == 12
+    worst = {}
+    for tag, d in rec.items():
+        per = {k: rel_l2(v, ref_rec[tag][k]) for k, v in d.items()}
+        k = max(per, key=per.get)
+        worst[tag] = (per[k], k)
+    report(f"train_batch_lr0/{tc_mode}/B{B}", dict(loss_worst=worst_loss, grads={t: [float(e), k] for t, (e, k) in worst.items()}))
+    assert worst_loss <= LOSS_TOL[tc_mode], (worst_loss, losses, ref_losses)
+    for tag, (e, k) in worst.items():
+        tol = DISC_W_TOL[tc_mode] if tag.startswith("D") else GE_STEP_TOL[tc_mode]
+        assert e <= tol, (tag, k, e, tol)
+
+
+@pytest.mark.parametrize("B", [129, 512])
+def test_tc_train_batch_with_updates(tc_mode, B):
+    """The same batch with the real learning rate: 11 losses, the first critic iteration's gradients (computed from
+    the shared initial state) at the per-mode bound; later ones see weights already moved by sign-like first Adam
+    steps, bounded loosely; post-step parameters."""
+    states, real, proto, noise, ref_losses, ref_rec, _ = batch_reference(B, 2e-4)
+    tr = trainer_with(states)
+    losses, rec = run_batch(tr, real, proto, noise)
+    worst_loss = max(abs(losses[k] - ref_losses[k]) / max(abs(ref_losses[k]), 1e-2) for k in LOSS_KEYS)
+    first = max(rel_l2(v, ref_rec[t][k]) for t in ("D1_grads_0", "D2_grads_0") for k, v in rec[t].items())
+    later = max(rel_l2(v, ref_rec[t][k]) for t in rec if t not in ("D1_grads_0", "D2_grads_0") for k, v in rec[t].items())
+    report(f"train_batch/{tc_mode}/B{B}", dict(loss_worst=worst_loss, first_critic_grads=first, later_grads=later))
+    assert worst_loss <= 2e-2, (worst_loss, losses, ref_losses)
+    assert first <= DISC_W_TOL[tc_mode], first
+    assert later <= 1e-1, later
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (iii) discriminator at B >= 3 * 148 + 1: every persistent conv CTA processes >= 4 gestures, so the 3-stage input
+# ring wraps (and its mbarrier phases flip) on every SM
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def disc_reference(B):
+    p = seed42_states()["D1"]
+    real, fake, _ = rand_inputs(DEFAULT, B, 70 + B)
+    rs, _, st_r = O.disc_fwd(p, DEFAULT, real, True)
+    fs, _, st_f = O.disc_fwd(p, DEFAULT, fake, True)
+    g_r, _ = O.disc_bwd(p, DEFAULT, st_r, np.full((B, 1), -1.0 / B), None)
+    g_f, dx = O.disc_bwd(p, DEFAULT, st_f, np.full((B, 1), 1.0 / B), None)
+    grads = {k: g_r[k] + g_f[k] for k in g_r}
+    ff, st_ff = O.disc_fwd(p, DEFAULT, fake, True, features_only=True)
+    rf, _ = O.disc_fwd(p, DEFAULT, real, True, features_only=True)
+    fm, dff = O.feature_matching(rf, ff)
+    _, dx_fm = O.disc_bwd(p, DEFAULT, st_ff, None, dff)
+    uv = {k: v.copy() for k, v in p.items() if k.endswith("weight_u") or k.endswith("weight_v")}
+    return seed42_states()["D1"], real, fake, rs, fs, grads, dx, ff, fm, dx_fm, uv
+
+
+@pytest.mark.parametrize("B", [445, 3 * 148 + 149])
+def test_tc_discriminator_ring_wrap(tc_mode, B):
+    p0, real, fake, rs_ref, fs_ref, g_ref, dx_ref, ff_ref, fm_ref, dx_fm_ref, uv_ref = disc_reference(B)
+    D = wgg.TemporalDiscriminator(model_cfg(DEFAULT)).to(DEV).train()
+    load_state(D, p0)
+    ft = to_t(fake).requires_grad_(True)
+    rs, fs = D(to_t(real)), D(ft)
+    e_fwd = max(max_abs_rel(to_np(rs), rs_ref), max_abs_rel(to_np(fs), fs_ref))
+    wgg.WassersteinLoss.discriminator_loss(rs, fs).backward()
+    per = {k: rel_l2(v, g_ref[k]) for k, v in grads_of(D).items()}
+    e_dx = rel_l2(to_np(ft.grad), dx_ref)
+    ft2 = to_t(fake).requires_grad_(True)
+    fstash = D.features_stash(ft2)
+    rstash = D.features_stash(to_t(real))
+    fm = wgg.feature_matching_from_stash(rstash, fstash, D.config, B)
+    e_fm = abs(fm.item() - fm_ref) / abs(fm_ref)
+    fm.backward()
+    e_dx_fm = rel_l2(to_np(ft2.grad), dx_fm_ref)
+    sd = state_of(D)
+    e_uv = max(max_abs_rel(sd[k], v) for k, v in uv_ref.items())
+    D.eval()
+    with torch.no_grad():
+        feats = D.get_all_features(to_t(fake))   # eval: no power iteration -> same weights as the last call above
+    worst = max(per, key=per.get)
+    report(f"discriminator/{tc_mode}/B{B}", dict(fwd=e_fwd, grad_worst=per[worst], grad_worst_tensor=worst, dx=e_dx,
+                                                 fm_loss=e_fm, fm_dx=e_dx_fm, uv=e_uv, per_tensor=per))
+    assert len(feats) == 5 and tuple(feats[0].shape) == (B, 8192)
+    assert e_fwd <= FWD_TOL, e_fwd
+    assert per[worst] <= DISC_W_TOL[tc_mode], (worst, per[worst])
+    assert e_dx <= DISC_DX_TOL[tc_mode] and e_dx_fm <= DISC_DX_TOL[tc_mode], (e_dx, e_dx_fm)
+    assert e_fm <= 1e-2 and e_uv <= 1e-5, (e_fm, e_uv)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (iv) both generator-side cycles at BASELINE configs[1]'s batch (4096 gestures): forward and all 9 losses; and with
+# the generator / encoder gradients of cycle-1 + cycle-2 at 1024 gestures (the fp64 CPU backward at 4096 needs ~36 GB)
+# ------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def cycles_reference(B, with_grad):
+    states = seed42_states()
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=DEFAULT, dtype=torch.float64)
+    tp.load_state(states)
+    rng = np.random.default_rng(B)
+    real = f32(rng.uniform(-1, 1, (B, 128, 3)))
+    proto = f32(rng.uniform(-1, 1, (B, 128, 3)))
+    z, eps_rec, eps = (f32(rng.standard_normal((B, 32))) for _ in range(3))
+    rt, pt = torch.from_numpy(real), torch.from_numpy(proto)
+    with torch.set_grad_enabled(with_grad):
+        fake1, total1, d1 = tp.cycle1(pt, rt, z, eps_rec)
+        fake2, total2, d2 = tp.cycle2(pt, rt, eps)
+    grads = None
+    if with_grad:
+        (total1 + total2).backward()
+        grads = {m: {k: p.grad.detach().numpy().copy() for k, p in net.named_parameters()} for m, net in (("G", tp.G), ("E", tp.E))}
+    return states, real, proto, z, eps_rec, eps, fake1.detach().numpy(), fake2.detach().numpy(), {**d1, **d2}, grads
+
+
+@pytest.mark.parametrize("B,with_grad", [(4096, False), (1024, True)])
+def test_tc_cycles_at_scale(tc_mode, B, with_grad):
+    states, real, proto, z, eps_rec, eps, fake1_ref, fake2_ref, d_ref, g_ref = cycles_reference(B, with_grad)
+    tr = trainer_with(states)
+    with torch.set_grad_enabled(with_grad):
+        fake1, fake2, t1, t2, d1, d2 = tr.cycles_tensors(to_t(proto), to_t(real), z=to_t(z), eps_recover=to_t(eps_rec),
+                                                         eps=to_t(eps))
+    e_f1, e_f2 = max_abs_rel(to_np(fake1), fake1_ref), max_abs_rel(to_np(fake2), fake2_ref)
+    mine = {k: v.item() for k, v in {**d1, **d2}.items()}
+    e_loss = {k: abs(mine[k] - v) / max(abs(v), 1e-2) for k, v in d_ref.items()}
+    rep = dict(fake1=e_f1, fake2=e_f2, losses=e_loss)
+    if with_grad:
+        (t1 + t2).backward()
+        per = {m: {k: rel_l2(v, g_ref[m][k]) for k, v in grads_of(getattr(tr, ATTR[m])).items()} for m in ("G", "E")}
+        rep.update(G_grad_worst=max(per["G"].values()), E_grad_worst=max(per["E"].values()))
+    report(f"cycles/{tc_mode}/B{B}", rep)
+    assert e_f1 <= FWD_TOL and e_f2 <= FWD_TOL, (e_f1, e_f2)
+    assert max(e_loss.values()) <= LOSS_TOL[tc_mode], e_loss
+    if with_grad:
+        assert rep["G_grad_worst"] <= GE_STEP_TOL[tc_mode] and rep["E_grad_worst"] <= GE_STEP_TOL[tc_mode], rep
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (v) re-synchronised step protocol, 100 / 20 steps, all three math modes
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,steps,B", [("tiny_temporal", 100, 8), ("default", 20, 16)])
+def test_resynchronised_steps_all_modes(any_mode, case, steps, B):
+    """SURVEY.md 8(c) protocol (2) (ref utils.py:62-135): the fp64 CPU restatement trains freely; before EVERY step
+    its complete pre-step state (parameters, u / v, Adam moments and step counts) is loaded into the CUDA trainer, both
+    take the step on the same batch and the same 13 noise tensors; compared per step: 11 losses, the first critic
+    iteration's gradients and the G / E gradients, the post-step parameters."""
+    mode = any_mode
+    g = Golden(case)
+    ocfg = oracle_cfg(g)
+    tr = trainer_with({m: g.init_state(m) for m in MODS}, ocfg)
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=ocfg, tc=O.TrainCfg(), dtype=torch.float64)
+    tp.load_state({m: g.init_state(m) for m in MODS})
+    opts = dict(G=tr.optimizer_G, E=tr.optimizer_E, D1=tr.optimizer_D1, D2=tr.optimizer_D2)
+    rng = np.random.default_rng(11)
+    worst = dict(loss=0.0, d_first=0.0, ge=0.0, post=0.0)
+    loss_tol = {"fp32": 5e-3, "tf32": 2e-2, "tf32x3": 5e-3}[mode]
+    for step in range(steps):
+        pre = tp.state()
+        for m in MODS:
+            load_state(getattr(tr, ATTR[m]), pre[m])
+            sd = tp.opt[m].state_dict()
+            if sd["state"]:
+                opts[m].load_state_dict(sd)
+        real = f32(rng.uniform(-1, 1, (B, ocfg.seq_length, ocfg.input_dim)))
+        proto = f32(rng.uniform(-1, 1, (B, ocfg.seq_length, ocfg.input_dim)))
+        noise = [f32(rng.standard_normal((B, ocfg.latent_dim))) for _ in range(13)]
+        ref_rec = {}
+        ref = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise, record=ref_rec)
+        losses, rec = run_batch(tr, real, proto, noise)
+        for k in LOSS_KEYS:
+            # adversarial terms are differences of nearly cancelling score means: judged on the scale of the scores
+            worst["loss"] = max(worst["loss"], abs(losses[k] - ref[k]) / max(abs(ref[k]), 1e-2))
+        for tag in ("D1_grads_0", "D2_grads_0"):
+            worst["d_first"] = max(worst["d_first"], max(rel_l2(v, ref_rec[tag][k]) for k, v in rec[tag].items()))
+        for tag in ("G_grads", "E_grads"):
+            worst["ge"] = max(worst["ge"], max(rel_l2(v, ref_rec[tag][k]) for k, v in rec[tag].items()))
+        post = tp.state()
+        for m in MODS:
+            for k, prm in getattr(tr, ATTR[m]).named_parameters():
+                worst["post"] = max(worst["post"], rel_l2(to_np(prm), post[m][k]))
+        assert worst["loss"] <= loss_tol, (mode, case, step, worst)
+        assert worst["d_first"] <= DISC_W_TOL[mode], (mode, case, step, worst)
+        assert worst["post"] <= 5e-3, (mode, case, step, worst)
+    report(f"resync/{mode}/{case}", dict(steps=steps, **worst))
+    # the G/E gradients follow five in-batch critic updates (each a sign-like Adam step): bounded loosely
+    assert worst["ge"] <= 1e-1, worst
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (vi) public train_generator_step_cycle1 / cycle2 against the reference's own methods
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["tiny_temporal", "tiny_mlp_time", "default"])
+def test_public_cycle_methods_match_reference(any_mode, case, monkeypatch):
+    """WordGestureGANTrainer.train_generator_step_cycle1/2 called exactly as the reference's are (trainer.py:84-193):
+    no injected noise - torch.randn is patched in the test process, like the fixture generator did for the reference,
+    so the draws (z; the recovery eps; cycle-2 eps) are consumed in call order.  Compared: returned fake gesture,
+    Python-float loss dict, total, G / E gradients of each cycle backward on its own, the critic's u / v buffers."""
+    mode = any_mode
+    g = CycleGolden(case)
+    ocfg = O.ModelCfg(**g.cfg_kwargs())
+    tr = trainer_with({m: g.init_state(m) for m in MODS}, ocfg)
+    real, proto, z, eps_rec, eps = g.inputs()
+    queue = [to_t(z), to_t(eps_rec), to_t(eps)]
+    orig = torch.randn
+
+    def fake_randn(*a, **k):
+        assert tuple(a[:2]) == tuple(queue[0].shape) or tuple(a[0]) == tuple(queue[0].shape)
+        return queue.pop(0)
+
+    monkeypatch.setattr(torch, "randn", fake_randn)
+    rep = {}
+    for cyc, fn, disc in ((1, tr.train_generator_step_cycle1, tr.discriminator_1),
+                          (2, tr.train_generator_step_cycle2, tr.discriminator_2)):
+        tr.optimizer_G.zero_grad()
+        tr.optimizer_E.zero_grad()
+        fake, total, d = fn(to_t(proto), to_t(real))
+        assert all(isinstance(v, float) for v in d.values()) and set(d) == set(g.losses(cyc))
+        total.backward()
+        e_fake = max_abs_rel(to_np(fake), g.z[f"c{cyc}/fake"])
+        e_loss = max(abs(d[k] - v) / max(abs(v), 1e-2) for k, v in g.losses(cyc).items())
+        e_grad = 0.0
+        for mod in ("G", "E"):
+            ref_g = g.grads(cyc, mod)
+            for k, p in getattr(tr, ATTR[mod]).named_parameters():
+                if np.abs(ref_g[k]).max() == 0:   # cycle 1 carries no encoder gradient (trainer.py:116-119)
+                    assert p.grad is None or float(p.grad.abs().max()) == 0.0, (cyc, mod, k)
+                else:
+                    e_grad = max(e_grad, rel_l2(to_np(p.grad), ref_g[k]))
+        sd = state_of(disc)
+        e_uv = max(max_abs_rel(sd[k], v) for k, v in g.uv(cyc).items())
+        rep[f"cycle{cyc}"] = dict(fake=e_fake, loss=e_loss, grad=e_grad, uv=e_uv)
+        assert e_fake <= (1e-4 if mode == "fp32" else FWD_TOL), (cyc, e_fake)
+        assert e_loss <= LOSS_TOL[mode], (cyc, e_loss)
+        assert e_grad <= GE_STEP_TOL[mode], (cyc, e_grad)
+        assert e_uv <= 1e-5, (cyc, e_uv)
+    monkeypatch.setattr(torch, "randn", orig)
+    assert not queue
+    report(f"public_cycles/{mode}/{case}", rep)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (vii) a captured graph owns its scratch: eager calls that regrow the process-wide scratch must not disturb it
+# ------------------------------------------------------------------------------------------------------------
+def test_graph_survives_scratch_regrowth(tc_mode):
+    g = Golden("default")
+    states = {m: g.init_state(m) for m in MODS}
+    B = 64
+    gen = torch.Generator().manual_seed(3)
+    real = (torch.rand(B, 128, 3, generator=gen) * 2 - 1).to(DEV)
+    proto = (torch.rand(B, 128, 3, generator=gen) * 2 - 1).to(DEV)
+    tr_e, tr_g = trainer_with(states), trainer_with(states)
+    gs = wgg.GraphedTrainStep(tr_g, B, 1.0)
+    big = 4096
+    for it in range(3):
+        torch.manual_seed(7 + it)
+        torch.cuda.manual_seed(7 + it)
+        out_e = {k: v.clone() for k, v in wgg.train_batch(tr_e, real, proto, 1.0).items()}
+        # between replays: eager work that needs far more scratch than the B=64 step (regrows the global buffers)
+        with torch.no_grad():
+            tr_g.generator(torch.rand(big, 128, 3, device=DEV), torch.randn(big, 32, device=DEV))
+        x = torch.rand(big, 128, 3, device=DEV, requires_grad=True)
+        tr_e.discriminator_2.eval()
+        tr_e.discriminator_2(x).sum().backward()   # eval: leaves u / v alone; grads are zeroed by the next step
+        tr_e.discriminator_2.train()
+        big *= 2
+        torch.manual_seed(7 + it)
+        torch.cuda.manual_seed(7 + it)
+        out_g = gs(real, proto)
+        torch.cuda.synchronize()
+        for k in LOSS_KEYS:
+            assert out_e[k].item() == out_g[k].item(), (it, k)
+        for m in MODS:
+            assert torch.equal(getattr(tr_e, ATTR[m]).flat_params(), getattr(tr_g, ATTR[m]).flat_params()), (it, m)

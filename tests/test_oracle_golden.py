@@ -68,9 +68,11 @@ def test_spectral_norm_gradient_formula():
     assert np.abs(an - num).max() < 1e-6
 
 
-@pytest.mark.parametrize("case", ["tiny_temporal", "tiny_mlp_time"])
+@pytest.mark.parametrize("case", ["tiny_temporal", "tiny_mlp_time", "default"])
 def test_torch_port_matches_reference_golden(case):
-    """oracle/torch_port.py (the CPU arm bench.py times) reproduces the reference's losses and post-step state."""
+    """oracle/torch_port.py (the CPU arm bench.py times, and the fp64 checker of the large-batch GPU parity tests)
+    reproduces the reference's losses, the un-clipped gradients of all 12 optimiser steps, both generator-side fake
+    gestures and the post-step state - on the default model too."""
     import torch
     from oracle import torch_port
     g = Golden(case)
@@ -78,13 +80,59 @@ def test_torch_port_matches_reference_golden(case):
     tp = torch_port.TorchPortTrainer(seed=0, cfg=cfg, dtype=torch.float64)
     tp.load_state({m: g.init_state(m) for m in MODS})
     real, proto, noise = g.inputs()
-    out = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise)
+    rec, fakes = {}, {}
+    out = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise, record=rec, fakes=fakes)
     for k in LOSS_KEYS:
         assert abs(out[k] - g.loss(k)) <= 1e-9 * max(1.0, abs(g.loss(k))), k
+    assert len(rec) == 2 * O.TrainCfg().n_critic + 2
+    for tag, d in rec.items():
+        for name, val in d.items():
+            g.check("grad", tag, name, val, 1e-7, "torch_port")
+    assert np.abs(fakes["fake1"] - g.z["fake_cycle1"]).max() <= 1e-9
+    assert np.abs(fakes["fake2"] - g.z["fake_cycle2"]).max() <= 1e-9
     st = tp.state()
     for m in MODS:
         for name, val in st[m].items():
             g.check("post", m, name, val, 1e-7, "torch_port")
+
+
+@pytest.mark.parametrize("case", ["tiny_temporal", "tiny_mlp_time", "default"])
+def test_torch_port_cycles_match_reference_direct_calls(case):
+    """The CPU restatement of train_generator_step_cycle1/2 (trainer.py:84-193) against fixtures produced by calling
+    those methods of the unmodified reference directly (oracle/make_golden_cycles.py): returned fake gesture, loss
+    dict, total, generator / encoder gradients of each cycle on its own, and the discriminator's u/v buffers after
+    its three calls."""
+    import torch
+    from golden_util import CycleGolden, rel_l2
+    from oracle import torch_port
+    g = CycleGolden(case)
+    cfg = O.ModelCfg(**g.cfg_kwargs())
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=cfg, dtype=torch.float64)
+    tp.load_state({m: g.init_state(m) for m in MODS})
+    real, proto, z, eps_rec, eps = g.inputs()
+    real, proto = torch.from_numpy(real), torch.from_numpy(proto)
+    for cyc, call, disc in ((1, lambda: tp.cycle1(proto, real, z, eps_rec), tp.D1), (2, lambda: tp.cycle2(proto, real, eps), tp.D2)):
+        tp.opt["G"].zero_grad()
+        tp.opt["E"].zero_grad()
+        fake, total, d = call()
+        total.backward()
+        assert np.abs(fake.detach().numpy() - g.z[f"c{cyc}/fake"]).max() <= 1e-10
+        assert abs(total.item() - float(g.z[f"c{cyc}/total"])) <= 1e-10
+        ref_d = g.losses(cyc)
+        assert set(d) == set(ref_d)
+        for k, v in ref_d.items():
+            assert abs(d[k] - v) <= 1e-10 * max(1.0, abs(v)), k
+        for mod, net in (("G", tp.G), ("E", tp.E)):
+            ref_g = g.grads(cyc, mod)
+            for k, p in net.named_parameters():
+                mine = np.zeros(tuple(p.shape)) if p.grad is None else p.grad.numpy()
+                if np.abs(ref_g[k]).max() == 0:
+                    assert np.abs(mine).max() == 0, (cyc, mod, k)  # cycle 1 carries no encoder gradient (trainer.py:116-119)
+                else:
+                    assert rel_l2(mine, ref_g[k]) <= 1e-8, (cyc, mod, k)
+        sd = disc.state_dict()
+        for k, v in g.uv(cyc).items():
+            assert np.abs(sd[k].numpy() - v).max() <= 1e-10, k
 
 
 def test_step_restructurings_are_exact():

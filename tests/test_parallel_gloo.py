@@ -83,6 +83,22 @@ def _worker(rank, world, port, ret):
         parallel.allreduce_mean_(bucket, None, world)
         first = opt.param_groups[0]["params"][0]
         assert torch.allclose(first.grad, torch.full_like(first, 1.5))  # .grad aliases the reduced bucket
+
+        # 6. the PRODUCT path's noise under data parallelism (train_step.train_batch / trainer._randn): every rank
+        # seeds alike, draws the global tensor and keeps its rows - ranks get DIFFERENT rows, their concatenation is
+        # the single-process draw for the global batch, and the generators stay in lock step over successive draws
+        from wgg_b200 import train_step
+        assert train_step.dp_slice(tr) == (rank, world)
+        wgg.seed_everything(42)
+        draws = [tr._randn(4) for _ in range(3)]
+        wgg.seed_everything(42)
+        ref = [torch.randn(world * 4, tr.model_config.latent_dim) for _ in range(3)]
+        for d, r in zip(draws, ref):
+            assert torch.equal(d, r[rank * 4:(rank + 1) * 4])
+            both = [torch.zeros_like(d) for _ in range(world)]
+            dist.all_gather(both, d)
+            assert torch.equal(torch.cat(both, 0), r)
+            assert not torch.equal(both[0], both[1])
         ret[rank] = "ok"
     except Exception as ex:  # pragma: no cover
         import traceback

@@ -199,16 +199,50 @@ class lane:
         return False
 
 
+_scope = None  # the active ScratchScope (None: the process-wide grow-only buffers in _ws)
+
+
+class ScratchScope:
+    """A private set of per-(device, lane) scratch buffers.  A captured CUDA graph bakes the addresses of the scratch
+    its kernels use into the graph, so the graph must OWN that scratch: GraphedTrainStep sizes a scope during its
+    warm-up, captures under the same scope (frozen: growing during capture would leave earlier captured launches
+    pointing at a freed buffer) and keeps the scope alive for as long as the graph lives.  Eager calls made outside
+    the scope use (and may regrow) the process-wide buffers without touching the graph's."""
+
+    def __init__(self):
+        self.buffers = {}
+        self.frozen = False
+        self._prev = None
+
+    def __enter__(self):
+        global _scope
+        self._prev = _scope
+        _scope = self
+        return self
+
+    def __exit__(self, *exc):
+        global _scope
+        _scope = self._prev
+        return False
+
+
 def workspace(device, nfloats: int) -> torch.Tensor:
     """Grow-only scratch buffer per (device, lane).  All calls of one lane are issued on one stream at a time, so a
-    single buffer is shared by every entry point of that lane."""
+    single buffer is shared by every entry point of that lane.  Inside a ScratchScope the scope's own buffers are
+    used."""
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
     key = (idx, _lane)
-    w = _ws.get(key)
+    store = _ws if _scope is None else _scope.buffers
+    w = store.get(key)
     if w is None or w.numel() < nfloats:
-        _ws[key] = None
-        w = _ws[key] = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
+        if _scope is not None and _scope.frozen:
+            raise WggError(f"scratch request of {nfloats} floats exceeds the {0 if w is None else w.numel()} floats sized "
+                           "by the warm-up of a captured graph (the warm-up must run the same step as the capture)")
+        if torch.cuda.is_current_stream_capturing():
+            raise WggError("scratch buffers cannot grow during CUDA graph capture; warm the step up first")
+        store[key] = None
+        w = store[key] = torch.empty(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
     return w
 
 

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <unordered_set>
+
 #include "wgg.h"
 
 struct wgg_ctx {
@@ -28,8 +30,21 @@ struct wgg_ctx {
   double prof_flops = 0.0, prof_bytes = 0.0;
   const char** prof_tag = nullptr;   // per event pair: static call-site tag
   double* prof_fl = nullptr;         // per event pair: FLOPs
+  // kernels whose dynamic-shared-memory limit has been raised ON THIS DEVICE (function attributes are per device;
+  // one ctx per device, see wgg_smem_ok)
+  std::unordered_set<const void*> smem_cfg;
   char err[512] = {0};
 };
+
+// Raises a kernel's dynamic shared memory limit once per context (= per device).
+template <typename F>
+inline bool wgg_smem_ok(wgg_ctx* ctx, F* fn, size_t smem) {
+  const void* key = reinterpret_cast<const void*>(fn);
+  if (ctx->smem_cfg.count(key)) return true;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+  ctx->smem_cfg.insert(key);
+  return true;
+}
 
 // RAII bracket: records a CUDA event pair around one launch of a profiled kernel class.
 struct ProfScope {

@@ -723,24 +723,16 @@ int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64
   a.ncols = Ktot + 8;
   a.gerr = ctx->async_err;
   const size_t smem = (size_t)ctc::W1_NST * ctc::W1_STAGE + 1024 + 16 * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(ctc::conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad_kernel: cannot reserve shared memory%s");
-    configured = true;
-  }
+  if (!wgg_smem_ok(ctx, ctc::conv_tc_wgrad_kernel, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad_kernel: cannot reserve shared memory%s");
   const int grid = conv_tc_grid(ctx, B);
   {
     ProfScope prof(ctx, "conv_tc_wgrad_kernel", st, 2.0 * (double)B * ctc::T * Cout * (double)(taps * Cin),
                    (double)B * ctc::T * 4.0 * (Cout + CinC * 4), "conv_tc_wgrad_kernel");
     if (CinC == 16) {
       const size_t smem3 = (size_t)2 * ctc::W3_STAGE + 2 * ctc::W3_RAW_SLOT + 16 * 64 * 4 + 10 * 8 + 16;
-      static bool configured3 = false;
-      if (!configured3) {
-        if (cudaFuncSetAttribute(ctc::conv_tc_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) != cudaSuccess)
-          return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad3_kernel: cannot reserve shared memory%s");
-        configured3 = true;
-      }
+      if (!wgg_smem_ok(ctx, ctc::conv_tc_wgrad3_kernel, smem3))
+        return wgg_fail(ctx, WGG_ECUDA, "conv_tc_wgrad3_kernel: cannot reserve shared memory%s");
       ctc::conv_tc_wgrad3_kernel<<<grid, ctc::W3_THREADS, smem3, st>>>(a);
     } else {
       ctc::conv_tc_wgrad_kernel<<<grid, ctc::W_THREADS, smem, st>>>(a);

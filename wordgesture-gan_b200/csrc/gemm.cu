@@ -719,14 +719,9 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
                       (p.bsB % 4 == 0) && (((uintptr_t)p.A | (uintptr_t)p.B) % 16 == 0);
   if (vec_ok) {
     constexpr size_t vsmem = (size_t)VSTAGES * VSTAGE_FLOATS * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(gemm_mma_vec_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
-      cudaFuncSetAttribute(gemm_mma_vec_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
-      cudaFuncSetAttribute(gemm_mma_vec_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
-      cudaFuncSetAttribute(gemm_mma_vec_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
-      configured = true;
-    }
+    if (!wgg_smem_ok(ctx, gemm_mma_vec_kernel<1, 1>, vsmem) || !wgg_smem_ok(ctx, gemm_mma_vec_kernel<1, 0>, vsmem) ||
+        !wgg_smem_ok(ctx, gemm_mma_vec_kernel<0, 1>, vsmem) || !wgg_smem_ok(ctx, gemm_mma_vec_kernel<0, 0>, vsmem))
+      return wgg_fail(ctx, WGG_ECUDA, "gemm_mma_vec_kernel: cannot reserve shared memory%s");
     if (a_kf && b_nf) gemm_mma_vec_kernel<1, 1><<<grid, 256, vsmem, st>>>(p);
     else if (a_kf) gemm_mma_vec_kernel<1, 0><<<grid, 256, vsmem, st>>>(p);
     else if (b_nf) gemm_mma_vec_kernel<0, 1><<<grid, 256, vsmem, st>>>(p);

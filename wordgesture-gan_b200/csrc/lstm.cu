@@ -277,11 +277,8 @@ template <int H>
 int rec_fwd_launch_t(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                      float* cseq, int T, int64_t B, int store, cudaStream_t st) {
   const size_t smem = (size_t)(H * H * 4 + 2 * H * 32) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(lstm_rec_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  if (!wgg_smem_ok(ctx, lstm_rec_fwd_kernel<H>, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "lstm_rec_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(B, 32), 2);
   // algorithmic work: 2 dirs x T steps x B x (8 H^2 MAC-flops + gate math); bytes: xproj in, gates/c/h out
   ProfScope prof(ctx, "lstm_rec_fwd_kernel", st, 2.0 * T * (double)B * 8.0 * H * H,
@@ -295,11 +292,8 @@ template <int H>
 int rec_bwd_launch_t(wgg_ctx* ctx, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
                      int64_t off_whh, const float* dh_out, int T, int64_t B, cudaStream_t st) {
   const size_t smem = (size_t)(4 * H * H + 4 * H * 32 + H * 32) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(lstm_rec_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  if (!wgg_smem_ok(ctx, lstm_rec_bwd_kernel<H>, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "lstm_rec_bwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(B, 32), 2);
   ProfScope prof(ctx, "lstm_rec_bwd_kernel", st, 2.0 * T * (double)B * 8.0 * H * H,
                  2.0 * T * (double)B * 4.0 * (4 * H + 4 * H + 2 * H + H));

@@ -124,11 +124,6 @@ __global__ void __launch_bounds__(256) build_x0_tc_kernel(const float* __restric
 //   h_rm : [T][B][2H] row-major, un-rounded fp32 (operand of the weight-gradient GEMMs and of the output head)
 constexpr int GC_CHUNKS = HID + HID / 4;  // 60
 
-// debug: per-step clock64 stamps of CTA (0,0) (enabled through wgg_debug_lstm_ts)
-__device__ long long g_fwd_ts[128 * 8];
-__device__ int g_fwd_ts_on = 0;
-#define TS(k) do { if (ts_on) g_fwd_ts[(step & 127) * 8 + (k)] = clock64(); } while (0)
-
 template <int KXC, int STASH>
 __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
                                                                   const float* __restrict__ wimg, int64_t img_stride,
@@ -191,7 +186,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const bool ts_on = g_fwd_ts_on && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (warp == 0) {
     // ===== producer: stream x_t sub-blocks =====
@@ -227,7 +221,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       const uint32_t use = (uint32_t)(step >> 1);  // how many times this buffer has been used before
       if (!mbar_wait(BAR_ACC_EMPTY(b), (use & 1) ^ 1, s_abort, gerr, 2)) break;
       tc_fence_after();
-      if (lane == 0) TS(0);
       const uint32_t tacc = tmem_base + (uint32_t)(b * ACC_COLS);
 #pragma unroll 1
       for (int sb = 0; sb < NSB; ++sb) {
@@ -244,7 +237,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
       if (!ok) break;
-      if (lane == 0) TS(1);
       // recurrent part, pipelined against the gate math of the previous step: every epilogue warp writes its h chunks
       // in three phases; as soon as phase ph is complete the two MMAs over K chunks (ph, 3+ph) and (6+ph, 9+ph) are
       // issued (the pair's second chunk is addressed through the descriptor's leading-byte-offset), so only the last
@@ -253,7 +245,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
         for (int ph = 0; ph < 3; ++ph) {
           if (!mbar_wait(BAR_H(ph), (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) { ok = false; break; }
           tc_fence_after();
-          if (lane == 0 && ph == 0) TS(2);
           if (elect_one()) {
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2)
@@ -266,7 +257,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       }
       if (elect_one()) mma_commit(BAR_ACC_FULL(b));
       __syncwarp();
-      if (lane == 0) TS(3);
     }
   } else {
     // ===== epilogue: 16 warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 (12 hidden units each) =====
@@ -283,7 +273,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       const int b = step & 1;
       if (!mbar_wait(BAR_ACC_FULL(b), (uint32_t)((step >> 1) & 1), s_abort, gerr, 5)) break;
       tc_fence_after();
-      if (warp == 2 && lane == 0) TS(4);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + part * 48);
       float4* hg4 = reinterpret_cast<float4*>(hout) +
                     (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * (TM) + row;
@@ -303,7 +292,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
-      if (warp == 2 && lane == 0) TS(5);
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
         const int chunk = part * 3 + ch;              // K chunk (4 hidden units) of this direction's h
@@ -347,12 +335,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
             *reinterpret_cast<float4*>(h_rm + ((int64_t)t * B + bidx) * (2 * HID) + dir * HID + chunk * 4) =
                 make_float4(hraw[0], hraw[1], hraw[2], hraw[3]);
         }
-        if (warp == 2 && lane == 0 && ch == 2) TS(6);
         fence_async_smem();   // this phase's h chunk is visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR_H(ch));
       }
-      if (warp == 2 && lane == 0) TS(7);
     }
   }
   tc_fence_before();
@@ -1083,12 +1069,8 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
                  int64_t B, float* gc, float* h_rm, cudaStream_t st) {
   constexpr size_t smem = (size_t)KXC * tc::CHUNK_BYTES_W + tc::KH_CHUNKS * tc::CHUNK_BYTES_W + tc::NSTAGE * tc::SB_BYTES +
                           tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 20 * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc::lstm_tc_fwd_kernel<KXC, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_fwd_kernel: cannot reserve shared memory%s");
-    configured = true;
-  }
+  if (!wgg_smem_ok(ctx, tc::lstm_tc_fwd_kernel<KXC, STASH>, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)ntiles, 2);
   // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out, and for the
   // grad-carrying forward the stash it has to write (gates + c: 960 B per gesture-step-direction, + h_rm rows)
@@ -1220,14 +1202,9 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
   constexpr size_t smem_bwd = (size_t)tc::HID * tc::CHUNK_BYTES_A + tc::HID * tc::WT_CHUNK_BYTES + 4 * 8 + 16;
   constexpr size_t smem_dx = (size_t)3 * (tc::HID / 2) * tc::CHUNK_BYTES_A + 2 * tc::HID * tc::WT_CHUNK_BYTES + 8 * 8 + 16;
   constexpr size_t smem_dw = (size_t)2 * tc::DW_STAGE + tc::DW_NRAW * tc::DW_RAW_SLOT + 12 * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc::lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd) != cudaSuccess ||
-        cudaFuncSetAttribute(tc::lstm_tc_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dx) != cudaSuccess ||
-        cudaFuncSetAttribute(tc::lstm_tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw) != cudaSuccess)
-      return wgg_fail(ctx, WGG_ECUDA, "generator_backward_tc: cannot reserve shared memory%s");
-    configured = true;
-  }
+  if (!wgg_smem_ok(ctx, tc::lstm_tc_bwd_kernel, smem_bwd) || !wgg_smem_ok(ctx, tc::lstm_tc_dx_kernel, smem_dx) ||
+      !wgg_smem_ok(ctx, tc::lstm_tc_dw_kernel, smem_dw))
+    return wgg_fail(ctx, WGG_ECUDA, "generator_backward_tc: cannot reserve shared memory%s");
   const int64_t npairs = (int64_t)p.T * p.ntiles;
   for (int l = p.L - 1; l >= 0; --l) {
     const int I = l == 0 ? p.pd + p.Z : 96;
@@ -1277,13 +1254,4 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
     WGG_CHECK_LAUNCH(ctx, "dz_chunk_kernel");
   }
   return WGG_OK;
-}
-
-// debug hook (not part of include/wgg.h): enable != 0 arms the per-step clock stamps of lstm_tc_fwd_kernel CTA (0,0);
-// out (host, 1024 int64) receives the stamps of the most recent launch.
-extern "C" __attribute__((visibility("default"))) int wgg_debug_lstm_ts(int enable, long long* out) {
-  cudaDeviceSynchronize();
-  if (out) cudaMemcpyFromSymbol(out, tc::g_fwd_ts, sizeof(long long) * 1024);
-  cudaMemcpyToSymbol(tc::g_fwd_ts_on, &enable, sizeof(int));
-  return 0;
 }

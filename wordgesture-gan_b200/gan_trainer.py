@@ -51,6 +51,13 @@ class WordGestureGANTrainer:
         self.use_cuda_graph = "auto"
 
     # ---- generator-side cycles ------------------------------------------------------------------
+    def _randn(self, B: int) -> torch.Tensor:
+        """One (B, Z) normal draw; under data parallelism the global draw sliced to this rank (parallel.py)."""
+        from .parallel import randn_rank_rows
+        from .train_step import dp_slice
+        rank, world = dp_slice(self)
+        return randn_rank_rows(B, self.model_config.latent_dim, rank, world, self.device)
+
     def _adversarial_terms(self, disc, fake, real):
         """-mean D(fake) and the feature-matching term; three discriminator calls in the reference's order
         (score(fake), features(fake), features(real)) because each advances the spectral-norm power iteration
@@ -69,9 +76,11 @@ class WordGestureGANTrainer:
         tc = self.training_config
         B = prototype.size(0)
         if z is None:
-            z = torch.randn(B, self.model_config.latent_dim, device=self.device)
+            z = self._randn(B)
         fake = self.generator(prototype, z)
         wgan, feat = self._adversarial_terms(self.discriminator_1, fake, real_gesture)
+        if eps_recover is None:
+            eps_recover = self._randn(B)  # drawn where the reference draws it: inside the recovery pass (trainer.py:118)
         with torch.no_grad():  # latent recovery carries no gradient in the reference either (trainer.py:116-119)
             z_rec, _, _ = self.encoder(fake, eps_recover)
         lat = self.latent_encoding_loss(z, z_rec)
@@ -81,6 +90,8 @@ class WordGestureGANTrainer:
     def cycle2_tensors(self, prototype, real_gesture, eps: Optional[torch.Tensor] = None):
         """Cycle 2 (X -> z -> X')."""
         tc = self.training_config
+        if eps is None:
+            eps = self._randn(prototype.size(0))
         z_enc, mu, log_var = self.encoder(real_gesture, eps)
         fake = self.generator(prototype, z_enc)
         wgan, feat = self._adversarial_terms(self.discriminator_2, fake, real_gesture)
@@ -91,21 +102,21 @@ class WordGestureGANTrainer:
                              "cycle2_total": total}
 
     def cycles_tensors(self, prototype, real_gesture, z: Optional[torch.Tensor] = None,
-                       eps_recover: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+                       eps_recover: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None,
+                       training_config: Optional[TrainingConfig] = None):
         """Cycle 1 and cycle 2 together, with ONE generator call on the stacked batch [z ; z_enc] (the two cycles'
         generator passes are independent, so stacking them is exact and doubles the SM fill of the persistent
         recurrent kernels; autograd then runs one generator backward for both).  The three normal draws are made
         in the reference's order (trainer.py:105, :118 via models.py:85, :161) before any of them is consumed.
         Returns (fake1, fake2, total1, total2, dict1, dict2) with the same values as cycle1_tensors / cycle2_tensors."""
-        tc = self.training_config
+        tc = training_config if training_config is not None else self.training_config
         B = prototype.size(0)
-        Z = self.model_config.latent_dim
         if z is None:
-            z = torch.randn(B, Z, device=self.device)
+            z = self._randn(B)
         if eps_recover is None:
-            eps_recover = torch.randn(B, Z, device=self.device)
+            eps_recover = self._randn(B)
         if eps is None:
-            eps = torch.randn(B, Z, device=self.device)
+            eps = self._randn(B)
         z_enc, mu, log_var = self.encoder(real_gesture, eps)
         fake = self.generator(torch.cat([prototype, prototype], 0), torch.cat([z, z_enc], 0))
         fake1, fake2 = fake[:B], fake[B:]

@@ -34,13 +34,17 @@ class GraphedTrainStep:
         gen = torch.Generator(device=dev).manual_seed(0)
         self.real.copy_(torch.rand(self.real.shape, device=dev, generator=gen) * 2 - 1)
         self.proto.copy_(torch.rand(self.proto.shape, device=dev, generator=gen) * 2 - 1)
+        from . import _lib
+        # The captured launches bake scratch addresses in: the graph owns its scratch (sized by the warm-up, frozen
+        # during capture, alive as long as this object) so that later eager calls cannot free it under the graph.
+        self.scratch = _lib.ScratchScope()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         prev_par = getattr(trainer, "parallel_critics", "auto")
         if prev_par == "auto":
             trainer.parallel_critics = True   # warm up the two-stream critic phase the capture will use
         try:
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), self.scratch:
                 for _ in range(max(1, warmup)):
                     train_batch(trainer, self.real, self.proto, max_norm)
         finally:
@@ -50,10 +54,10 @@ class GraphedTrainStep:
         self._restore(snap)
         for name in _OPTS:
             getattr(trainer, name).refresh_device_scalars(force_step=True)
-        from . import _lib
         l0 = _lib.launch_count(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        self.scratch.frozen = True
+        with self.scratch, torch.cuda.graph(self.graph):
             self.out = train_batch(trainer, self.real, self.proto, max_norm)
         self.launches_per_step = _lib.launch_count(dev) - l0  # libwgg_sm100 kernels captured (replayed every call)
         # capture records, it does not execute: training state is untouched

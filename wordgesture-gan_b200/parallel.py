@@ -36,6 +36,18 @@ def draw_global_noise(n_draws: int, global_batch: int, latent_dim: int, device, 
     return [torch.randn(global_batch, latent_dim, device=device, generator=generator) for _ in range(n_draws)]
 
 
+def randn_rank_rows(per_rank_batch: int, latent_dim: int, rank: int, world_size: int, device, generator=None
+                    ) -> torch.Tensor:
+    """One (B, Z) normal draw of the step as the product path makes it under data parallelism: EVERY rank draws the
+    GLOBAL (world * B, Z) tensor - same seed, same generator offset on all ranks, so the same numbers - and keeps
+    its own rows.  The concatenation over ranks is exactly the draw a single process would make for the global
+    batch (utils.py:71, trainer.py:105, models.py:85), and the generators stay in lock step."""
+    if world_size == 1:
+        return torch.randn(per_rank_batch, latent_dim, device=device, generator=generator)
+    full = torch.randn(world_size * per_rank_batch, latent_dim, device=device, generator=generator)
+    return full[rank * per_rank_batch:(rank + 1) * per_rank_batch].contiguous()
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None, world_size: Optional[int] = None) -> torch.Tensor:
     """In-place mean all-reduce of a flat gradient bucket."""
     if world_size is None:
@@ -70,6 +82,7 @@ class DataParallelGAN:
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
         self.group_d2 = dist.new_group(ranks=ranks)
         trainer.optimizer_D2.process_group = self.group_d2
+        trainer._dp = self  # train_step.train_batch draws the step's noise for the global batch and slices by rank
         self.sync_state()
 
     def sync_state(self):

@@ -25,8 +25,14 @@ def run_training(gestures: torch.Tensor, prototypes: torch.Tensor, num_epochs: i
                  resume: bool = True, model_config: Optional[ModelConfig] = None,
                  training_config: Optional[TrainingConfig] = None, checkpoint_every: int = 10,
                  grad_clip_norm: float = 1.0, seed: int = 42, device="cuda", use_cuda_graph: bool = True,
-                 verbose: bool = True) -> List[Dict[str, float]]:
+                 verbose: bool = True, math_mode: Optional[str] = None) -> List[Dict[str, float]]:
+    """``math_mode`` ("fp32" | "tf32" | "tf32x3", see set_math_mode) is set explicitly when given; either way the
+    mode the run uses is logged (every measured number in DESIGN.md is in a tensor-core mode; the process default
+    is the fp32 FMA path)."""
     import torch.distributed as dist
+    from . import _lib
+    if math_mode is not None:
+        _lib.set_math_mode(math_mode)
     model_config = model_config or ModelConfig()
     training_config = training_config or TrainingConfig(num_epochs=num_epochs, save_every=checkpoint_every)
     device = torch.device(device)
@@ -60,6 +66,8 @@ def run_training(gestures: torch.Tensor, prototypes: torch.Tensor, num_epochs: i
                 sched.step()
         if verbose and rank == 0:
             log(f"Resumed from epoch {start_epoch}")
+    if verbose and rank == 0:
+        log(f"math mode {_lib.get_math_mode()}, world size {world}, {per_rank_batch} gestures per rank per batch")
     history: List[Dict[str, float]] = []
     for epoch in range(start_epoch, num_epochs):                               # :150-199
         trainer.current_epoch = epoch

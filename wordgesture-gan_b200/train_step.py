@@ -42,20 +42,38 @@ def _critic_side_stream(trainer, dev):
     return st
 
 
+def dp_slice(trainer):
+    """(rank, world) of the data-parallel group attached to ``trainer`` by parallel.DataParallelGAN, else (0, 1)."""
+    dp = getattr(trainer, "_dp", None)
+    return (dp.rank, dp.world_size) if dp is not None else (0, 1)
+
+
 def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, max_norm: float,
-                noise: Optional[List[torch.Tensor]] = None, on_step=None) -> Dict[str, torch.Tensor]:
+                noise: Optional[List[torch.Tensor]] = None, on_step=None, training_config=None,
+                model_config=None) -> Dict[str, torch.Tensor]:
     """One batch of the step.  ``noise`` optionally injects the 2*n_critic+3 (B, Z) normal draws in consumption
     order (z_rand, eps) x n_critic, z, eps_recover, eps; by default each is a torch.randn call made at the point
     where the reference makes it, so the global RNG stream is consumed identically.
-    ``on_step(tag, optimizer)`` (optional) is called right before each of the 12 optimiser steps (tests use it
-    to read the un-clipped gradients).  Returns 0-dim device tensors for all 11 logged scalars."""
-    tc, mc = trainer.training_config, trainer.model_config
+    Under data parallelism (a DataParallelGAN is attached) ``real_gesture`` / ``prototype`` are this rank's shard and
+    every default draw is made for the GLOBAL batch - torch.randn(world * B, Z) on every rank from the shared seed -
+    and sliced to the rank's rows, so an N-rank run consumes the same numbers as the 1-rank run on the global batch
+    (injected ``noise`` is taken as already sharded).
+    ``training_config`` / ``model_config`` default to the trainer's (train_epoch_with_grad_clip forwards its own
+    arguments, utils.py:68,71).  ``on_step(tag, optimizer)`` (optional) is called right before each of the 12
+    optimiser steps (tests use it to read the un-clipped gradients).  Returns 0-dim device tensors for all 11
+    logged scalars."""
+    tc = training_config if training_config is not None else trainer.training_config
+    mc = model_config if model_config is not None else trainer.model_config
     dev = real_gesture.device
     B = real_gesture.size(0)
     it = iter(noise) if noise is not None else None
+    rank, world = dp_slice(trainer)
 
     def draw():
-        return next(it) if it is not None else torch.randn(B, mc.latent_dim, device=dev)
+        if it is not None:
+            return next(it)
+        from .parallel import randn_rank_rows
+        return randn_rank_rows(B, mc.latent_dim, rank, world, dev)
 
     out: Dict[str, torch.Tensor] = {}
     # ---- critic phase (utils.py:68-109) ----
@@ -107,6 +125,9 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
             on_step(f"{name[:2].upper()}_grads_{critic_it}", opt)
         opt.step(max_norm=max_norm)
         out[name] = loss.detach()
+        if side is not None and name == "d2_loss" and not torch.cuda.is_current_stream_capturing():
+            # eager two-stream mode: this scalar was allocated on the side stream and is read on the main one
+            out[name].record_stream(main)
 
     for critic_it in range(n):
         d_step("d1_loss", trainer.discriminator_1, trainer.optimizer_D1, fakes_1[critic_it], critic_it)
@@ -121,7 +142,8 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
     trainer.optimizer_G.zero_grad()
     trainer.optimizer_E.zero_grad()
     z_c1, eps_rec, eps_c2 = draw(), draw(), draw()  # reference order: cycle-1 z, its recovery eps, cycle-2 eps
-    _, _, loss1, loss2, d1, d2 = trainer.cycles_tensors(prototype, real_gesture, z=z_c1, eps_recover=eps_rec, eps=eps_c2)
+    _, _, loss1, loss2, d1, d2 = trainer.cycles_tensors(prototype, real_gesture, z=z_c1, eps_recover=eps_rec, eps=eps_c2,
+                                                        training_config=tc)
     # the discriminators' own weight gradients of this backward are never used (the reference zeroes them before
     # the next critic step, utils.py:75,96): skip computing them, keep d(loss)/d(fake gesture)
     _lib.SKIP_DISC_WEIGHT_GRADS = True
@@ -157,6 +179,9 @@ def train_epoch_with_grad_clip(trainer, dataloader, max_norm, model_config, trai
         except TypeError:  # an iterable without a length
             use_graph = False
     use_graph = bool(use_graph)
+    # the reference reads n_critic / the loss weights / latent_dim from the ARGUMENTS (utils.py:68,71); a captured
+    # graph is specific to the configuration it was captured with
+    same_cfg = training_config is trainer.training_config or training_config == trainer.training_config
     for batch in dataloader:
         real = batch["gesture"].to(device, non_blocking=True)
         proto = batch["prototype"].to(device, non_blocking=True)
@@ -164,16 +189,25 @@ def train_epoch_with_grad_clip(trainer, dataloader, max_norm, model_config, trai
             # full batches replay one captured CUDA graph (graph_step.py); a ragged last batch runs eagerly
             from .graph_step import GraphedTrainStep
             cache = trainer.__dict__.setdefault("_graphed_steps", {})
-            key = (real.size(0), float(max_norm))
-            if key not in cache and (not cache or real.size(0) == training_config.batch_size):
+            key = (real.size(0), float(max_norm), _lib.get_math_mode())
+            if same_cfg and key not in cache and (not cache or real.size(0) == training_config.batch_size):
                 cache[key] = GraphedTrainStep(trainer, real.size(0), max_norm)
-            out = cache[key](real, proto) if key in cache else train_batch(trainer, real, proto, max_norm)
+            out = cache[key](real, proto) if (same_cfg and key in cache) else train_batch(
+                trainer, real, proto, max_norm, training_config=training_config, model_config=model_config)
         else:
-            out = train_batch(trainer, real, proto, max_norm)
+            out = train_batch(trainer, real, proto, max_norm, training_config=training_config, model_config=model_config)
         vals = torch.stack([out[k] for k in keys])
         sums = vals if sums is None else sums + vals
         num_batches += 1
     if num_batches == 0:
         raise ZeroDivisionError("empty dataloader")
     means = (sums / num_batches).tolist()  # the only host sync of the epoch
+    # the persistent tcgen05 kernels end on a bounded mbarrier wait instead of hanging; a wedged pipeline leaves a
+    # code in the context's error word - surface it here, at the epoch's one synchronisation point
+    code = _lib.async_error(device)
+    if code:
+        raise _lib.WggError(f"a persistent tensor-core kernel timed out during this epoch (pipeline code {code}); "
+                            "the epoch's updates are not trustworthy")
+    if not all(np.isfinite(m) for m in means):
+        raise _lib.WggError(f"non-finite epoch losses {dict(zip(keys, means))}")
     return dict(zip(keys, means))
