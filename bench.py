@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 METRIC = "GAN train gestures/sec (G+D step)"
 UNIT = "gestures/s"
 FLOP_PER_GESTURE_STEP = 1.340e9  # BASELINE.md section 3 (default model, as-written call counts)
+DEFAULT_MATH = "tf32"
+PROFILE_CANDIDATES = ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel", "lstm_tc_dw_kernel", "lstm_tc_dx_kernel",
+                      "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel")
 
 
 def load_peaks():
@@ -142,6 +145,61 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def reference_cuda_leg(dev, batches, steps, sample_batch):
+    """The reference's library path on THIS GPU (SURVEY.md 8(d) last row): oracle/torch_port.py - the reference's
+    modules restated on torch.nn - on device cuda with torch's defaults, i.e. cuDNN LSTM / conv with TF32 allowed and
+    fp32 cuBLAS (src/gan/models.py:160,163,270-291), 11 .item() syncs per batch like utils.py:84-131.  Reported next to
+    our numbers as the library-kernel bar; it is not the CPU baseline and not the driver's reference arm."""
+    import torch
+    from oracle import torch_port
+    out = {"what": "oracle/torch_port.py on cuda (cuDNN TF32 LSTM/conv + fp32 cuBLAS, torch defaults), eager, same step"}
+    try:
+        for B in batches:
+            tp = torch_port.TorchPortTrainer(seed=42, device=dev)
+            g = torch.Generator().manual_seed(0)
+            real = (torch.rand(B, 128, 3, generator=g) * 2 - 1).to(dev)
+            proto = (torch.rand(B, 128, 3, generator=g) * 2 - 1).to(dev)
+            for _ in range(2):
+                tp.train_batch(real, proto)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                tp.train_batch(real, proto)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[f"train_B{B}"] = {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps}
+            if B == batches[-1]:
+                proto_s = (torch.rand(sample_batch, 128, 3, generator=g) * 2 - 1).to(dev)
+                z = torch.randn(sample_batch, 32, device=dev)
+                tp.G.eval()
+                for _ in range(2):
+                    tp.sample(proto_s, z)
+                torch.cuda.synchronize(dev)
+                e0.record()
+                for _ in range(5):
+                    tp.sample(proto_s, z)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                out["sampling"] = {"value": sample_batch * 5 / (e0.elapsed_time(e1) / 1e3), "unit": "samples/s",
+                                   "batch": sample_batch}
+            del tp
+    except Exception as ex:  # a reported extra: never lose the GPU line because of it
+        out["error"] = repr(ex)
+    return out
+
+
+def load_json(rel):
+    path = os.path.join(ROOT, rel)
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -152,11 +210,14 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--sample-batch", type=int, default=74 * 128, help="gestures per generator sampling call")
+    ap.add_argument("--sample-total", type=int, default=1_000_000, help="BASELINE configs[4]: total samples over all GPUs")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying the captured CUDA graph")
-    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32", "tf32x3"],
-                    help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); fp32: FMA only")
+    ap.add_argument("--math", default=DEFAULT_MATH, choices=["fp32", "tf32", "tf32x3"],
+                    help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); tf32x3: conv "
+                         "contractions error-compensated (every gradient within the north star's 1e-3); fp32: FMA only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,17 +240,25 @@ def main():
     mc, tc = wgg.ModelConfig(), wgg.TrainingConfig(batch_size=B)
     wgg.seed_everything(42)
     tr = wgg.WordGestureGANTrainer(mc, tc, dev)
+    tr.use_cuda_graph = not args.no_graph
     if world > 1:
         parallel.DataParallelGAN(tr)
-    for m in (tr.generator, tr.encoder, tr.discriminator_1, tr.discriminator_2):
-        m.train()
     g = torch.Generator().manual_seed(1000 + rank)
     real_h = (torch.rand(B, 128, 3, generator=g) * 2 - 1).pin_memory()
     proto_h = (torch.rand(B, 128, 3, generator=g) * 2 - 1).pin_memory()
     real_d, proto_d = real_h.to(dev), proto_h.to(dev)
-    keys = ("d1_loss", "d2_loss", "cycle1_total", "cycle2_total")
+    host_batch = [{"gesture": real_h, "prototype": proto_h}]  # what a DataLoader(pin_memory=True) yields (data.py:526-533)
 
-    gs = None if args.no_graph else wgg.GraphedTrainStep(tr, B, 1.0)
+    def epoch_from_host(nbatches):
+        """The reference's entry point (utils.py:28) over pinned host batches: H2D copies, the step, and the read-back
+        of the epoch means inside."""
+        return wgg.train_epoch_with_grad_clip(tr, host_batch * nbatches, 1.0, mc, tc, dev)
+
+    # warm-up THROUGH the public entry point: the first full batch captures the step's CUDA graph, the rest replay it
+    epoch_from_host(max(args.warmup, 3))
+    gs = None
+    if not args.no_graph:
+        gs = tr._graphed_steps[(B, 1.0, args.math)]
 
     def step_eager():
         return wgg.train_batch(tr, real_d, proto_d, 1.0)
@@ -198,11 +267,7 @@ def main():
         return gs(real_d, proto_d) if gs is not None else step_eager()
 
     def step_e2e():
-        if gs is not None:
-            out = gs(real_h, proto_h)  # pinned host -> the graph's static device inputs, then one replay
-        else:
-            out = wgg.train_batch(tr, real_h.to(dev, non_blocking=True), proto_h.to(dev, non_blocking=True), 1.0)
-        return torch.stack([out[k] for k in keys]).tolist()  # D2H read of the step's losses
+        return epoch_from_host(1)   # one batch per call: every step pays its H2D copies and the D2H read of its losses
 
     def sync():
         if world > 1:
@@ -231,8 +296,7 @@ def main():
     prof_kernel = args.profile_kernel
     shares = {}
     if prof_kernel == "auto":
-        for cand in ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel", "lstm_tc_dw_kernel", "lstm_tc_dx_kernel",
-                     "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel"):
+        for cand in PROFILE_CANDIDATES:
             _lib.profile_enable(dev, cand)
             step_eager()
             shares[cand] = _lib.profile_read(dev)["ms"]
@@ -256,8 +320,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # generator sampling throughput (second half of the BASELINE metric): eval / no-grad, output written to HBM.
-    # Batch = 74 tiles x 128 gestures: with two directions that is exactly one wave of the persistent recurrent
-    # kernel on 148 SMs.
     tr.generator.eval()
     BS = args.sample_batch
     gs_ = torch.Generator().manual_seed(2000 + rank)
@@ -272,6 +334,22 @@ def main():
         sample()
     ms_s = timed(sample, 10)
     samples_per_s = world * BS * 10 / (ms_s / 1e3)
+    # BASELINE configs[4]: sample_total samples over all GPUs (each rank its shard, no collective), in calls of BS
+    per_rank = args.sample_total // world
+    calls = max(1, (per_rank + BS - 1) // BS)
+    out_buf = torch.empty(min(per_rank, calls * BS), 128, 3, device=dev)
+
+    def sample_shard():
+        with torch.no_grad():
+            for c in range(calls):
+                n = min(BS, per_rank - c * BS)
+                if n <= 0:
+                    break
+                out_buf[c * BS:c * BS + n].copy_(tr.generator(proto_s[:n], zs[:n]))
+
+    sample_shard()
+    ms_1m = timed(sample_shard, 1)
+    del out_buf
 
     if rank != 0:
         return finish(world, dev)
@@ -286,18 +364,14 @@ def main():
     ai = prof["flops"] / max(prof["bytes"], 1.0)
     ridge = peaks["tf32_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
     hbm_bound = ai < ridge
+    # DRAM traffic of the same kernel class over the SAME launch mix (every launch of one step), from the committed
+    # `ncu --set full` capture of this command (scripts/ncu_traffic.py writes the file); null if there is none
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_full_lstm_tc_fwd_B4096.json")
-    if prof_kernel == "lstm_tc_fwd_kernel" and os.path.exists(tpath):
-        try:
-            caps = json.load(open(tpath))
-            def gb(c, key):
-                return float(next(v for k, v in c.items() if k.startswith(key)).replace(",", ""))
-            traffic = sum(gb(c, "dram__bytes_read.sum") + gb(c, "dram__bytes_write.sum") for c in caps) / len(caps) * 1e9
-            traffic_src = ("profiles/r01_ncu_full_lstm_tc_fwd_B4096.json: mean DRAM read+write bytes of the captured launches "
-                           "(the three 40960-gesture critic-phase layer launches, B=4096; algorithmic 3.6 / 6.0 / 6.0 GB)")
-        except Exception:
-            traffic = None
+    tr_file = load_json(f"profiles/r02_ncu_traffic_{prof_kernel}.json")
+    if tr_file and tr_file.get("batch_per_gpu") == B and tr_file.get("math") == args.math:
+        traffic = tr_file["dram_bytes_per_launch_mean"]
+        traffic_src = (f"profiles/r02_ncu_traffic_{prof_kernel}.json: mean dram__bytes_read.sum + dram__bytes_write.sum over "
+                       f"the {tr_file['launches']} launches of one step (same launch mix as algorithmic_bytes_per_launch)")
     roof = {"bound": "hbm" if hbm_bound else "tensor", "kernel": prof_kernel,
             "achieved": k_gbs if hbm_bound else k_tflops, "peak": peaks["hbm_gbs"] if hbm_bound else peaks["tf32_tflops"],
             "unit": "GB/s" if hbm_bound else "TFLOP/s",
@@ -313,7 +387,9 @@ def main():
             "whole_step": {"achieved": FLOP_PER_GESTURE_STEP * value / world / 1e12, "unit": "TFLOP/s",
                            "frac": FLOP_PER_GESTURE_STEP * value / world / 1e12 / peaks["tf32_tflops"]}}
     cpu = None
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
+        # rank 0 at N = 1 only: under torchrun the other ranks would sit in an NCCL barrier (GPUs busy-waiting) while
+        # this leg runs, and the host cores are shared by N processes
         cores = os.cpu_count() or 1
         try:
             v, dt = cpu_port_gestures_per_s(args.cpu_sample, cores)
@@ -322,22 +398,38 @@ def main():
                              f"(torch CPU kernels, {cores} threads)"}
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line because of it
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex!r}"}
+    ref_cuda = None
+    if world == 1 and not args.no_reference_cuda:
+        ref_cuda = reference_cuda_leg(dev, (512, B) if B != 512 else (512,), 3, BS)
+    numerics = load_json("profiles/r02_numerics_by_mode.json")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tf32": "tf32", "tf32x3": "tf32x3", "fp32": "f32"}[args.math],
+        "math_mode": args.math,
+        "numerics": (numerics or {}).get(args.math, {"note": "profiles/r02_numerics_by_mode.json not found"}),
         "data": "synthetic",
         "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
                                "T=128), BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "launch": "eager" if gs is None else "cuda-graph (1 replay per step)", "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
+                   "parallelism": f"dp{world}", "launch": "eager" if gs is None else "cuda-graph (1 replay per step)",
+                   "math_mode": args.math,
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 128 * 3 * 4,
-                "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 16 + 4, "ms_per_step": ms_e2e / args.steps,
+                "api": "train_epoch_with_grad_clip(trainer, [pinned CPU batch dict], 1.0, model_config, training_config, device) "
+                       "once per step: H2D of gesture + prototype, one graph replay, D2H of the four loss means + the "
+                       "pipeline-health word"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": cpu,
+        "reference_cuda": ref_cuda,
         "clocks": clocks,
         "sampling": {"value": samples_per_s, "unit": "samples/s", "batch_per_gpu": BS,
-                     "roofline_frac": 50.6e6 * samples_per_s / world / 1e12 / peaks["tf32_tflops"]},
+                     "roofline_frac": 50.6e6 * samples_per_s / world / 1e12 / peaks["tf32_tflops"],
+                     "configs4": {"total_samples": per_rank * world, "per_gpu": per_rank, "ms": ms_1m,
+                                  "value": per_rank * world / (ms_1m / 1e3), "unit": "samples/s",
+                                  "note": "BASELINE configs[4]: every rank generates its shard in calls of batch_per_gpu "
+                                          "and writes it to one HBM buffer; no collective; max over ranks"}},
     }
     print(json.dumps(line), flush=True)
     finish(world, dev)

@@ -98,39 +98,44 @@ def _fm(real_f, fake_f):
 
 
 class TorchPortTrainer:
-    def __init__(self, seed: int = 42, cfg: ModelCfg = None, tc: TrainCfg = None, dtype=torch.float32):
+    def __init__(self, seed: int = 42, cfg: ModelCfg = None, tc: TrainCfg = None, dtype=torch.float32, device="cpu"):
+        """``device="cuda"`` runs the same restatement on the library kernels the reference reaches on a GPU (cuDNN
+        LSTM / conv with TF32 allowed, fp32 cuBLAS - torch's defaults, which the reference does not change): the
+        "reference on CUDA" bar of SURVEY.md 8(d)."""
         self.cfg, self.tc = cfg or ModelCfg(), tc or TrainCfg()
+        self.device = torch.device(device)
         torch.manual_seed(seed)
         D = _DT if self.cfg.use_temporal_disc else _DM
         self.G, self.E, self.D1, self.D2 = _G(self.cfg), _E(self.cfg), D(self.cfg), D(self.cfg)
         self.mods = {"G": self.G, "E": self.E, "D1": self.D1, "D2": self.D2}
         for m in self.mods.values():
-            m.to(dtype).train()
+            m.to(dtype).to(self.device).train()
         self.dtype = dtype
         self.opt = {k: torch.optim.Adam(m.parameters(), lr=self.tc.learning_rate, betas=self.tc.betas)
                     for k, m in self.mods.items()}
 
     def load_state(self, states):
         for k, m in self.mods.items():
-            m.load_state_dict({n: torch.as_tensor(v, dtype=self.dtype) for n, v in states[k].items()})
+            m.load_state_dict({n: torch.as_tensor(v, dtype=self.dtype, device=self.device) for n, v in states[k].items()})
 
     def state(self):
-        return {k: {n: v.detach().double().numpy() for n, v in m.state_dict().items()} for k, m in self.mods.items()}
+        return {k: {n: v.detach().double().cpu().numpy() for n, v in m.state_dict().items()} for k, m in self.mods.items()}
 
     def _record(self, rec, tag, mod):
         """Un-clipped gradients of one optimiser step (same tags as wgg_oracle.train_batch / the product's on_step)."""
         if rec is not None:
-            rec[tag] = {n: p.grad.detach().double().numpy().copy() for n, p in mod.named_parameters()}
+            rec[tag] = {n: p.grad.detach().double().cpu().numpy().copy() for n, p in mod.named_parameters()}
 
     def train_batch(self, real, proto, noise=None, max_norm: float = 1.0, record=None, fakes=None):
         """One batch of utils.py:62-135.  ``record`` (dict) receives the un-clipped gradients of the 12 optimiser steps
         (D1_grads_i, D2_grads_i, G_grads, E_grads); ``fakes`` (dict) the two generator-side fake gestures."""
         c, tc = self.cfg, self.tc
         B = real.shape[0]
-        real, proto = real.to(self.dtype), proto.to(self.dtype)
+        dev = self.device
+        real, proto = real.to(dev, self.dtype), proto.to(dev, self.dtype)
         it = iter(noise) if noise is not None else None
-        draw = (lambda: torch.as_tensor(next(it), dtype=self.dtype)) if it is not None else (
-            lambda: torch.randn(B, c.latent_dim, dtype=self.dtype))
+        draw = (lambda: torch.as_tensor(next(it), dtype=self.dtype, device=dev)) if it is not None else (
+            lambda: torch.randn(B, c.latent_dim, dtype=self.dtype, device=dev))
         out = {}
         for it_c in range(tc.n_critic):
             for key, D in (("D1", self.D1), ("D2", self.D2)):
@@ -151,7 +156,7 @@ class TorchPortTrainer:
         z = draw()
         fake = self.G(proto, z)
         if fakes is not None:
-            fakes["fake1"] = fake.detach().double().numpy()
+            fakes["fake1"] = fake.detach().double().cpu().numpy()
         wg, ff, rf = -self.D1(fake).mean(), self.D1.feats(fake), self.D1.feats(real)
         with torch.no_grad():
             zr = self.E(fake, draw())[0]
@@ -161,7 +166,7 @@ class TorchPortTrainer:
         ze, mu, lv = self.E(real, draw())
         fake = self.G(proto, ze)
         if fakes is not None:
-            fakes["fake2"] = fake.detach().double().numpy()
+            fakes["fake2"] = fake.detach().double().cpu().numpy()
         wg, ff, rf = -self.D2(fake).mean(), self.D2.feats(fake), self.D2.feats(real)
         feat, rec = _fm(rf, ff), F.l1_loss(fake, real)
         kld = (-0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=1)).mean()
@@ -180,8 +185,9 @@ class TorchPortTrainer:
     def cycle1(self, proto, real, z, eps_recover):
         """trainer.py:84-140 (train_generator_step_cycle1) with the two normal draws injected."""
         tc = self.tc
-        proto, real = proto.to(self.dtype), real.to(self.dtype)
-        z, eps_recover = torch.as_tensor(z, dtype=self.dtype), torch.as_tensor(eps_recover, dtype=self.dtype)
+        dev = self.device
+        proto, real = proto.to(dev, self.dtype), real.to(dev, self.dtype)
+        z, eps_recover = torch.as_tensor(z, dtype=self.dtype, device=dev), torch.as_tensor(eps_recover, dtype=self.dtype, device=dev)
         fake = self.G(proto, z)
         wg, ff, rf = -self.D1(fake).mean(), self.D1.feats(fake), self.D1.feats(real)
         with torch.no_grad():
@@ -194,8 +200,9 @@ class TorchPortTrainer:
     def cycle2(self, proto, real, eps):
         """trainer.py:142-193 (train_generator_step_cycle2) with the reparameterisation noise injected."""
         tc = self.tc
-        proto, real = proto.to(self.dtype), real.to(self.dtype)
-        ze, mu, lv = self.E(real, torch.as_tensor(eps, dtype=self.dtype))
+        dev = self.device
+        proto, real = proto.to(dev, self.dtype), real.to(dev, self.dtype)
+        ze, mu, lv = self.E(real, torch.as_tensor(eps, dtype=self.dtype, device=dev))
         fake = self.G(proto, ze)
         wg, ff, rf = -self.D2(fake).mean(), self.D2.feats(fake), self.D2.feats(real)
         feat, rec = _fm(rf, ff), F.l1_loss(fake, real)
@@ -206,4 +213,4 @@ class TorchPortTrainer:
 
     def sample(self, proto, z):
         with torch.no_grad():
-            return self.G(proto.to(self.dtype), z.to(self.dtype))
+            return self.G(proto.to(self.device, self.dtype), z.to(self.device, self.dtype))

@@ -18,7 +18,10 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly the timed steps
 for _ in range(nsteps): wgg.train_batch(tr, real, proto, 1.0)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 t_issue = time.perf_counter() - t0
 e1.record(); torch.cuda.synchronize()
 print(f"B={B} mode={mode}: {e0.elapsed_time(e1)/nsteps:.2f} ms/step device, CPU issue time {t_issue/nsteps*1e3:.2f} ms/step")
