@@ -91,43 +91,58 @@ class ClockSampler:
                 "samples": len(mhz)}
 
 
-def cpu_port_gestures_per_s(batch: int, threads: int):
-    """Times the CPU restatement of the step (oracle/torch_port.py: the reference's modules restated with the same
-    torch CPU library kernels the reference itself runs on, all host threads) on a bounded sample."""
+def synthetic_batch(batch, seed=0):
     import torch
-    from oracle import torch_port
-    torch.set_num_threads(threads)
-    tp = torch_port.TorchPortTrainer(seed=42)
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator().manual_seed(seed)
     real = torch.rand(batch, 128, 3, generator=g) * 2 - 1
     proto = torch.rand(batch, 128, 3, generator=g) * 2 - 1
-    tp.train_batch(real, proto)  # warm-up
+    return real, proto
+
+
+def make_cpu_stepper(batch: int, threads: int):
+    """The reference's CPU implementation of the step on all host threads: the reference's OWN files when they are
+    reachable (/root/reference in the build container, the vendored oracle/_ref on the GPU box - oracle/ref_loader.py),
+    else the torch.nn restatement oracle/torch_port.py.  Returns (kind, description, step_fn)."""
+    import torch
+    torch.set_num_threads(threads)
+    real, proto = synthetic_batch(batch)
+    try:
+        from oracle.ref_runner import ReferenceRunner, reference_available
+        if reference_available():
+            rr = ReferenceRunner("cpu", seed=42, batch_size=batch)
+            batches = [{"gesture": real, "prototype": proto}]
+            return ("reference", "the unmodified reference: WordGestureGANTrainer + train_epoch_with_grad_clip "
+                    f"(src/shared/utils.py:28) from {rr.ref.root}, torch CPU kernels (oneDNN LSTM/conv)",
+                    lambda: rr.train_batches(batches))
+    except Exception as ex:  # fall back to the restatement, say why
+        print(f"[bench] reference not usable ({ex!r}); timing oracle/torch_port.py instead", file=sys.stderr)
+    from oracle import torch_port
+    tp = torch_port.TorchPortTrainer(seed=42)
+    return ("port", "oracle/torch_port.py (the reference's modules restated on torch.nn; torch CPU kernels)",
+            lambda: tp.train_batch(real, proto))
+
+
+def cpu_baseline_gestures_per_s(batch: int, threads: int):
+    kind, desc, step = make_cpu_stepper(batch, threads)
+    step()  # warm-up
     t0 = time.perf_counter()
-    tp.train_batch(real, proto)
+    step()
     dt = time.perf_counter() - t0
-    return batch / dt, dt
+    return batch / dt, dt, kind, desc
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     cores = os.cpu_count() or 1
-    vals = []
-    t_all = time.perf_counter()
     batch = args.ref_batch
-    from oracle import torch_port
-    torch.set_num_threads(cores)
-    tp = torch_port.TorchPortTrainer(seed=42)
-    g = torch.Generator().manual_seed(0)
-    real = torch.rand(batch, 128, 3, generator=g) * 2 - 1
-    proto = torch.rand(batch, 128, 3, generator=g) * 2 - 1
+    kind, desc, step = make_cpu_stepper(batch, cores)
     for _ in range(args.warmup):
-        tp.train_batch(real, proto)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        tp.train_batch(real, proto)
+        step()
     dt = (time.perf_counter() - t0) / args.steps
     value = batch / dt
     line = {
@@ -136,55 +151,67 @@ def run_reference(args):
         "data": "synthetic", "impl": "reference",
         "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
                                f"T=128), CPU, bounded sample of {batch} gestures per step", "batch_per_step": batch},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} gestures, torch CPU kernels (oneDNN LSTM/conv), "
-                                   f"{cores} threads; the reference is pure Python and cannot travel to this box, so "
-                                   "oracle/torch_port.py restates its modules on the same library path"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {batch} gestures, {cores} threads; {desc}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def reference_cuda_leg(dev, batches, steps, sample_batch):
-    """The reference's library path on THIS GPU (SURVEY.md 8(d) last row): oracle/torch_port.py - the reference's
-    modules restated on torch.nn - on device cuda with torch's defaults, i.e. cuDNN LSTM / conv with TF32 allowed and
-    fp32 cuBLAS (src/gan/models.py:160,163,270-291), 11 .item() syncs per batch like utils.py:84-131.  Reported next to
-    our numbers as the library-kernel bar; it is not the CPU baseline and not the driver's reference arm."""
+    """The reference's library path on THIS GPU (SURVEY.md 8(d) last row): the unmodified reference trainer + epoch
+    function on device cuda with torch's defaults, i.e. cuDNN LSTM / conv with TF32 allowed and fp32 cuBLAS
+    (src/gan/models.py:160,163,270-291), its 11 .item() syncs per batch included (utils.py:84-131); the torch.nn
+    restatement oracle/torch_port.py where the reference's files are not reachable.  Reported next to our numbers as
+    the library-kernel bar; it is not the CPU baseline and not the driver's reference arm."""
     import torch
-    from oracle import torch_port
-    out = {"what": "oracle/torch_port.py on cuda (cuDNN TF32 LSTM/conv + fp32 cuBLAS, torch defaults), eager, same step"}
+    out = {}
+    try:
+        from oracle.ref_runner import ReferenceRunner, reference_available
+        use_ref = reference_available()
+    except Exception:
+        use_ref = False
+    out["what"] = (("the unmodified reference (WordGestureGANTrainer + train_epoch_with_grad_clip)" if use_ref else
+                    "oracle/torch_port.py") + " on cuda: cuDNN TF32 LSTM/conv + fp32 cuBLAS (torch defaults), eager, same step")
     try:
         for B in batches:
-            tp = torch_port.TorchPortTrainer(seed=42, device=dev)
-            g = torch.Generator().manual_seed(0)
-            real = (torch.rand(B, 128, 3, generator=g) * 2 - 1).to(dev)
-            proto = (torch.rand(B, 128, 3, generator=g) * 2 - 1).to(dev)
+            real, proto = synthetic_batch(B)
+            real, proto = real.to(dev), proto.to(dev)
+            if use_ref:
+                rr = ReferenceRunner(dev, seed=42, batch_size=B)
+                batch_list = [{"gesture": real, "prototype": proto}]
+                step = lambda: rr.train_batches(batch_list)
+                sample = rr.sample
+            else:
+                from oracle import torch_port
+                tp = torch_port.TorchPortTrainer(seed=42, device=dev)
+                step = lambda: tp.train_batch(real, proto)
+                sample = tp.sample
             for _ in range(2):
-                tp.train_batch(real, proto)
+                step()
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
-                tp.train_batch(real, proto)
+                step()
             e1.record()
             torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1) / steps
             out[f"train_B{B}"] = {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps}
             if B == batches[-1]:
+                g = torch.Generator().manual_seed(1)
                 proto_s = (torch.rand(sample_batch, 128, 3, generator=g) * 2 - 1).to(dev)
                 z = torch.randn(sample_batch, 32, device=dev)
-                tp.G.eval()
                 for _ in range(2):
-                    tp.sample(proto_s, z)
+                    sample(proto_s, z)
                 torch.cuda.synchronize(dev)
                 e0.record()
                 for _ in range(5):
-                    tp.sample(proto_s, z)
+                    sample(proto_s, z)
                 e1.record()
                 torch.cuda.synchronize(dev)
                 out["sampling"] = {"value": sample_batch * 5 / (e0.elapsed_time(e1) / 1e3), "unit": "samples/s",
                                    "batch": sample_batch}
-            del tp
     except Exception as ex:  # a reported extra: never lose the GPU line because of it
         out["error"] = repr(ex)
     return out
@@ -211,7 +238,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
-    ap.add_argument("--sample-batch", type=int, default=74 * 128, help="gestures per generator sampling call")
+    ap.add_argument("--sample-batch", type=int, default=148 * 128,
+                    help="gestures per generator sampling call (148 tiles x 2 directions = two full waves of the persistent kernel)")
     ap.add_argument("--sample-total", type=int, default=1_000_000, help="BASELINE configs[4]: total samples over all GPUs")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying the captured CUDA graph")
@@ -392,10 +420,9 @@ def main():
         # this leg runs, and the host cores are shared by N processes
         cores = os.cpu_count() or 1
         try:
-            v, dt = cpu_port_gestures_per_s(args.cpu_sample, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1 step x {args.cpu_sample} gestures ({dt:.1f} s) after 1 warm-up, oracle/torch_port.py "
-                             f"(torch CPU kernels, {cores} threads)"}
+            v, dt, kind, desc = cpu_baseline_gestures_per_s(args.cpu_sample, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"1 step x {args.cpu_sample} gestures ({dt:.1f} s) after 1 warm-up, {cores} threads; {desc}"}
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line because of it
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex!r}"}
     ref_cuda = None

@@ -206,6 +206,27 @@ WGG_API int wgg_clip_adam_dev(wgg_ctx* ctx, float* p, float* g, float* m, float*
 WGG_API int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
                int32_t K, int act /*0 none, 1 leaky(0.2), 2 tanh*/, void* stream);
 
+/* ---- Evaluation metrics on the GPU: the kernels behind evaluate_all_metrics,
+ * src/gan/evaluation.py:297-500.  n is the number of gestures; all arrays fp32 device memory. --------------------- */
+/* out (na, nb): Euclidean distance matrix, replaces scipy cdist(a, b, 'euclidean') at evaluation.py:335,474-476;
+ * a (na, d), b (nb, d) row-major (d = 2 T for the flattened (x, y) trajectories). */
+WGG_API int wgg_eval_cdist(wgg_ctx* ctx, const float* a, int64_t na, const float* b, int64_t nb, int32_t d, float* out,
+                           void* stream);
+/* out[r] = np.sort(m, axis=1)[r, k] (the k-NN radius of evaluation.py:475,478); m (rows, cols); 0 <= k < 8. */
+WGG_API int wgg_eval_row_kth(wgg_ctx* ctx, const float* m, int64_t rows, int64_t cols, int32_t k, float* out, void* stream);
+/* out2 = {precision, recall} of evaluation.py:480-484 from rf = cdist(real, fake) (n_real, n_fake) and the two radius
+ * vectors; ws2: 2 floats of scratch. */
+WGG_API int wgg_eval_precision_recall(wgg_ctx* ctx, const float* rf, int64_t n_real, int64_t n_fake, const float* real_radii,
+                                      const float* fake_radii, float* out2, float* ws2, void* stream);
+/* out[0] = mean over gestures of mean_t sqrt((S x)_t^2 + (S y)_t^2) (evaluation.py:364-374); g (n, T, C >= 2);
+ * S (T, T): the linear operator of savgol_filter(window, poly, deriv=3) built by the host; ws: n floats. */
+WGG_API int wgg_eval_jerk(wgg_ctx* ctx, const float* g, int64_t n, int32_t T, int32_t C, const float* S, float* out, float* ws,
+                          void* stream);
+/* out4 = {velocity_corr, acceleration_corr, speed_profile_corr, time_delta_corr} of evaluation.py:162-305 for the
+ * pairs (real_i, fake_i); real, fake (n, T, C >= 3) with time in channel 2; T <= 257; ws: 8 n floats. */
+WGG_API int wgg_eval_dynamics(wgg_ctx* ctx, const float* real, const float* fake, int64_t n, int32_t T, int32_t C, float* out4,
+                              float* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -424,12 +424,16 @@ def test_resynchronised_steps_all_modes(any_mode, case, steps, B):
     tp.load_state({m: g.init_state(m) for m in MODS})
     opts = dict(G=tr.optimizer_G, E=tr.optimizer_E, D1=tr.optimizer_D1, D2=tr.optimizer_D2)
     rng = np.random.default_rng(11)
-    worst = dict(loss=0.0, d_first=0.0, ge=0.0, post=0.0)
-    # d1_loss / d2_loss are those of the LAST critic iteration and the cycle losses see critics that took five Adam
-    # steps inside the batch; the first Adam steps are sign-like (|update| = lr whatever the gradient's size), so a
-    # gradient element whose sign differs between two roundings moves a weight by 2 lr.  fp32 keeps that rare; TF32
-    # operands do not.  The losses are differences of nearly cancelling score means, judged on the scores' scale.
-    loss_tol = {"fp32": 5e-3, "tf32": 1e-1, "tf32x3": 5e-2}[mode]
+    worst = dict(loss=0.0, adv_abs=0.0, d_first=0.0, ge=0.0, post=0.0)
+    # The non-adversarial terms (feature matching, latent / reconstruction L1, KL) are compared relatively.  The
+    # adversarial ones (d1_loss / d2_loss of the LAST critic iteration, the cycles' wgan terms and the totals that
+    # contain them) are means of critic scores after up to five Adam steps taken inside the batch; the first Adam
+    # steps are sign-like (|update| = lr whatever the gradient's size), so a gradient element whose sign differs
+    # between two roundings moves a weight by 2 lr and shifts every score.  fp32 keeps that rare, TF32 operands do
+    # not: those terms are bounded ABSOLUTELY, on the scale of the scores (|D(x)| ~ 0.1).
+    loss_tol = {"fp32": 1e-3, "tf32": 2e-2, "tf32x3": 5e-3}[mode]
+    adv_tol = {"fp32": 2e-4, "tf32": 1e-2, "tf32x3": 5e-3}[mode]
+    stable = ("cycle1_feat", "cycle1_lat", "cycle2_feat", "cycle2_rec", "cycle2_kld")
     for step in range(steps):
         pre = tp.state()
         for m in MODS:
@@ -444,7 +448,10 @@ def test_resynchronised_steps_all_modes(any_mode, case, steps, B):
         ref = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise, record=ref_rec)
         losses, rec = run_batch(tr, real, proto, noise)
         for k in LOSS_KEYS:
-            worst["loss"] = max(worst["loss"], abs(losses[k] - ref[k]) / max(abs(ref[k]), 1e-2))
+            if k in stable:
+                worst["loss"] = max(worst["loss"], abs(losses[k] - ref[k]) / max(abs(ref[k]), 1e-6))
+            else:
+                worst["adv_abs"] = max(worst["adv_abs"], abs(losses[k] - ref[k]))
         for tag in ("D1_grads_0", "D2_grads_0"):
             worst["d_first"] = max(worst["d_first"], max(rel_err(v, ref_rec[tag][k]) for k, v in rec[tag].items()))
         for tag in ("G_grads", "E_grads"):
@@ -453,7 +460,7 @@ def test_resynchronised_steps_all_modes(any_mode, case, steps, B):
         for m in MODS:
             for k, prm in getattr(tr, ATTR[m]).named_parameters():
                 worst["post"] = max(worst["post"], rel_l2(to_np(prm), post[m][k]))
-        assert worst["loss"] <= loss_tol, (mode, case, step, worst)
+        assert worst["loss"] <= loss_tol and worst["adv_abs"] <= adv_tol, (mode, case, step, worst)
         assert worst["post"] <= 5e-3, (mode, case, step, worst)
         report(f"resync/{mode}/{case}", dict(steps=step + 1, **worst))
     # Gradients at these tiny batches (8 / 16 gestures) are not held to the per-mode bounds: the critic gradient is

@@ -135,6 +135,50 @@ def test_torch_port_cycles_match_reference_direct_calls(case):
             assert np.abs(sd[k].numpy() - v).max() <= 1e-10, k
 
 
+def test_eval_oracle_matches_reference(tmp_path):
+    """oracle/eval_oracle.py (the checker of the GPU metric kernels) against the reference's own
+    evaluate_all_metrics (src/gan/evaluation.py:297-500) and its time-aware correlation functions, on a slice of the
+    realistic fixture.  Needs the reference's files (/root/reference, or oracle/_ref on the GPU box)."""
+    import torch
+    from oracle import eval_oracle as E
+    from oracle.ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference sources not reachable")
+    ref = load_reference()
+    ev = ref.evaluation
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "realistic_gestures.npz"))
+    n = 64
+    real = fx["test_gesture"][:n].astype(np.float64)
+    rng = np.random.default_rng(3)
+    fake = fx["test_gesture"][n:2 * n].astype(np.float64) + 0.02 * rng.standard_normal((n, 128, 3))
+    fake[:, :, 2] = np.sort(np.clip(fake[:, :, 2], 0, 1), axis=1)
+    assert abs(E.velocity_corr(real, fake) - ev.time_aware_velocity_correlation(real, fake)) <= 1e-12
+    assert abs(E.acceleration_corr(real, fake) - ev.time_aware_acceleration_correlation(real, fake)) <= 1e-12
+    assert abs(E.speed_profile_corr(real, fake) - ev.speed_profile_correlation(real, fake)) <= 1e-12
+    assert abs(E.time_delta_corr(real, fake) - ev.time_delta_correlation(real, fake)) <= 1e-12
+    ecfg = ref.config.EvaluationConfig(fid_autoencoder_epochs=1)
+    old = ev._get_ae_cache_path
+    ev._get_ae_cache_path = lambda train_data, eval_config: tmp_path / "ae.pt"
+    try:
+        torch.manual_seed(0)
+        res = ev.evaluate_all_metrics(real.astype(np.float32), fake.astype(np.float32), eval_config=ecfg, device="cpu",
+                                      skip_dtw=True)
+    finally:
+        ev._get_ae_cache_path = old
+    r32, f32_ = real.astype(np.float32), fake.astype(np.float32)
+    assert abs(E.l2_wasserstein(r32, f32_) - res["l2_wasserstein"]) <= 1e-9
+    assert abs(E.jerk(r32) - res["jerk_real"]) <= 1e-9 * max(1.0, res["jerk_real"])
+    assert abs(E.jerk(f32_) - res["jerk_fake"]) <= 1e-9 * max(1.0, res["jerk_fake"])
+    prec, rec = E.precision_recall(r32, f32_, ecfg.precision_recall_k)
+    assert prec == res["precision"] and rec == res["recall"]
+    ae = res["_cached_real"]["autoencoder"]
+    with torch.no_grad():
+        ff = ae.encode(torch.from_numpy(f32_)).numpy()
+    fid = E.fid_from_features(res["_cached_real"]["real_features"], ff, ecfg.fid_hidden_dim)
+    assert abs(fid - res["fid"]) <= 1e-8 * max(1.0, abs(res["fid"]))
+
+
 def test_step_restructurings_are_exact():
     """The product path restructures the step without changing its numbers (train_step.py / gan_trainer.py):
     (a) ONE generator call on the stacked critic-phase batch instead of 2*n_critic calls,

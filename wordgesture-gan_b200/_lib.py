@@ -81,6 +81,11 @@ _SIG = {
                               _P, _P, _P]),
     "wgg_clip_adam_dev": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, _P, c_float, _P, _P, _P]),
     "wgg_linear": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int, _P]),
+    "wgg_eval_cdist": (c_int, [_P, _P, c_int64, _P, c_int64, c_int32, _P, _P]),
+    "wgg_eval_row_kth": (c_int, [_P, _P, c_int64, c_int64, c_int32, _P, _P]),
+    "wgg_eval_precision_recall": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "wgg_eval_jerk": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
+    "wgg_eval_dynamics": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIG)
 
