@@ -91,11 +91,11 @@ class ClockSampler:
                 "samples": len(mhz)}
 
 
-def synthetic_batch(batch, seed=0):
+def synthetic_batch(batch, seed=0, T=128):
     import torch
     g = torch.Generator().manual_seed(seed)
-    real = torch.rand(batch, 128, 3, generator=g) * 2 - 1
-    proto = torch.rand(batch, 128, 3, generator=g) * 2 - 1
+    real = torch.rand(batch, T, 3, generator=g) * 2 - 1
+    proto = torch.rand(batch, T, 3, generator=g) * 2 - 1
     return real, proto
 
 
@@ -158,7 +158,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def reference_cuda_leg(dev, batches, steps, sample_batch):
+def reference_cuda_leg(dev, batches, steps, sample_batch, model_kwargs=None):
     """The reference's library path on THIS GPU (SURVEY.md 8(d) last row): the unmodified reference trainer + epoch
     function on device cuda with torch's defaults, i.e. cuDNN LSTM / conv with TF32 allowed and fp32 cuBLAS
     (src/gan/models.py:160,163,270-291), its 11 .item() syncs per batch included (utils.py:84-131); the torch.nn
@@ -175,16 +175,18 @@ def reference_cuda_leg(dev, batches, steps, sample_batch):
                     "oracle/torch_port.py") + " on cuda: cuDNN TF32 LSTM/conv + fp32 cuBLAS (torch defaults), eager, same step")
     try:
         for B in batches:
-            real, proto = synthetic_batch(B)
+            T = (model_kwargs or {}).get("seq_length", 128)
+            real, proto = synthetic_batch(B, T=T)
             real, proto = real.to(dev), proto.to(dev)
             if use_ref:
-                rr = ReferenceRunner(dev, seed=42, batch_size=B)
+                rr = ReferenceRunner(dev, seed=42, batch_size=B, model_kwargs=model_kwargs)
                 batch_list = [{"gesture": real, "prototype": proto}]
                 step = lambda: rr.train_batches(batch_list)
                 sample = rr.sample
             else:
                 from oracle import torch_port
-                tp = torch_port.TorchPortTrainer(seed=42, device=dev)
+                from oracle.wgg_oracle import ModelCfg
+                tp = torch_port.TorchPortTrainer(seed=42, device=dev, cfg=ModelCfg(**(model_kwargs or {})))
                 step = lambda: tp.train_batch(real, proto)
                 sample = tp.sample
             for _ in range(2):
@@ -200,7 +202,7 @@ def reference_cuda_leg(dev, batches, steps, sample_batch):
             out[f"train_B{B}"] = {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps}
             if B == batches[-1]:
                 g = torch.Generator().manual_seed(1)
-                proto_s = (torch.rand(sample_batch, 128, 3, generator=g) * 2 - 1).to(dev)
+                proto_s = (torch.rand(sample_batch, T, 3, generator=g) * 2 - 1).to(dev)
                 z = torch.randn(sample_batch, 32, device=dev)
                 for _ in range(2):
                     sample(proto_s, z)
@@ -243,6 +245,8 @@ def main():
     ap.add_argument("--sample-total", type=int, default=1_000_000, help="BASELINE configs[4]: total samples over all GPUs")
     ap.add_argument("--profile-kernel", default="auto")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--hidden", type=int, default=48, help="gen_hidden_dim (BASELINE configs[3]: scaled sweep 128 ... 1024)")
+    ap.add_argument("--seq", type=int, default=128, help="seq_length (configs[3]: 256-point gestures)")
     ap.add_argument("--math", default=DEFAULT_MATH, choices=["fp32", "tf32", "tf32x3"],
                     help="tf32: LSTM/conv contractions on TF32 tensor cores (the reference CUDA path's numerics); tf32x3: conv "
                          "contractions error-compensated (every gradient within the north star's 1e-3); fp32: FMA only")
@@ -265,15 +269,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     wgg.set_math_mode(args.math)
-    mc, tc = wgg.ModelConfig(), wgg.TrainingConfig(batch_size=B)
+    T = args.seq
+    mc, tc = wgg.ModelConfig(gen_hidden_dim=args.hidden, seq_length=T), wgg.TrainingConfig(batch_size=B)
+    scaled = (args.hidden, T) != (48, 128)
     wgg.seed_everything(42)
     tr = wgg.WordGestureGANTrainer(mc, tc, dev)
     tr.use_cuda_graph = not args.no_graph
     if world > 1:
         parallel.DataParallelGAN(tr)
     g = torch.Generator().manual_seed(1000 + rank)
-    real_h = (torch.rand(B, 128, 3, generator=g) * 2 - 1).pin_memory()
-    proto_h = (torch.rand(B, 128, 3, generator=g) * 2 - 1).pin_memory()
+    real_h = (torch.rand(B, T, 3, generator=g) * 2 - 1).pin_memory()
+    proto_h = (torch.rand(B, T, 3, generator=g) * 2 - 1).pin_memory()
     real_d, proto_d = real_h.to(dev), proto_h.to(dev)
     host_batch = [{"gesture": real_h, "prototype": proto_h}]  # what a DataLoader(pin_memory=True) yields (data.py:526-533)
 
@@ -287,6 +293,12 @@ def main():
     gs = None
     if not args.no_graph:
         gs = tr._graphed_steps[(B, 1.0, args.math)]
+    # per-gesture-step FLOPs of this configuration (BASELINE.md section 3 formula; 1.340 GFLOP for the default model)
+    H = args.hidden
+    f_g = T * (160 * H * H + 16 * 34 * H + 12 * H)
+    f_d = (T / 128.0) * (245760 + 5242880 + 1572864) + 65536 + 16384 + 128
+    f_e = (T * 3 * 192 + 192 * 96 + 96 * 48 + 48 * 32 + 2 * 32 * 32) * 2
+    flop_per_gesture_step = 16 * f_g + 74 * f_d + 9 * f_e
 
     def step_eager():
         return wgg.train_batch(tr, real_d, proto_d, 1.0)
@@ -324,7 +336,7 @@ def main():
     prof_kernel = args.profile_kernel
     shares = {}
     if prof_kernel == "auto":
-        for cand in PROFILE_CANDIDATES:
+        for cand in (PROFILE_CANDIDATES if not scaled else ("gemm_kernel", "lstm_cell")):
             _lib.profile_enable(dev, cand)
             step_eager()
             shares[cand] = _lib.profile_read(dev)["ms"]
@@ -351,7 +363,10 @@ def main():
     tr.generator.eval()
     BS = args.sample_batch
     gs_ = torch.Generator().manual_seed(2000 + rank)
-    proto_s = (torch.rand(BS, 128, 3, generator=gs_) * 2 - 1).to(dev)
+    if scaled:
+        BS = min(BS, 4 * B)
+        args.sample_total = min(args.sample_total, 16 * BS)
+    proto_s = (torch.rand(BS, T, 3, generator=gs_) * 2 - 1).to(dev)
     zs = torch.randn(BS, 32, device=dev)
 
     def sample():
@@ -365,7 +380,7 @@ def main():
     # BASELINE configs[4]: sample_total samples over all GPUs (each rank its shard, no collective), in calls of BS
     per_rank = args.sample_total // world
     calls = max(1, (per_rank + BS - 1) // BS)
-    out_buf = torch.empty(min(per_rank, calls * BS), 128, 3, device=dev)
+    out_buf = torch.empty(min(per_rank, calls * BS), T, 3, device=dev)
 
     def sample_shard():
         with torch.no_grad():
@@ -412,8 +427,9 @@ def main():
             "algorithmic_bytes_per_launch": prof["bytes"] / max(prof["launches"], 1),
             "share_of_step": prof["ms"] / max(ms_prof, 1e-9), "peak_source": peaks["source"],
             "kernel_share_ms_per_step": shares,
-            "whole_step": {"achieved": FLOP_PER_GESTURE_STEP * value / world / 1e12, "unit": "TFLOP/s",
-                           "frac": FLOP_PER_GESTURE_STEP * value / world / 1e12 / peaks["tf32_tflops"]}}
+            "whole_step": {"achieved": flop_per_gesture_step * value / world / 1e12, "unit": "TFLOP/s",
+                           "frac": flop_per_gesture_step * value / world / 1e12 / peaks["tf32_tflops"],
+                           "flop_per_gesture_step": flop_per_gesture_step}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         # rank 0 at N = 1 only: under torchrun the other ranks would sit in an NCCL barrier (GPUs busy-waiting) while
@@ -427,7 +443,8 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex!r}"}
     ref_cuda = None
     if world == 1 and not args.no_reference_cuda:
-        ref_cuda = reference_cuda_leg(dev, (512, B) if B != 512 else (512,), 3, BS)
+        ref_cuda = reference_cuda_leg(dev, (512, B) if B != 512 else (512,), 3, BS,
+                                      dict(gen_hidden_dim=args.hidden, seq_length=T) if scaled else None)
     numerics = load_json("profiles/r02_numerics_by_mode.json")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -436,8 +453,11 @@ def main():
         "math_mode": args.math,
         "numerics": (numerics or {}).get(args.math, {"note": "profiles/r02_numerics_by_mode.json not found"}),
         "data": "synthetic",
-        "config": {"workload": "default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
-                               "T=128), BASELINE configs[1]", "batch_per_gpu": B, "global_batch": B * world,
+        "config": {"workload": ("default WordGesture-GAN train step (n_critic=5, TemporalDiscriminator x2, H=48 L=4 "
+                                "T=128), BASELINE configs[1]") if not scaled else
+                               (f"scaled WordGesture-GAN train step (BASELINE configs[3]): gen_hidden_dim={H}, seq_length={T}, "
+                                "n_critic=5, TemporalDiscriminator x2, L=4"),
+                   "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "launch": "eager" if gs is None else "cuda-graph (1 replay per step)",
                    "math_mode": args.math,
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
@@ -452,7 +472,7 @@ def main():
         "reference_cuda": ref_cuda,
         "clocks": clocks,
         "sampling": {"value": samples_per_s, "unit": "samples/s", "batch_per_gpu": BS,
-                     "roofline_frac": 50.6e6 * samples_per_s / world / 1e12 / peaks["tf32_tflops"],
+                     "roofline_frac": f_g * samples_per_s / world / 1e12 / peaks["tf32_tflops"],
                      "configs4": {"total_samples": per_rank * world, "per_gpu": per_rank, "ms": ms_1m,
                                   "value": per_rank * world / (ms_1m / 1e3), "unit": "samples/s",
                                   "note": "BASELINE configs[4]: every rank generates its shard in calls of batch_per_gpu "

@@ -1,0 +1,71 @@
+"""-m gpu: the scaled-model regime (BASELINE configs[3]: gen_hidden_dim 128 ... 1024, 256-point gestures).
+``gen_hidden_dim`` / ``seq_length`` are free knobs of the reference (src/shared/config.py:15,22; src/gan/models.py:114-120);
+beyond H = 64 the recurrence runs step by step on the contraction engine (csrc/lstm.cu: rec_fwd_generic / rec_bwd_generic).
+Checked against the fp64 oracles with the tolerances of tests/test_gpu_parity.py (fp32: forward 1e-4, gradients 1e-3) and
+of the TF32 modes (forward 2e-3, generator gradients 2e-3)."""
+import numpy as np
+import pytest
+import torch
+
+import wgg_b200 as wgg
+from golden_util import LOSS_KEYS, max_abs_rel, rel_l2
+from gpu_util import ATTR, DEV, grads_of, load_state, model_cfg, rand_inputs, state_of, to_np, to_t
+from oracle import torch_port
+from oracle import wgg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+H128 = O.ModelCfg(seq_length=256, gen_hidden_dim=128, gen_num_layers=2)
+H96 = O.ModelCfg(seq_length=64, gen_hidden_dim=96, gen_num_layers=3)
+H256 = O.ModelCfg(seq_length=32, gen_hidden_dim=256, gen_num_layers=1)
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def mode(request):
+    wgg.set_math_mode(request.param)
+    yield request.param
+    wgg.set_math_mode("fp32")
+
+
+@pytest.mark.parametrize("ocfg,B,seed", [(H128, 5, 0), (H96, 3, 1), (H256, 9, 2)])
+def test_generator_any_hidden_size(mode, ocfg, B, seed):
+    torch.manual_seed(seed)
+    G = wgg.Generator(model_cfg(ocfg)).to(DEV)
+    p = state_of(G)
+    _, proto, z = rand_inputs(ocfg, B, seed)
+    dy = np.random.default_rng(seed).standard_normal((B, ocfg.seq_length, 3)).astype(np.float32).astype(np.float64)
+    y_ref, stash = O.generator_fwd(p, ocfg, proto, z)
+    g_ref, dz_ref = O.generator_bwd(p, ocfg, stash, dy)
+    zt = to_t(z).requires_grad_(True)
+    y = G(to_t(proto), zt)
+    y.backward(to_t(dy))
+    with torch.no_grad():
+        y_ng = G(to_t(proto), to_t(z))
+    fwd_tol, grad_tol = (1e-4, 1e-3) if mode == "fp32" else (2e-3, 2e-3)
+    assert max_abs_rel(to_np(y), y_ref) <= fwd_tol and max_abs_rel(to_np(y_ng), y_ref) <= fwd_tol
+    worst = max(rel_l2(v, g_ref[k]) for k, v in grads_of(G).items())
+    e_dz = rel_l2(to_np(zt.grad), dz_ref)
+    print(f"{mode} H={ocfg.gen_hidden_dim} T={ocfg.seq_length}: fwd {max_abs_rel(to_np(y), y_ref):.2e} grads {worst:.2e} dz {e_dz:.2e}")
+    assert worst <= grad_tol and e_dz <= grad_tol, (worst, e_dz)
+
+
+def test_train_batch_h128_t256():
+    """One whole training batch of the scaled model (H = 128, T = 256, 4 layers, TemporalDiscriminator on 256-point
+    gestures) against the fp64 CPU restatement, fp32 mode: all 11 losses."""
+    ocfg = O.ModelCfg(seq_length=256, gen_hidden_dim=128)
+    B = 4
+    wgg.seed_everything(7)
+    tr = wgg.WordGestureGANTrainer(model_cfg(ocfg), wgg.TrainingConfig(), DEV)
+    tp = torch_port.TorchPortTrainer(seed=0, cfg=ocfg, tc=O.TrainCfg(), dtype=torch.float64)
+    tp.load_state({m: state_of(getattr(tr, ATTR[m])) for m in ("G", "E", "D1", "D2")})
+    for m in ("G", "E", "D1", "D2"):
+        getattr(tr, ATTR[m]).train()
+    rng = np.random.default_rng(3)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    real = f32(rng.uniform(-1, 1, (B, 256, 3)))
+    proto = f32(rng.uniform(-1, 1, (B, 256, 3)))
+    noise = [f32(rng.standard_normal((B, 32))) for _ in range(13)]
+    ref = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise)
+    out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise])
+    for k in LOSS_KEYS:
+        assert abs(out[k].item() - ref[k]) <= 2e-3 * max(abs(ref[k]), 1e-2), (k, out[k].item(), ref[k])

@@ -302,6 +302,131 @@ int rec_bwd_launch_t(wgg_ctx* ctx, float* gates, const float* cseq, const float*
   return WGG_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Any hidden size (the scaled-model regime, BASELINE configs[3]: H = 128 ... 1024, T = 256; config.py:22 is a free
+// knob in the reference).  W_hh no longer fits shared memory, so the recurrence runs step by step: per timestep one
+// batched (both directions) GEMM  gates[d][t] += h[d][t_prev] W_hh[d]^T  on the contraction engine (TF32 tensor cores in
+// the tensor-core math modes, fp32 FMA otherwise) followed by one cell kernel; backward mirrors it with
+// dh_rec[d] = da[d][t] W_hh[d].  Same HBM layouts and the same stash conventions as the persistent kernels above
+// (gates hold the input projection, then the activated gates, then d(pre-activation)), so every other GEMM of the
+// layer (input projection, dW_ih, dW_hh, db, dx) is shared with them.
+// ---------------------------------------------------------------------------------------------
+__global__ void lstm_cell_fwd_kernel(float* __restrict__ gates, float* __restrict__ cseq, float* __restrict__ cstate,
+                                     float* __restrict__ hseq, int T, int64_t B, int H, int step, int store) {
+  const int64_t n = 2 * B * H;
+  const int64_t TB = (int64_t)T * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % H);
+    const int64_t b = (i / H) % B;
+    const int dir = (int)(i / ((int64_t)H * B));
+    const int t = dir ? T - 1 - step : step;
+    const int tp = dir ? t + 1 : t - 1;
+    float* gp = gates + (((int64_t)dir * T + t) * B + b) * 4 * H;
+    const float ig = sigmoid_f(gp[u]);
+    const float fg = sigmoid_f(gp[H + u]);
+    const float gg = tanhf(gp[2 * H + u]);
+    const float og = sigmoid_f(gp[3 * H + u]);
+    float cprev = 0.f;
+    if (step > 0) cprev = store ? cseq[(int64_t)dir * TB * H + ((int64_t)tp * B + b) * H + u] : cstate[i];
+    const float c = fg * cprev + ig * gg;
+    hseq[((int64_t)t * B + b) * 2 * H + dir * H + u] = og * tanhf(c);
+    if (store) {
+      gp[u] = ig; gp[H + u] = fg; gp[2 * H + u] = gg; gp[3 * H + u] = og;
+      cseq[(int64_t)dir * TB * H + ((int64_t)t * B + b) * H + u] = c;
+    } else {
+      cstate[i] = c;
+    }
+  }
+}
+
+// da over the activated gates; dc carried in `dcs` [2][B][H]; dh_rec [2][B][H] is the previous launch's GEMM result
+__global__ void lstm_cell_bwd_kernel(float* __restrict__ gates, const float* __restrict__ cseq, const float* __restrict__ dh_out,
+                                     const float* __restrict__ dhrec, float* __restrict__ dcs, int T, int64_t B, int H,
+                                     int step) {
+  const int64_t n = 2 * B * H;
+  const int64_t TB = (int64_t)T * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i % H);
+    const int64_t b = (i / H) % B;
+    const int dir = (int)(i / ((int64_t)H * B));
+    const int t = dir ? T - 1 - step : step;
+    const int tp = dir ? t + 1 : t - 1;
+    float* gp = gates + (((int64_t)dir * T + t) * B + b) * 4 * H;
+    const float* cb = cseq + (int64_t)dir * TB * H;
+    const float ig = gp[u], fg = gp[H + u], gg = gp[2 * H + u], og = gp[3 * H + u];
+    const float cc = cb[((int64_t)t * B + b) * H + u];
+    const float cprev = step > 0 ? cb[((int64_t)tp * B + b) * H + u] : 0.f;
+    const float tc = tanhf(cc);
+    const float dh = dh_out[((int64_t)t * B + b) * 2 * H + dir * H + u] + (step < T - 1 ? dhrec[i] : 0.f);
+    const float d_o = dh * tc;
+    const float dct = (step < T - 1 ? dcs[i] : 0.f) + dh * og * (1.f - tc * tc);
+    gp[u] = dct * gg * ig * (1.f - ig);
+    gp[H + u] = dct * cprev * fg * (1.f - fg);
+    gp[2 * H + u] = dct * ig * (1.f - gg * gg);
+    gp[3 * H + u] = d_o * og * (1.f - og);
+    dcs[i] = dct * fg;
+  }
+}
+
+bool rec_has_persistent_kernel(int H) { return H == 8 || H == 16 || H == 32 || H == 48 || H == 64; }
+
+// scratch (floats) of the step-by-step path: forward without a stash keeps the cell state [2][B][H];
+// backward keeps dh_rec and dc [2][B][H] each
+int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
+  if (rec_has_persistent_kernel(H)) return 0;
+  return (backward ? 4 : 2) * B * (int64_t)H;
+}
+
+int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                    float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
+  const int64_t TB = (int64_t)T * B;
+  const int H4 = 4 * H;
+  for (int step = 0; step < T; ++step) {
+    if (step > 0) {
+      // direction 0 consumes h at t - 1 and writes gates at t = step; direction 1 consumes h at t + 1, writes t = T-1-step
+      const float* a0 = hseq + (int64_t)(step - 1) * B * 2 * H;
+      const float* a1 = hseq + (int64_t)(T - step) * B * 2 * H + H;
+      float* c0 = gates + (int64_t)step * B * H4;
+      float* c1 = gates + TB * H4 + (int64_t)(T - 1 - step) * B * H4;
+      GemmP p;
+      p.tag = "gemm_kernel/lstm_rec_step";
+      p.A = a0; p.M = B; p.K = H; p.sam = 2 * H; p.sak = 1;
+      p.B = lp + off_whh; p.N = H4; p.sbk = 1; p.sbn = H;
+      p.C = c0; p.scm = H4; p.scn = 1; p.accumulate = 1;
+      p.nbatch = 2; p.bsA = a1 - a0; p.bsB = dir_stride; p.bsC = c1 - c0;
+      WGG_TRY(gemm_launch(ctx, p, st));
+    }
+    lstm_cell_fwd_kernel<<<ew_blocks(2 * B * H), 256, 0, st>>>(gates, cseq, cstate, hseq, T, B, H, step, store);
+    WGG_CHECK_LAUNCH(ctx, "lstm_cell_fwd_kernel");
+  }
+  return WGG_OK;
+}
+
+int rec_bwd_generic(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
+                    int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st) {
+  const int64_t TB = (int64_t)T * B;
+  const int H4 = 4 * H;
+  float* dhrec = scratch;
+  float* dcs = scratch + 2 * B * H;
+  for (int step = T - 1; step >= 0; --step) {
+    lstm_cell_bwd_kernel<<<ew_blocks(2 * B * H), 256, 0, st>>>(gates, cseq, dh_out, dhrec, dcs, T, B, H, step);
+    WGG_CHECK_LAUNCH(ctx, "lstm_cell_bwd_kernel");
+    if (step > 0) {
+      const float* a0 = gates + (int64_t)step * B * H4;
+      const float* a1 = gates + TB * H4 + (int64_t)(T - 1 - step) * B * H4;
+      GemmP p;  // dh_rec[d] (B x H) = da[d][t] (B x 4H) * W_hh[d] (4H x H)
+      p.tag = "gemm_kernel/lstm_rec_step_bwd";
+      p.A = a0; p.M = B; p.K = H4; p.sam = H4; p.sak = 1;
+      p.B = lp + off_whh; p.N = H; p.sbk = H; p.sbn = 1;
+      p.C = dhrec; p.scm = H; p.scn = 1;
+      p.nbatch = 2; p.bsA = a1 - a0; p.bsB = dir_stride; p.bsC = B * H;
+      WGG_TRY(gemm_launch(ctx, p, st));
+    }
+  }
+  return WGG_OK;
+}
+
 #define WGG_DISPATCH_H(H, CALL)                                                                         \
   switch (H) {                                                                                          \
     case 8: { constexpr int HH = 8; return CALL; }                                                      \
@@ -315,12 +440,16 @@ int rec_bwd_launch_t(wgg_ctx* ctx, float* gates, const float* cseq, const float*
   }
 
 int rec_fwd_launch(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh,
-                   float* hseq, float* cseq, int T, int64_t B, int store, cudaStream_t st) {
+                   float* hseq, float* cseq, float* scratch, int T, int64_t B, int store, cudaStream_t st) {
+  if (!rec_has_persistent_kernel(H))
+    return rec_fwd_generic(ctx, H, gates, lp, dir_stride, off_whh, hseq, cseq, scratch, T, B, store, st);
   WGG_DISPATCH_H(H, (rec_fwd_launch_t<HH>(ctx, gates, lp, dir_stride, off_whh, hseq, cseq, T, B, store, st)));
 }
 
 int rec_bwd_launch(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
-                   int64_t off_whh, const float* dh_out, int T, int64_t B, cudaStream_t st) {
+                   int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st) {
+  if (!rec_has_persistent_kernel(H))
+    return rec_bwd_generic(ctx, H, gates, cseq, lp, dir_stride, off_whh, dh_out, scratch, T, B, st);
   WGG_DISPATCH_H(H, (rec_bwd_launch_t<HH>(ctx, gates, cseq, lp, dir_stride, off_whh, dh_out, T, B, st)));
 }
 
@@ -373,14 +502,14 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   if (gen_layout(cfg, &g) != WGG_OK) return -1;
   const int64_t TB = (int64_t)g.T * B;
   if (!backward) {  // no-grad forward: x0 + two hseq + gates (FMA path) or the tcgen05 path's buffers
-    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H);
+    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0);
     const int64_t tcw = generator_tc_workspace_floats(cfg, B);
     return simt > tcw ? simt : tcw;
   }
   const int64_t maxI = g.I0 > 2 * g.H ? g.I0 : 2 * g.H;
   // dpre | dh | dx | split-K partials | column-sum scratch | (tcgen05 path: its own backward workspace)
   return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2) +
-         generator_tc_bwd_workspace_floats(cfg, B);
+         generator_tc_bwd_workspace_floats(cfg, B) + rec_generic_scratch_floats(g.H, B, 1);
 }
 
 extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
@@ -403,6 +532,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   StashView sv;
   float* hbuf[2] = {nullptr, nullptr};
   float* gates_ws = nullptr;
+  float* rec_scratch = nullptr;  // cell state of the step-by-step recurrence when nothing is stashed
   if (stash) {
     stash_view(g, B, stash, &sv);
   } else {
@@ -412,6 +542,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     hbuf[0] = ws + TB * g.I0;
     hbuf[1] = hbuf[0] + TB * 2 * g.H;
     gates_ws = hbuf[1] + TB * 2 * g.H;
+    rec_scratch = gates_ws + TB * 8 * g.H;
   }
   build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sv.x0, g.T, B, g.C, g.pd, g.Z);
   WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
@@ -431,7 +562,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
     p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
     WGG_TRY(gemm_launch(ctx, p, st));
-    WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, g.T, B, stash ? 1 : 0, st));
+    WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, rec_scratch, g.T, B, stash ? 1 : 0, st));
     in = hout;
   }
   GemmP p;  // out[b][t][:] = tanh(h[t][b][:] * Wo^T + bo), batched over t to transpose (t,b)->(b,t)
@@ -466,6 +597,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   float* part = dx + TB * maxI;
   float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
   float* tcws = csws + colsum_ws_floats(H4, 2);
+  float* rec_scratch = tcws + generator_tc_bwd_workspace_floats(cfg, B);  // dh_rec | dc of the step-by-step recurrence
 
   if (tcp) {
     // head and LSTM stack backward run entirely on the tcgen05 path (fused head, BPTT, dx and dW/db kernels)
@@ -498,7 +630,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     float* dlp = dparams + g.layer_off[l];
     float* da = sv.gates[l];
     const float* in = l == 0 ? sv.x0 : sv.hseq[l - 1];
-    WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, g.T, B, st));
+    WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, st));
     {
       GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
       p.tag = "gemm_kernel/lstm_dWih";

@@ -25,6 +25,8 @@
 // fully coalesced 16-byte stores (lane = row).
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace tc {
 
 constexpr int TM = 128;   // samples per CTA tile (UMMA M)
@@ -36,8 +38,11 @@ constexpr int CHUNK_BYTES_W = (N4 / 8) * 128;  // 3072: one 16-byte K chunk of t
 constexpr int SB_CHUNKS = 8;                   // K chunks per ring stage (32 floats)
 constexpr int SB_BYTES = SB_CHUNKS * CHUNK_BYTES_A;  // 16384
 constexpr int NSTAGE = 5;
-constexpr int NTHREADS = 576;                  // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
-constexpr int EPI_WARPS = 16;
+// warp 0 producer, warp 1 MMA issuer, then 4 * (12 / NCH) epilogue warps: every epilogue thread owns one gesture row and
+// NCH K-chunks (4 * NCH hidden units) of it.  NCH = 3: 16 epilogue warps (576 threads); NCH = 2: 24 epilogue warps (832
+// threads, 6 per scheduler) - more warps to hide the MUFU / tcgen05.ld latencies of the gate math behind each other.
+__host__ __device__ constexpr int fwd_epi_warps(int nch) { return 4 * (KH_CHUNKS / nch); }
+__host__ __device__ constexpr int fwd_threads(int nch) { return 64 + 32 * fwd_epi_warps(nch); }
 constexpr int ACC_COLS = N4;                   // TMEM columns per accumulator buffer
 constexpr int TMEM_COLS = 512;
 
@@ -124,8 +129,8 @@ __global__ void __launch_bounds__(256) build_x0_tc_kernel(const float* __restric
 //   h_rm : [T][B][2H] row-major, un-rounded fp32 (operand of the weight-gradient GEMMs and of the output head)
 constexpr int GC_CHUNKS = HID + HID / 4;  // 60
 
-template <int KXC, int STASH>
-__global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
+template <int KXC, int STASH, int NCH>
+__global__ void __launch_bounds__(fwd_threads(NCH), 1) lstm_tc_fwd_kernel(const float* __restrict__ xin,
                                                                   const float* __restrict__ wimg, int64_t img_stride,
                                                                   float* __restrict__ hout, int T, int ntiles,
                                                                   float* __restrict__ gc, float* __restrict__ h_rm,
@@ -133,6 +138,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   constexpr int NSB = (KXC + SB_CHUNKS - 1) / SB_CHUNKS;
   constexpr int WX_BYTES = KXC * CHUNK_BYTES_W;
   constexpr int WH_BYTES = KH_CHUNKS * CHUNK_BYTES_W;
+  constexpr int NTHREADS = fwd_threads(NCH), EPI_WARPS = fwd_epi_warps(NCH);
+  constexpr int NPART = KH_CHUNKS / NCH;  // column parts of the accumulator (one per group of four epilogue warps)
+  static_assert(KH_CHUNKS % NCH == 0 && NPART % 2 == 0, "h chunks are handed over in NCH phases of NPART / 2 MMAs");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_wx = smem;
   uint8_t* s_wh = s_wx + WX_BYTES;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
   auto BAR_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
   auto BAR_ACC_FULL = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
   auto BAR_ACC_EMPTY = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
-  auto BAR_H = [&](int ph) { return bar0 + 8u * (2 * NSTAGE + 4 + ph); };  // h chunks {ph, 3+ph, 6+ph, 9+ph} written
+  auto BAR_H = [&](int ph) { return bar0 + 8u * (2 * NSTAGE + 4 + ph); };  // h chunks {ph + NCH j} written
 
   // ---- one-time setup -------------------------------------------------------------------------
   {
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       mbar_init(BAR_ACC_FULL(b), 1);
       mbar_init(BAR_ACC_EMPTY(b), EPI_WARPS);
     }
-    for (int ph = 0; ph < 3; ++ph) mbar_init(BAR_H(ph), EPI_WARPS);
+    for (int ph = 0; ph < NCH; ++ph) mbar_init(BAR_H(ph), EPI_WARPS);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
     bool ok = true;
     const uint32_t wx = smem_u32(s_wx), wh = smem_u32(s_wh), hs = smem_u32(s_h);
     const uint64_t bdx0 = make_desc(wx, CHUNK_BYTES_W, 128);
-    const uint64_t adh3 = make_desc(hs, 3 * CHUNK_BYTES_A, 128), bdh3 = make_desc(wh, 3 * CHUNK_BYTES_W, 128);  // chunk pairs (c, c+3)
+    const uint64_t adh3 = make_desc(hs, NCH * CHUNK_BYTES_A, 128), bdh3 = make_desc(wh, NCH * CHUNK_BYTES_W, 128);  // chunk pairs (c, c+NCH)
     constexpr uint64_t kAStep = (2 * CHUNK_BYTES_A) >> 4, kWStep = (2 * CHUNK_BYTES_W) >> 4;
     for (int step = 0; step < T && ok; ++step) {
       const int b = step & 1;
@@ -238,18 +246,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       }
       if (!ok) break;
       // recurrent part, pipelined against the gate math of the previous step: every epilogue warp writes its h chunks
-      // in three phases; as soon as phase ph is complete the two MMAs over K chunks (ph, 3+ph) and (6+ph, 9+ph) are
-      // issued (the pair's second chunk is addressed through the descriptor's leading-byte-offset), so only the last
-      // third of W_hh h is exposed after the gate math
+      // in NCH phases; as soon as phase ph is complete the MMAs over the K-chunk pairs (ph + 2 NCH g, ph + 2 NCH g + NCH)
+      // are issued (the pair's second chunk is addressed through the descriptor's leading-byte-offset), so only the
+      // last 1 / NCH of W_hh h is exposed after the gate math
       if (step > 0) {
-        for (int ph = 0; ph < 3; ++ph) {
+        for (int ph = 0; ph < NCH; ++ph) {
           if (!mbar_wait(BAR_H(ph), (uint32_t)((step - 1) & 1), s_abort, gerr, 4)) { ok = false; break; }
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2)
-              mma_tf32_ss(tacc, adh3 + (uint64_t)(((6 * g2 + ph) * CHUNK_BYTES_A) >> 4),
-                          bdh3 + (uint64_t)(((6 * g2 + ph) * CHUNK_BYTES_W) >> 4), kIdesc, 1u);
+            for (int g2 = 0; g2 < NPART / 2; ++g2)
+              mma_tf32_ss(tacc, adh3 + (uint64_t)(((2 * NCH * g2 + ph) * CHUNK_BYTES_A) >> 4),
+                          bdh3 + (uint64_t)(((2 * NCH * g2 + ph) * CHUNK_BYTES_W) >> 4), kIdesc, 1u);
           }
           __syncwarp();
         }
@@ -259,47 +267,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
       __syncwarp();
     }
   } else {
-    // ===== epilogue: 16 warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 (12 hidden units each) =====
-    // Four warps per scheduler keep the MUFU pipe (5 EX2 + 2 RCP per cell) and the FMA pipe busy at the same time.
+    // ===== epilogue: EPI_WARPS warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 (UPT hidden units each) =====
+    // Four or six warps per scheduler keep the MUFU pipe (5 EX2 + 2 RCP per cell) and the FMA pipe busy at the same time.
+    constexpr int UPT = 4 * NCH;  // hidden units per thread
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    float c[12];
+    float c[UPT];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) c[i] = 0.f;
+    for (int i = 0; i < UPT; ++i) c[i] = 0.f;
     float4* hs4 = reinterpret_cast<float4*>(s_h);
     for (int step = 0; step < T; ++step) {
       const int t = dir ? T - 1 - step : step;
       const int b = step & 1;
       if (!mbar_wait(BAR_ACC_FULL(b), (uint32_t)((step >> 1) & 1), s_abort, gerr, 5)) break;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + part * 48);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + part * 4 * UPT);
       float4* hg4 = reinterpret_cast<float4*>(hout) +
                     (((int64_t)t * ntiles + tile) * (2 * KH_CHUNKS) + dir * KH_CHUNKS) * (TM) + row;
       float4* gc4 = nullptr;
       if (STASH)
         gc4 = reinterpret_cast<float4*>(gc) + ((((int64_t)dir * T + t) * ntiles + tile) * GC_CHUNKS) * TM + row;
-      float v[48];
-      {
-        float v0[16], v1[16], v2[16];
-        tmem_ld16(taddr, v0);
-        tmem_ld16(taddr + 16, v1);
-        tmem_ld16(taddr + 32, v2);
+      float v[16 * NCH];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] = v0[i]; v[16 + i] = v1[i]; v[32 + i] = v2[i]; }
+      for (int q = 0; q < NCH; ++q) {
+        float vq[16];
+        tmem_ld16(taddr + 16 * q, vq);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * q + i] = vq[i];
       }
       // accumulator fully read by this warp: hand the buffer back to the MMA issuer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_ACC_EMPTY(b));
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const int chunk = part * 3 + ch;              // K chunk (4 hidden units) of this direction's h
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int chunk = part * NCH + ch;            // K chunk (4 hidden units) of this direction's h
         float hv[4], hraw[4];
 #pragma unroll
         for (int uu = 0; uu < 4; ++uu) {
-          const int ul = ch * 4 + uu;                 // unit index inside this thread's 12
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (part * 12 + ul) * 4);
+          const int ul = ch * 4 + uu;                 // unit index inside this thread's UPT
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (part * UPT + ul) * 4);
           // 5 gate non-linearities with 5 EX2 + 2 RCP (instead of 5 + 5): the sigmoids / tanh of a unit share their
           // reciprocals.  sigma(x) = 1/(1+E), E = 2^(-x log2 e); tanh(x) = (1-E2)/(1+E2), E2 = 2^(-2x log2 e).  The
           // scale and the (pre-scaled) bias are one FMA; exponents are capped at 40 so that the product of three
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_tc_fwd_kernel(const float* _
           const float og = r2 * pc;
           hraw[uu] = fmaf(-Ec, r2, r2);               // = og * tanh(c)
           hv[uu] = rna_tf32(hraw[uu]);
-          if (STASH) gc4[(int64_t)(part * 12 + ul) * TM] = make_float4(ig, fg, gg, og);
+          if (STASH) gc4[(int64_t)(part * UPT + ul) * TM] = make_float4(ig, fg, gg, og);
         }
         const float4 q = make_float4(hv[0], hv[1], hv[2], hv[3]);
         hs4[chunk * TM + row] = q;                    // next step's A operand
@@ -1064,12 +1072,18 @@ bool tc_plan(const wgg_model_cfg* c, int64_t B, TcPlan* p) {
   return true;
 }
 
-template <int KXC, int STASH>
+// development knob (read once): WGG_FWD_NCH = 2 | 3 chooses the no-grad forward's epilogue split (24 | 16 warps)
+int fwd_nch() {
+  static const int v = [] { const char* e = getenv("WGG_FWD_NCH"); return e ? atoi(e) : 3; }();
+  return v;
+}
+
+template <int KXC, int STASH, int NCH = 3>
 int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_stride, float* hout, int T, int ntiles,
                  int64_t B, float* gc, float* h_rm, cudaStream_t st) {
   constexpr size_t smem = (size_t)KXC * tc::CHUNK_BYTES_W + tc::KH_CHUNKS * tc::CHUNK_BYTES_W + tc::NSTAGE * tc::SB_BYTES +
                           tc::KH_CHUNKS * tc::CHUNK_BYTES_A + tc::N4 * 4 + 20 * 8 + 16;
-  if (!wgg_smem_ok(ctx, tc::lstm_tc_fwd_kernel<KXC, STASH>, smem))
+  if (!wgg_smem_ok(ctx, tc::lstm_tc_fwd_kernel<KXC, STASH, NCH>, smem))
     return wgg_fail(ctx, WGG_ECUDA, "lstm_tc_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)ntiles, 2);
   // algorithmic FLOPs: 2 dirs x T x B x 2 x 192 x (K_x + 48); bytes: x in (both dirs read it) + h out, and for the
@@ -1077,7 +1091,7 @@ int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_s
   ProfScope prof(ctx, "lstm_tc_fwd_kernel", st, 2.0 * T * (double)B * 2.0 * tc::N4 * (KXC * 4 + tc::HID),
                  (double)T * B * 4.0 * (2.0 * KXC * 4 + 96) +
                      (STASH ? (double)T * B * (2.0 * tc::GC_CHUNKS * 16 + (h_rm ? 96 * 4.0 : 0.0)) : 0.0));
-  tc::lstm_tc_fwd_kernel<KXC, STASH><<<grid, tc::NTHREADS, smem, st>>>(xin, img, img_stride, hout, T, ntiles, gc, h_rm, B,
+  tc::lstm_tc_fwd_kernel<KXC, STASH, NCH><<<grid, tc::fwd_threads(NCH), smem, st>>>(xin, img, img_stride, hout, T, ntiles, gc, h_rm, B,
                                                                          ctx->async_err);
   WGG_CHECK_LAUNCH(ctx, "lstm_tc_fwd_kernel");
   return WGG_OK;
@@ -1154,10 +1168,12 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
     const float* img = ws + p.img_off[l];
     if (l == 0) {
       if (stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else WGG_TRY((launch_layer<kKX0 / 4, 0>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      else if (fwd_nch() == 2) WGG_TRY((launch_layer<kKX0 / 4, 0, 2>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      else WGG_TRY((launch_layer<kKX0 / 4, 0, 3>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     } else {
       if (stash) WGG_TRY((launch_layer<24, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else WGG_TRY((launch_layer<24, 0>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      else if (fwd_nch() == 2) WGG_TRY((launch_layer<24, 0, 2>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
+      else WGG_TRY((launch_layer<24, 0, 3>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     }
     in = hout;
   }
