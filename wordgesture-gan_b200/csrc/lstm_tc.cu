@@ -25,8 +25,6 @@
 // fully coalesced 16-byte stores (lane = row).
 #include "tc_common.cuh"
 
-#include <stdlib.h>
-
 namespace tc {
 
 constexpr int TM = 128;   // samples per CTA tile (UMMA M)
@@ -39,8 +37,9 @@ constexpr int SB_CHUNKS = 8;                   // K chunks per ring stage (32 fl
 constexpr int SB_BYTES = SB_CHUNKS * CHUNK_BYTES_A;  // 16384
 constexpr int NSTAGE = 5;
 // warp 0 producer, warp 1 MMA issuer, then 4 * (12 / NCH) epilogue warps: every epilogue thread owns one gesture row and
-// NCH K-chunks (4 * NCH hidden units) of it.  NCH = 3: 16 epilogue warps (576 threads); NCH = 2: 24 epilogue warps (832
-// threads, 6 per scheduler) - more warps to hide the MUFU / tcgen05.ld latencies of the gate math behind each other.
+// NCH K-chunks (4 * NCH hidden units) of it.  NCH = 3: 16 epilogue warps (576 threads) is what ships; NCH = 2 (24 epilogue
+// warps, 6 per scheduler) was measured SLOWER on B200 (6.91 vs 6.47 ms for a 40 960-gesture call): the gate math is
+// bound by the MUFU / MIO instruction stream, not by latency hiding.
 __host__ __device__ constexpr int fwd_epi_warps(int nch) { return 4 * (KH_CHUNKS / nch); }
 __host__ __device__ constexpr int fwd_threads(int nch) { return 64 + 32 * fwd_epi_warps(nch); }
 constexpr int ACC_COLS = N4;                   // TMEM columns per accumulator buffer
@@ -1072,12 +1071,6 @@ bool tc_plan(const wgg_model_cfg* c, int64_t B, TcPlan* p) {
   return true;
 }
 
-// development knob (read once): WGG_FWD_NCH = 2 | 3 chooses the no-grad forward's epilogue split (24 | 16 warps)
-int fwd_nch() {
-  static const int v = [] { const char* e = getenv("WGG_FWD_NCH"); return e ? atoi(e) : 3; }();
-  return v;
-}
-
 template <int KXC, int STASH, int NCH = 3>
 int launch_layer(wgg_ctx* ctx, const float* xin, const float* img, int64_t img_stride, float* hout, int T, int ntiles,
                  int64_t B, float* gc, float* h_rm, cudaStream_t st) {
@@ -1168,11 +1161,9 @@ int generator_forward_tc(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* pa
     const float* img = ws + p.img_off[l];
     if (l == 0) {
       if (stash) WGG_TRY((launch_layer<kKX0 / 4, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else if (fwd_nch() == 2) WGG_TRY((launch_layer<kKX0 / 4, 0, 2>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
       else WGG_TRY((launch_layer<kKX0 / 4, 0, 3>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     } else {
       if (stash) WGG_TRY((launch_layer<24, 1>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, gcl, hrm, st)));
-      else if (fwd_nch() == 2) WGG_TRY((launch_layer<24, 0, 2>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
       else WGG_TRY((launch_layer<24, 0, 3>(ctx, in, img, p.img_floats[l], hout, p.T, p.ntiles, B, nullptr, nullptr, st)));
     }
     in = hout;
