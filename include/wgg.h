@@ -227,6 +227,21 @@ WGG_API int wgg_eval_jerk(wgg_ctx* ctx, const float* g, int64_t n, int32_t T, in
 WGG_API int wgg_eval_dynamics(wgg_ctx* ctx, const float* real, const float* fake, int64_t n, int32_t T, int32_t C, float* out4,
                               float* ws, void* stream);
 
+/* ---- Word prototypes / minimum-jerk trajectories on the GPU ---------------------------------
+ * keys (n, maxk, 2) float64 key centres of each word (QWERTYKeyboard._get_key_positions, src/shared/keyboard.py:679-686),
+ * nkeys (n) int32 -> out (n, T, 3) fp32 rows (x, y, t).  One thread block per word, float64 arithmetic like numpy. */
+/* QWERTYKeyboard.get_word_prototype, keyboard.py:710-765: straight segments between key centres sampled at uniform arc
+ * length, t = linspace(0, 1); maxk <= 64. */
+WGG_API int wgg_word_prototypes(wgg_ctx* ctx, const double* keys, const int32_t* nkeys, int64_t n, int32_t maxk, int32_t T,
+                                float* out, void* stream);
+/* generate_minimum_jerk_trajectory, keyboard.py:389-514 (C2 quintic-Hermite path through the via-points, 1000-point fine
+ * trajectory, arc-length resampling, time from the inverted s(tau)).  The reference's random draws are inputs:
+ * key_noise (n, maxk, 2) = N(0, offset_std) for the interior keys (row i - 1 for key i, :426-429), mid_noise (n, maxk) =
+ * N(0, offset_std / 2) per segment (:440-442); both NULL for offset_std = 0.  maxk <= 32. */
+WGG_API int wgg_minimum_jerk(wgg_ctx* ctx, const double* keys, const int32_t* nkeys, int64_t n, int32_t maxk,
+                             const double* key_noise, const double* mid_noise, int include_midpoints, int32_t T, float* out,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,23 @@ if rank == 0:
     first = max(((grads_dp[t] - grads_1[t]).norm() / grads_1[t].norm()).item() for t in ("D1_grads_0", "D2_grads_0"))
     okay = first < (1e-5 if mode == "fp32" else 5e-3) and worst < (1e-3 if mode == "fp32" else 2e-2)
     print("DP_PARITY", "OK" if okay else "FAIL", "first-step", first, "worst", worst)
+# ---- the PRODUCT path's own noise: no injection; every rank seeds alike, train_batch draws the global tensors and
+# keeps its rows (parallel.randn_rank_rows) - the N-rank step must equal the 1-rank step on the global batch seeded
+# the same way
+tr_dp2 = make(); dp2 = parallel.DataParallelGAN(tr_dp2)
+tr_2 = make() if rank == 0 else None
+grads_dp.clear(); grads_1.clear()
+torch.cuda.manual_seed(77)
+wgg.train_batch(tr_dp2, dp2.shard(real), dp2.shard(proto), 1.0, on_step=hook_dp)
+if rank == 0:
+    torch.cuda.manual_seed(77)
+    wgg.train_batch(tr_2, real, proto, 1.0, on_step=hook_1)
+torch.cuda.synchronize(); dist.barrier()
+if rank == 0:
+    first = max(((grads_dp[t] - grads_1[t]).norm() / grads_1[t].norm()).item() for t in ("D1_grads_0", "D2_grads_0"))
+    worst = max(((grads_dp[t] - grads_1[t]).norm() / grads_1[t].norm()).item() for t in grads_1)
+    okay = first < (1e-5 if mode == "fp32" else 5e-3) and worst < (1e-3 if mode == "fp32" else 2e-2)
+    print("DP_PRODUCT_NOISE_PARITY", "OK" if okay else "FAIL", "first-step", first, "worst", worst)
 # replicas identical?
 for name in ("generator", "discriminator_1"):
     f = getattr(tr_dp, name).flat_params(); ref = f.clone(); dist.broadcast(ref, src=0)

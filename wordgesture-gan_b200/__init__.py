@@ -9,7 +9,7 @@ from .gan_losses import (FeatureMatchingLoss, KLDivergenceLoss, LatentEncodingLo
                          WassersteinLoss, feature_matching_from_stash)
 from .gan_modules import Discriminator, Generator, TemporalDiscriminator, VariationalEncoder
 from .gan_trainer import WordGestureGANTrainer
-from . import eval_metrics
+from . import eval_metrics, keyboard_gpu
 from .graph_step import GraphedTrainStep
 from .optim import FusedClipAdam
 from .resident_loader import DeviceResidentLoader
@@ -21,5 +21,5 @@ __all__ = [
     "Generator", "VariationalEncoder", "Discriminator", "TemporalDiscriminator",
     "WassersteinLoss", "FeatureMatchingLoss", "ReconstructionLoss", "LatentEncodingLoss", "KLDivergenceLoss",
     "feature_matching_from_stash", "WordGestureGANTrainer", "FusedClipAdam", "GraphedTrainStep", "DeviceResidentLoader", "run_training",
-    "set_math_mode", "get_math_mode", "eval_metrics", "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
+    "set_math_mode", "get_math_mode", "eval_metrics", "keyboard_gpu", "seed_everything", "log", "train_batch", "train_epoch_with_grad_clip",
 ]

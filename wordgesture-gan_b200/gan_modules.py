@@ -33,6 +33,7 @@ class FlatModule(nn.Module):
         super().__init__()
         self._flat = None
         self._flat_buf = None
+        self._gflat = None  # persistent flat gradient buffer; every parameter's .grad is a view into it
 
     def _flatten(self) -> None:
         with torch.no_grad():
@@ -86,10 +87,48 @@ class FlatModule(nn.Module):
             self._flatten()
         return self._flat_buf
 
+    # ---- gradients -------------------------------------------------------------------------------
+    # The backward kernels ACCUMULATE (+=) into one flat gradient buffer per module (include/wgg.h), and that buffer
+    # is what clip + Adam and the data-parallel all-reduce consume.  Handing autograd a fresh zero-filled tensor per
+    # backward call would make it add the pieces into .grad with one elementwise launch per parameter (130 adds + 83
+    # fills per training step); instead the module owns ONE persistent buffer, every parameter's .grad is a view of it,
+    # the autograd Functions accumulate straight into it and return None for the parameter inputs.  zero_grad() is one
+    # fill.  (Consequence: torch.autograd.grad(..., parameters) does not see these gradients - use .backward().)
+    def grad_buffer(self) -> torch.Tensor:
+        """The flat gradient buffer, with every parameter's .grad attached as a view of it.  A parameter whose .grad is
+        None (never written, or reset by zero_grad(set_to_none=True)) gets its slice zeroed; a foreign .grad tensor
+        (assigned by the user) is copied in - so accumulation semantics are those of autograd."""
+        flat = self.flat_params()
+        if self._gflat is None or self._gflat.device != flat.device or self._gflat.numel() != flat.numel():
+            self._gflat = torch.zeros_like(flat)
+        off = 0
+        base = self._gflat.data_ptr()
+        with torch.no_grad():
+            for p in self.parameters():
+                n = p.numel()
+                g = p.grad
+                if g is None:
+                    self._gflat[off:off + n].zero_()
+                    p.grad = self._gflat[off:off + n].view(p.shape)
+                elif g.data_ptr() != base + 4 * off or g.dtype != torch.float32:
+                    self._gflat[off:off + n].copy_(g.reshape(-1))
+                    p.grad = self._gflat[off:off + n].view(p.shape)
+                off += n
+        return self._gflat
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """One fill of the flat gradient buffer; the .grad views stay attached (set_to_none is accepted for signature
+        compatibility: a zeroed gradient and an absent one are the same to every consumer in this package)."""
+        if self._gflat is None:
+            return super().zero_grad(set_to_none)
+        g = self.grad_buffer()
+        g.zero_()
+
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         self._flat = None
         self._flat_buf = None
+        self._gflat = None
         self._flatten()
         return out
 
@@ -99,7 +138,7 @@ class FlatModule(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_flat", "_flat_buf"):
+            if k in ("_flat", "_flat_buf", "_gflat"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -232,7 +271,7 @@ class _GeneratorFn(torch.autograd.Function):
         if ctx.math_mode != _lib.get_math_mode():
             raise _lib.WggError("math mode changed between a generator forward and its backward")
         B = ctx.B
-        dflat = torch.zeros_like(flat)
+        dflat = module.grad_buffer()   # accumulated in place; the parameter inputs get None (see FlatModule.grad_buffer)
         dz = torch.empty(B, module.config.latent_dim, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
         nws = lib.wgg_generator_workspace_floats(cfg, B, 1)
         ws = _lib.workspace(dev, nws)
@@ -240,18 +279,7 @@ class _GeneratorFn(torch.autograd.Function):
                                               _lib.ptr(dout.contiguous()), _lib.ptr(dflat), _lib.ptr(dz),
                                               _lib.ptr(ws), ws.numel(), _lib.stream(dev)), c)
         ctx.stash = None
-        grads = _split_like(dflat, _param_list(module))
-        return (None, None, dz) + tuple(grads)
-
-
-def _split_like(flat: torch.Tensor, params: List[nn.Parameter]):
-    out = []
-    off = 0
-    for p in params:
-        n = p.numel()
-        out.append(flat[off:off + n].view(p.shape))
-        off += n
-    return out
+        return (None, None, dz) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 class Generator(FlatModule):
@@ -312,7 +340,7 @@ class _EncoderFn(torch.autograd.Function):
         cfg = _lib.c_cfg(module.config)
         flat = module.flat_params()
         B = x.shape[0]
-        dflat = torch.zeros_like(flat)
+        dflat = module.grad_buffer()
         dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
         nws = lib.wgg_encoder_workspace_floats(cfg, B)
         ws = _lib.workspace(dev, nws)
@@ -321,7 +349,7 @@ class _EncoderFn(torch.autograd.Function):
                                             _lib.ptr(stash), _lib.ptr(cont(dz)), _lib.ptr(cont(dmu)),
                                             _lib.ptr(cont(dlv)), _lib.ptr(dflat), _lib.ptr(dx), _lib.ptr(ws),
                                             ws.numel(), _lib.stream(dev)), c)
-        return (None, dx, None) + tuple(_split_like(dflat, _param_list(module)))
+        return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 class VariationalEncoder(FlatModule):
@@ -415,7 +443,7 @@ class _DiscFn(torch.autograd.Function):
         if dscore is None and dstash is None:
             return (None,) * n_in
         want_params = any(ctx.needs_input_grad[3:]) and not _lib.SKIP_DISC_WEIGHT_GRADS
-        dflat = torch.zeros_like(flat) if want_params else None
+        dflat = module.grad_buffer() if want_params else None
         dx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
         nws = lib.wgg_disc_workspace_floats(cfg, B)
         ws = _lib.workspace(dev, nws)
@@ -423,8 +451,7 @@ class _DiscFn(torch.autograd.Function):
         _lib.check(lib.wgg_disc_backward(c, cfg, _lib.ptr(flat), _lib.ptr(sn), _lib.ptr(x), B, _lib.ptr(stash),
                                          _lib.ptr(cont(dscore)), _lib.ptr(cont(dstash)), _lib.ptr(dflat), _lib.ptr(dx),
                                          _lib.ptr(ws), ws.numel(), _lib.stream(dev)), c)
-        pg = tuple(_split_like(dflat, _param_list(module))) if want_params else (None,) * (n_in - 3)
-        return (None, None, dx) + pg
+        return (None, None, dx) + (None,) * (n_in - 3)
 
 
 class _FeatureViewFn(torch.autograd.Function):

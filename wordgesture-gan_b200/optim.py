@@ -96,6 +96,10 @@ class FusedClipAdam(torch.optim.Optimizer):
             }
             off += n
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """One fill of the module's flat gradient buffer (FlatModule.zero_grad) instead of dropping every .grad."""
+        self.module.zero_grad(set_to_none)
+
     def flat_grad(self) -> torch.Tensor:
         """Gradients as ONE contiguous tensor in parameter order.  The backward kernels already write one flat
         buffer per module (each .grad is a view of it); otherwise the pieces are packed here and .grad re-aliased."""
@@ -126,14 +130,16 @@ class FusedClipAdam(torch.optim.Optimizer):
 
     # ---- step ---------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, closure=None, max_norm: Optional[float] = None):
+    def step(self, closure=None, max_norm: Optional[float] = None, grads_already_reduced: bool = False):
         """One fused update.  ``max_norm`` > 0 applies clip_grad_norm_ semantics (L2, coefficient
-        min(1, max_norm / (norm + 1e-6))) inside the same pass."""
+        min(1, max_norm / (norm + 1e-6))) inside the same pass.  Under data parallelism the flat gradient bucket is
+        mean-all-reduced first, unless the caller already did (``grads_already_reduced``: train_batch reduces the
+        generator's and the encoder's buckets with ONE collective)."""
         loss = closure() if closure is not None else None
         group = self.param_groups[0]
         flat = self._ensure_state()
         g = self.flat_grad()
-        if self.process_group is not None and self.world_size > 1:
+        if self.process_group is not None and self.world_size > 1 and not grads_already_reduced:
             from .parallel import allreduce_mean_
             allreduce_mean_(g, self.process_group, self.world_size)
         dev = flat.device

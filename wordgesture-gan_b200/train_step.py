@@ -154,8 +154,18 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
     if on_step is not None:
         on_step("G_grads", trainer.optimizer_G)
         on_step("E_grads", trainer.optimizer_E)
-    trainer.optimizer_G.step(max_norm=max_norm)
-    trainer.optimizer_E.step(max_norm=max_norm)
+    reduced = False
+    if world > 1 and trainer.optimizer_G.process_group is not None:
+        # one collective for the generator's and the encoder's gradient buckets (G || E = 301 523 floats, 1.2 MB)
+        from .parallel import allreduce_mean_
+        g_g, g_e = trainer.optimizer_G.flat_grad(), trainer.optimizer_E.flat_grad()
+        joint = torch.cat([g_g, g_e])
+        allreduce_mean_(joint, trainer.optimizer_G.process_group, world)
+        g_g.copy_(joint[:g_g.numel()])
+        g_e.copy_(joint[g_g.numel():])
+        reduced = True
+    trainer.optimizer_G.step(max_norm=max_norm, grads_already_reduced=reduced)
+    trainer.optimizer_E.step(max_norm=max_norm, grads_already_reduced=reduced)
     for d in (d1, d2):
         for k, v in d.items():
             out[k] = v.detach()
