@@ -275,8 +275,7 @@ def main():
     wgg.seed_everything(42)
     tr = wgg.WordGestureGANTrainer(mc, tc, dev)
     tr.use_cuda_graph = not args.no_graph
-    if world > 1:
-        parallel.DataParallelGAN(tr)
+    dp = parallel.DataParallelGAN(tr) if world > 1 else None
     g = torch.Generator().manual_seed(1000 + rank)
     real_h = (torch.rand(B, T, 3, generator=g) * 2 - 1).pin_memory()
     proto_h = (torch.rand(B, T, 3, generator=g) * 2 - 1).pin_memory()
@@ -460,6 +459,8 @@ def main():
                    "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "launch": "eager" if gs is None else "cuda-graph (1 replay per step)",
                    "math_mode": args.math,
+                   "gradient_exchange": None if dp is None else ("one-shot peer-memory reduce (wgg_p2p_allreduce_avg), 12 per step"
+                                                                  if dp.p2p else "NCCL all-reduce (AVG), 11 per step"),
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * 128 * 3 * 4,
                 "d2h_bytes_per_step": 16 + 4, "ms_per_step": ms_e2e / args.steps,

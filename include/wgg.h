@@ -206,6 +206,18 @@ WGG_API int wgg_clip_adam_dev(wgg_ctx* ctx, float* p, float* g, float* m, float*
 WGG_API int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
                int32_t K, int act /*0 none, 1 leaky(0.2), 2 tanh*/, void* stream);
 
+/* ---- Data-parallel gradient exchange over peer memory (no counterpart in the single-GPU reference) ----
+ * One-shot mean all-reduce of a flat gradient bucket: every rank reads all peers' buckets over NVLink and sums them in
+ * rank order.  peer_grads / peer_flags: DEVICE arrays of `world` pointers - entry r is rank r's bucket (n floats) and
+ * flag block (wgg_p2p_flag_words() uint32, zero-initialised) as mapped into THIS process (CUDA IPC; entry `rank` is
+ * the local memory).  avg: n floats of local scratch; local_grad: the local bucket (receives the mean);
+ * state: 4 zero-initialised uint32 of local device memory private to this bucket.  n % 4 == 0, world <= 16.
+ * Every rank must issue the same sequence of calls per bucket; asynchronous on `stream`, CUDA-graph capturable
+ * (the epoch lives in `state`); a peer that never arrives ends the wait after ~2 s and sets wgg_async_error. */
+WGG_API int64_t wgg_p2p_flag_words(void);
+WGG_API int wgg_p2p_allreduce_avg(wgg_ctx* ctx, const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
+                                  int64_t n, float* avg, float* local_grad, uint32_t* state, void* stream);
+
 /* ---- Evaluation metrics on the GPU: the kernels behind evaluate_all_metrics,
  * src/gan/evaluation.py:297-500.  n is the number of gestures; all arrays fp32 device memory. --------------------- */
 /* out (na, nb): Euclidean distance matrix, replaces scipy cdist(a, b, 'euclidean') at evaluation.py:335,474-476;

@@ -21,6 +21,22 @@ g = torch.Generator().manual_seed(7)
 real = (torch.rand(G, 128, 3, generator=g) * 2 - 1).to(dev); proto = (torch.rand(G, 128, 3, generator=g) * 2 - 1).to(dev)
 tr_dp = make(); dp = parallel.DataParallelGAN(tr_dp)
 tr_1 = make() if rank == 0 else None
+print(f"[rank {rank}] gradient exchange: {'peer-memory one-shot reduce' if dp.p2p else 'NCCL all-reduce'}", flush=True)
+if dp.p2p:
+    # the one-shot reduce on known data: bucket_r = (r + 1) * pattern  ->  mean = (W + 1) / 2 * pattern, bit-exact here
+    for opt in (tr_dp.optimizer_D1, tr_dp.optimizer_G):
+        gbuf = opt.module.grad_buffer()
+        pattern = torch.arange(gbuf.numel(), device=dev, dtype=torch.float32) % 1024 - 512.0
+        for rep in range(3):
+            gbuf.copy_((rank + 1 + rep) * pattern)
+            opt.p2p.allreduce_mean_()
+            torch.cuda.synchronize()
+            expect = (sum(r + 1 + rep for r in range(world)) / world) * pattern
+            assert torch.equal(gbuf, expect), (rank, rep, (gbuf - expect).abs().max().item())
+        gbuf.zero_()
+    from wgg_b200 import _lib
+    assert _lib.async_error(dev) == 0
+    if rank == 0: print("P2P_REDUCE_EXACT OK")
 from wgg_b200.train_step import n_noise_draws
 nd = n_noise_draws(tc)
 grads_dp, grads_1 = {}, {}

@@ -86,6 +86,8 @@ _SIG = {
     "wgg_eval_precision_recall": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "wgg_eval_jerk": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "wgg_eval_dynamics": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "wgg_p2p_flag_words": (c_int64, []),
+    "wgg_p2p_allreduce_avg": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P]),
     "wgg_word_prototypes": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "wgg_minimum_jerk": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int, c_int32, _P, _P]),
 }

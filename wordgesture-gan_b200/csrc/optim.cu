@@ -109,7 +109,133 @@ __global__ void __launch_bounds__(256) clip_adam_dev_kernel(float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One-shot mean all-reduce of a flat gradient bucket over peer memory (NVLink 5 / NVSwitch), for the data-parallel
+// step: the buckets are small (276 KB per critic, 1.2 MB for G || E), so the collective is pure
+// latency - every rank simply READS all W peers' buckets over NVLink and sums them in rank order (the same order on
+// every rank: replicas stay bit-identical), instead of going through NCCL's ring / tree protocol.
+// Each rank's bucket and flag block live in memory the peers have mapped (CUDA IPC); flags[0][r] / flags[1][r] are
+// written by rank r (entry: "my gradients are complete", exit: "I have finished reading yours").  The launch:
+//   entry barrier (system-scope release / acquire flags) -> avg = (1/W) sum_r grad_r into a LOCAL buffer ->
+//   local grid barrier -> exit barrier -> local gradient bucket := avg   (what clip + Adam then consume).
+// The epoch lives in device memory, so the launch is CUDA-graph capturable; every spin is bounded (~2 s) and reports
+// through the context's async error word instead of hanging the GPU.  grid <= 32 CTAs: all co-resident.
+// ---------------------------------------------------------------------------------------------
+constexpr int kP2PMaxWorld = 16;
+constexpr int kP2PBlocks = 32;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// spins until *p >= target (acquire at the given scope); false (and the error word set) after ~2 s
+template <bool SYS>
+__device__ bool spin_until(const uint32_t* p, uint32_t target, int* gerr, int code) {
+  const long long t0 = clock64();
+  while (true) {
+    const uint32_t v = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+    if ((int32_t)(v - target) >= 0) return true;
+    if (clock64() - t0 > 4000000000ll) {
+      atomicCAS(gerr, 0, code);
+      return false;
+    }
+  }
+}
+
+// state[0] = epoch of the last completed launch, state[1] = monotonic CTA counter, state[2] / state[3] = gates
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(const float* const* __restrict__ peer_grads,
+                                                            uint32_t* const* __restrict__ peer_flags, int rank, int world,
+                                                            int64_t n4, float* __restrict__ avg, float* __restrict__ local_grad,
+                                                            uint32_t* __restrict__ state, int* __restrict__ gerr) {
+  const int tid = threadIdx.x;
+  const uint32_t e = state[0] + 1u;
+  uint32_t* my_flags = peer_flags[rank];
+  // ---- entry barrier: every rank's bucket is complete ----
+  if (blockIdx.x == 0) {
+    if (tid < world) {
+      __threadfence_system();
+      st_release_sys(peer_flags[tid] + rank, e);
+      spin_until<true>(my_flags + tid, e, gerr, 61);
+    }
+    __syncthreads();
+    if (tid == 0) st_release_gpu(state + 2, e);
+  } else {
+    if (tid == 0) spin_until<false>(state + 2, e, gerr, 62);
+    __syncthreads();
+  }
+  // ---- avg = mean over ranks, summed in rank order (identical on every rank) ----
+  const float inv = 1.f / (float)world;
+  float4* avg4 = reinterpret_cast<float4*>(avg);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n4; i += (int64_t)gridDim.x * 256) {
+    float4 a = ld_sys_f4(reinterpret_cast<const float4*>(peer_grads[0]) + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 b = ld_sys_f4(reinterpret_cast<const float4*>(peer_grads[r]) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    avg4[i] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+  // ---- local grid barrier, then exit barrier: nobody overwrites a bucket a peer may still be reading ----
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(state + 1, 1u);
+  }
+  if (blockIdx.x == 0) {
+    if (tid == 0) spin_until<false>(state + 1, e * gridDim.x, gerr, 63);
+    __syncthreads();
+    if (tid < world) {
+      st_release_sys(peer_flags[tid] + kP2PMaxWorld + rank, e);
+      spin_until<true>(my_flags + kP2PMaxWorld + tid, e, gerr, 64);
+    }
+    __syncthreads();
+    if (tid == 0) st_release_gpu(state + 3, e);
+  } else {
+    if (tid == 0) spin_until<false>(state + 3, e, gerr, 65);
+    __syncthreads();
+  }
+  // ---- the local bucket becomes the averaged gradient ----
+  float4* g4 = reinterpret_cast<float4*>(local_grad);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n4; i += (int64_t)gridDim.x * 256) g4[i] = avg4[i];
+  if (blockIdx.x == 0 && tid == 0) state[0] = e;  // every CTA has read the old epoch: they all passed the grid barrier
+}
+
 }  // namespace
+
+extern "C" int64_t wgg_p2p_flag_words(void) { return 2 * kP2PMaxWorld; }
+
+extern "C" int wgg_p2p_allreduce_avg(wgg_ctx* ctx, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
+                                     int world, int64_t n, float* avg, float* local_grad, uint32_t* state, void* stream) {
+  if (!ctx || !peer_grads || !peer_flags || !avg || !local_grad || !state || world < 1 || world > kP2PMaxWorld || rank < 0 ||
+      rank >= world || n <= 0 || (n & 3))
+    return wgg_fail(ctx, WGG_EINVAL, "wgg_p2p_allreduce_avg: bad argument (n must be a multiple of 4, world <= 16)%s");
+  const int64_t n4 = n / 4;
+  // the grid size is part of the barrier arithmetic (state[1] counts CTAs): a function of n only
+  int grid = (int)cdiv64(n4, 256 * 4);
+  if (grid > kP2PBlocks) grid = kP2PBlocks;
+  if (grid < 1) grid = 1;
+  p2p_allreduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(peer_grads, peer_flags, rank, world, n4, avg, local_grad, state,
+                                                              ctx->async_err);
+  WGG_CHECK_LAUNCH(ctx, "p2p_allreduce_kernel");
+  return WGG_OK;
+}
 
 extern "C" int wgg_clip_adam_dev(wgg_ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev,
                                  float beta1, float beta2, float eps, int* step_dev, float max_norm,

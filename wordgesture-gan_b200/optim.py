@@ -30,6 +30,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         self._lr_cached = None
         self.process_group = None  # set by parallel.DataParallelGAN: all-reduce (mean) grads before clipping
         self.world_size = 1
+        self.p2p = None            # parallel.P2PBucket: one-shot peer-memory reduce instead of the NCCL collective
         self.last_grad_norm = None  # device scalar: pre-clip global L2 norm of the last step
 
     # ---- flat views ---------------------------------------------------------------------------
@@ -140,8 +141,11 @@ class FusedClipAdam(torch.optim.Optimizer):
         flat = self._ensure_state()
         g = self.flat_grad()
         if self.process_group is not None and self.world_size > 1 and not grads_already_reduced:
-            from .parallel import allreduce_mean_
-            allreduce_mean_(g, self.process_group, self.world_size)
+            if self.p2p is not None and g.data_ptr() == self.p2p.shared.data_ptr():
+                self.p2p.allreduce_mean_()
+            else:
+                from .parallel import allreduce_mean_
+                allreduce_mean_(g, self.process_group, self.world_size)
         dev = flat.device
         c = _lib.ctx(dev)
         lib = _lib.lib()

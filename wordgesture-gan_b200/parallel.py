@@ -63,6 +63,81 @@ def allreduce_mean_(flat: torch.Tensor, group=None, world_size: Optional[int] = 
     return flat
 
 
+class P2PBucket:
+    """A module's flat gradient bucket placed in memory that every rank of the node has mapped (CUDA IPC), reduced by
+    the one-shot peer-memory kernel ``wgg_p2p_allreduce_avg`` (csrc/optim.cu) instead of an NCCL collective: the
+    buckets of this model are 0.3 - 1.2 MB, so the exchange is pure latency; reading the peers' buckets directly over
+    NVLink and summing them in rank order takes one small launch and keeps replicas bit-identical.
+
+    Setup (once): each rank allocates [bucket | flag block] as one torch tensor, shares its storage through torch's
+    CUDA-IPC reducer (``UntypedStorage._share_cuda_``), all-gathers the handles over the process group and maps the
+    peers' storages; the module's persistent gradient buffer (FlatModule._gflat) is redirected INTO the shared
+    tensor, so the backward kernels write where the peers read - no staging copy."""
+
+    def __init__(self, module, group, rank: int, world: int):
+        from . import _lib
+        flat = module.flat_params()
+        dev = flat.device
+        self.n = flat.numel()
+        self.npad = (self.n + 3) // 4 * 4
+        words = int(_lib.lib().wgg_p2p_flag_words())
+        self.rank, self.world = rank, world
+        self.shared = torch.zeros(self.npad + words, dtype=torch.float32, device=dev)
+        # Every rank takes part in every collective below whatever happens locally, and failure is decided
+        # collectively - a rank that fell back to NCCL while its peers spin on flags would hang the job.
+        try:
+            info = self.shared.untyped_storage()._share_cuda_()
+            meta = (tuple(info), self.shared.storage_offset(), self.shared.numel())
+        except Exception as ex:
+            meta = repr(ex)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, meta, group=group)
+        bad = [m for m in gathered if isinstance(m, str)]
+        self.peer_tensors = []
+        err = bad[0] if bad else None
+        if err is None:
+            try:
+                for r, (inf, off, numel) in enumerate(gathered):
+                    if r == rank:
+                        self.peer_tensors.append(self.shared)
+                        continue
+                    storage = torch.UntypedStorage._new_shared_cuda(*inf)
+                    t = torch.empty(0, dtype=torch.float32, device=storage.device).set_(storage, off, (numel,))
+                    self.peer_tensors.append(t)
+            except Exception as ex:
+                err = repr(ex)
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError(f"peer mapping failed on at least one rank ({err or 'on a peer'})")
+        grads = [t.data_ptr() for t in self.peer_tensors]
+        flags = [t.data_ptr() + 4 * self.npad for t in self.peer_tensors]
+        self.grad_ptrs = torch.tensor(grads, dtype=torch.int64, device=dev)
+        self.flag_ptrs = torch.tensor(flags, dtype=torch.int64, device=dev)
+        self.avg = torch.zeros(self.npad, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.module = module
+        # the module's gradient buffer now lives in the shared tensor (padding floats stay zero)
+        module._gflat = self.shared[:self.n]
+        module.grad_buffer()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)   # every rank has mapped every bucket before the first reduce
+
+    def allreduce_mean_(self):
+        """In-place mean of the module's gradient bucket over all ranks (asynchronous, graph-capturable)."""
+        from . import _lib
+        dev = self.shared.device
+        c = _lib.ctx(dev)
+        _lib.check(_lib.lib().wgg_p2p_allreduce_avg(c, self.grad_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank,
+                                                    self.world, self.npad, self.avg.data_ptr(), self.shared.data_ptr(),
+                                                    self.state.data_ptr(), _lib.stream(dev)), c)
+
+
+def p2p_enabled() -> bool:
+    import os
+    return os.environ.get("WGG_P2P", "1") != "0"
+
+
 class DataParallelGAN:
     """Attaches a process group to a trainer's four fused optimisers: each ``step`` first mean-all-reduces the
     module's flat gradient bucket.  Also broadcasts rank 0's state so replicas start identical."""
@@ -84,6 +159,20 @@ class DataParallelGAN:
         trainer.optimizer_D2.process_group = self.group_d2
         trainer._dp = self  # train_step.train_batch draws the step's noise for the global batch and slices by rank
         self.sync_state()
+        # Gradient exchange: one-shot peer-memory reduce (P2PBucket) when every rank sits on a CUDA device of this
+        # node; NCCL all-reduce otherwise (CPU / gloo tests, WGG_P2P=0, or if the IPC mapping fails).
+        self.p2p = False
+        dev = trainer.generator.flat_params().device
+        if dev.type == "cuda" and self.world_size > 1 and p2p_enabled():
+            try:
+                for opt in (trainer.optimizer_G, trainer.optimizer_E, trainer.optimizer_D1, trainer.optimizer_D2):
+                    opt.p2p = P2PBucket(opt.module, self.group, self.rank, self.world_size)
+                self.p2p = True
+            except RuntimeError as ex:   # raised on EVERY rank (collective decision): keep the NCCL path; say why
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({ex!r}); using NCCL all-reduce")
+                for opt in (trainer.optimizer_G, trainer.optimizer_E, trainer.optimizer_D1, trainer.optimizer_D2):
+                    opt.p2p = None
 
     def sync_state(self):
         for mod in (self.trainer.generator, self.trainer.encoder, self.trainer.discriminator_1,

@@ -155,8 +155,9 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
         on_step("G_grads", trainer.optimizer_G)
         on_step("E_grads", trainer.optimizer_E)
     reduced = False
-    if world > 1 and trainer.optimizer_G.process_group is not None:
-        # one collective for the generator's and the encoder's gradient buckets (G || E = 301 523 floats, 1.2 MB)
+    if world > 1 and trainer.optimizer_G.process_group is not None and trainer.optimizer_G.p2p is None:
+        # NCCL path: one collective for the generator's and the encoder's gradient buckets (G || E = 301 523 floats,
+        # 1.2 MB); the peer-memory path reduces each bucket with its own one-shot launch inside step()
         from .parallel import allreduce_mean_
         g_g, g_e = trainer.optimizer_G.flat_grad(), trainer.optimizer_E.flat_grad()
         joint = torch.cat([g_g, g_e])
