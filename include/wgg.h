@@ -215,6 +215,12 @@ WGG_API int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float
  * Every rank must issue the same sequence of calls per bucket; asynchronous on `stream`, CUDA-graph capturable
  * (the epoch lives in `state`); a peer that never arrives ends the wait after ~2 s and sets wgg_async_error. */
 WGG_API int64_t wgg_p2p_flag_words(void);
+/* Shared bucket memory: wgg_p2p_alloc = cudaMalloc (zero-filled) on ctx's device + its 64-byte CUDA IPC handle (send it
+ * to the peers by any means); wgg_p2p_open maps a peer's handle into THIS rank's device address space (NVLink peer
+ * access enabled on demand); wgg_p2p_close(ptr, imported) unmaps an imported bucket / frees an own one. */
+WGG_API int wgg_p2p_alloc(wgg_ctx* ctx, int64_t bytes, void** ptr, unsigned char* handle64);
+WGG_API int wgg_p2p_open(wgg_ctx* ctx, const unsigned char* handle64, void** ptr);
+WGG_API int wgg_p2p_close(wgg_ctx* ctx, void* ptr, int imported);
 WGG_API int wgg_p2p_allreduce_avg(wgg_ctx* ctx, const float* const* peer_grads, uint32_t* const* peer_flags, int rank, int world,
                                   int64_t n, float* avg, float* local_grad, uint32_t* state, void* stream);
 

@@ -87,6 +87,9 @@ _SIG = {
     "wgg_eval_jerk": (c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P]),
     "wgg_eval_dynamics": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
     "wgg_p2p_flag_words": (c_int64, []),
+    "wgg_p2p_alloc": (c_int, [_P, c_int64, POINTER(c_void_p), ctypes.c_char_p]),
+    "wgg_p2p_open": (c_int, [_P, ctypes.c_char_p, POINTER(c_void_p)]),
+    "wgg_p2p_close": (c_int, [_P, _P, c_int]),
     "wgg_p2p_allreduce_avg": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P]),
     "wgg_word_prototypes": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "wgg_minimum_jerk": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int, c_int32, _P, _P]),

@@ -221,6 +221,46 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const float* const* 
 
 extern "C" int64_t wgg_p2p_flag_words(void) { return 2 * kP2PMaxWorld; }
 
+// Shared buckets are plain cudaMalloc allocations of the library (an IPC handle names a whole allocation, and the
+// importing side must map it with ITS OWN device current so that the mapping lands in the address space its kernels
+// run in; cudaIpcMemLazyEnablePeerAccess then enables NVLink peer access to the owner's device).
+extern "C" int wgg_p2p_alloc(wgg_ctx* ctx, int64_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ctx || !ptr || !handle64 || bytes <= 0) return WGG_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return wgg_fail(ctx, WGG_ECUDA, "wgg_p2p_alloc: cudaSetDevice%s");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    return wgg_fail(ctx, WGG_ECUDA, "wgg_p2p_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return WGG_OK;
+}
+
+extern "C" int wgg_p2p_open(wgg_ctx* ctx, const unsigned char* handle64, void** ptr) {
+  if (!ctx || !ptr || !handle64) return WGG_EINVAL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return wgg_fail(ctx, WGG_ECUDA, "wgg_p2p_open: cudaSetDevice%s");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return wgg_fail(ctx, WGG_ECUDA, "wgg_p2p_open: %s", cudaGetErrorString(e));
+  *ptr = p;
+  return WGG_OK;
+}
+
+extern "C" int wgg_p2p_close(wgg_ctx* ctx, void* ptr, int imported) {
+  if (!ctx || !ptr) return WGG_EINVAL;
+  cudaSetDevice(ctx->device);
+  const cudaError_t e = imported ? cudaIpcCloseMemHandle(ptr) : cudaFree(ptr);
+  return e == cudaSuccess ? WGG_OK : wgg_fail(ctx, WGG_ECUDA, "wgg_p2p_close: %s", cudaGetErrorString(e));
+}
+
 extern "C" int wgg_p2p_allreduce_avg(wgg_ctx* ctx, const float* const* peer_grads, uint32_t* const* peer_flags, int rank,
                                      int world, int64_t n, float* avg, float* local_grad, uint32_t* state, void* stream) {
   if (!ctx || !peer_grads || !peer_flags || !avg || !local_grad || !state || world < 1 || world > kP2PMaxWorld || rank < 0 ||

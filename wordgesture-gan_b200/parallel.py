@@ -63,61 +63,71 @@ def allreduce_mean_(flat: torch.Tensor, group=None, world_size: Optional[int] = 
     return flat
 
 
+class _DeviceMemory:
+    """Raw device memory exposed to torch through __cuda_array_interface__ (torch.as_tensor aliases it, no copy)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
 class P2PBucket:
     """A module's flat gradient bucket placed in memory that every rank of the node has mapped (CUDA IPC), reduced by
     the one-shot peer-memory kernel ``wgg_p2p_allreduce_avg`` (csrc/optim.cu) instead of an NCCL collective: the
     buckets of this model are 0.3 - 1.2 MB, so the exchange is pure latency; reading the peers' buckets directly over
     NVLink and summing them in rank order takes one small launch and keeps replicas bit-identical.
 
-    Setup (once): each rank allocates [bucket | flag block] as one torch tensor, shares its storage through torch's
-    CUDA-IPC reducer (``UntypedStorage._share_cuda_``), all-gathers the handles over the process group and maps the
-    peers' storages; the module's persistent gradient buffer (FlatModule._gflat) is redirected INTO the shared
-    tensor, so the backward kernels write where the peers read - no staging copy."""
+    Setup (once): each rank allocates [bucket | flag block] with ``wgg_p2p_alloc`` (cudaMalloc + IPC handle),
+    all-gathers the 64-byte handles over the process group and maps the peers' allocations with ``wgg_p2p_open``; the
+    module's persistent gradient buffer (FlatModule._gflat) is redirected INTO the shared allocation, so the backward
+    kernels write where the peers read - no staging copy."""
 
     def __init__(self, module, group, rank: int, world: int):
+        import ctypes
         from . import _lib
+        lib = _lib.lib()
         flat = module.flat_params()
         dev = flat.device
+        c = _lib.ctx(dev)
         self.n = flat.numel()
         self.npad = (self.n + 3) // 4 * 4
-        words = int(_lib.lib().wgg_p2p_flag_words())
+        words = int(lib.wgg_p2p_flag_words())
+        total = self.npad + words
         self.rank, self.world = rank, world
-        self.shared = torch.zeros(self.npad + words, dtype=torch.float32, device=dev)
         # Every rank takes part in every collective below whatever happens locally, and failure is decided
         # collectively - a rank that fell back to NCCL while its peers spin on flags would hang the job.
-        try:
-            info = self.shared.untyped_storage()._share_cuda_()
-            meta = (tuple(info), self.shared.storage_offset(), self.shared.numel())
-        except Exception as ex:
-            meta = repr(ex)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        rc = lib.wgg_p2p_alloc(c, 4 * total, ctypes.byref(own), handle)
+        meta = bytes(handle.raw) if rc == 0 else f"wgg_p2p_alloc failed: {lib.wgg_last_error(c).decode()}"
         gathered = [None] * world
         dist.all_gather_object(gathered, meta, group=group)
-        bad = [m for m in gathered if isinstance(m, str)]
-        self.peer_tensors = []
-        err = bad[0] if bad else None
+        err = next((m for m in gathered if isinstance(m, str)), None)
+        ptrs = []
         if err is None:
-            try:
-                for r, (inf, off, numel) in enumerate(gathered):
-                    if r == rank:
-                        self.peer_tensors.append(self.shared)
-                        continue
-                    storage = torch.UntypedStorage._new_shared_cuda(*inf)
-                    t = torch.empty(0, dtype=torch.float32, device=storage.device).set_(storage, off, (numel,))
-                    self.peer_tensors.append(t)
-            except Exception as ex:
-                err = repr(ex)
+            for r, h in enumerate(gathered):
+                if r == rank:
+                    ptrs.append(own.value)
+                    continue
+                p = ctypes.c_void_p()
+                if lib.wgg_p2p_open(c, h, ctypes.byref(p)) != 0:
+                    err = f"wgg_p2p_open(rank {r}) failed: {lib.wgg_last_error(c).decode()}"
+                    break
+                ptrs.append(p.value)
+        torch.cuda.set_device(dev)
         ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
             raise RuntimeError(f"peer mapping failed on at least one rank ({err or 'on a peer'})")
-        grads = [t.data_ptr() for t in self.peer_tensors]
-        flags = [t.data_ptr() + 4 * self.npad for t in self.peer_tensors]
-        self.grad_ptrs = torch.tensor(grads, dtype=torch.int64, device=dev)
-        self.flag_ptrs = torch.tensor(flags, dtype=torch.int64, device=dev)
+        self._mem = _DeviceMemory(own.value, total)            # keeps the interface object alive
+        self.shared = torch.as_tensor(self._mem, device=dev)   # aliases the cudaMalloc'ed bucket + flag block
+        assert self.shared.data_ptr() == own.value and self.shared.numel() == total
+        self.peer_ptrs = ptrs
+        self.grad_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.flag_ptrs = torch.tensor([p + 4 * self.npad for p in ptrs], dtype=torch.int64, device=dev)
         self.avg = torch.zeros(self.npad, dtype=torch.float32, device=dev)
         self.state = torch.zeros(4, dtype=torch.int32, device=dev)
         self.module = module
-        # the module's gradient buffer now lives in the shared tensor (padding floats stay zero)
+        # the module's gradient buffer now lives in the shared allocation (padding floats stay zero)
         module._gflat = self.shared[:self.n]
         module.grad_buffer()
         torch.cuda.synchronize(dev)
