@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 N=${1:-2}
 for mode in ${MODES:-tf32}; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/dp_parity.py $mode > gpurun_out/r02_dp_parity_$mode.log 2>&1; echo "dp_parity $mode exit $?"
+  WGG_P2P=${P2P_PARITY:-1} timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/dp_parity.py $mode > gpurun_out/r02_dp_parity_$mode.log 2>&1; echo "dp_parity $mode exit $?"
   grep "DP_\|replicas\|P2P\|exchange\|Error\|error" gpurun_out/r02_dp_parity_$mode.log | head -12
 done
 for p2p in 1 0; do
