@@ -1,20 +1,13 @@
 #!/bin/bash
-# bench (N=1 default flags) + reference arm + one `ncu --set full` capture of the dominant kernel
-set -u
+# what the driver runs at round end, in one call: build check, pytest -m gpu, smoke(), bench (ours + reference arm)
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"
-python - <<'PY'
+timeout 1500 python -m pytest tests/ -m gpu -q -x --tb=short > gpurun_out/r02_gpu_all.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r02_gpu_all.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/r02_smoke.log
+S0=$SECONDS; timeout 900 python bench.py --impl reference --gpus 1 --steps 8 --warmup 3 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "reference arm rc=$? wall $((SECONDS-S0)) s"
+S0=$SECONDS; timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo "bench rc=$? wall $((SECONDS-S0)) s"
+tail -n 3 gpurun_out/r02_gpu_all.log; tail -n 2 gpurun_out/r02_smoke.log
+python -c "
 import json
-try:
-    d = json.loads(open("gpurun_out/bench.log").read().strip().splitlines()[-1])
-    print("value", round(d["value"]), d["unit"], "ms/step", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]), "launches", d["gpu_launches"])
-    r = d["roofline"]; print("roofline", {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "frac", "traffic", "share_of_step")}, "tensor", r["tensor"]["frac"], "shares", r["kernel_share_ms_per_step"])
-    print("cpu", d["cpu_baseline"], "sampling", round(d["sampling"]["value"]), "clocks", d["clocks"])
-except Exception as e:
-    print("bench parse failed", e)
-PY
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>> gpurun_out/bench.err; tail -c 400 gpurun_out/bench_ref.log
-python scripts/one_step.py 4096 tf32 1 > gpurun_out/plain.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_fwd_kernel -s 8 -c 3 -f -o gpurun_out/r01_lstm_tc_fwd \
-  python scripts/one_step.py 4096 tf32 1 > gpurun_out/ncu_full.log 2>&1
-echo "ncu exit $?"; tail -1 gpurun_out/plain.log
+d=json.loads(open('gpurun_out/r02_bench_final.json').read().strip().splitlines()[-1]); r=json.loads(open('gpurun_out/r02_bench_reference_arm.json').read().strip().splitlines()[-1])
+print('ours', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['frac'], 'traffic', d['roofline']['traffic'], 'ref', r['value'], 'ratio e2e', d['e2e']['value']/r['value'])
+print('refcuda', d['reference_cuda']); print('cpu', d['cpu_baseline']); print('clocks', d['clocks'])"

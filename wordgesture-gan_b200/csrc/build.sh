@@ -6,7 +6,7 @@ PKG="$(dirname "$HERE")"
 ROOT="$(dirname "$PKG")"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$PKG/libwgg_sm100.so"
-SRCS=(api.cu gemm.cu ew.cu lstm.cu lstm_tc.cu conv_tc.cu encoder.cu disc.cu loss.cu optim.cu eval.cu keyboard.cu)
+SRCS=(api.cu gemm.cu gemm_tc.cu ew.cu lstm.cu lstm_tc.cu conv_tc.cu encoder.cu disc.cu loss.cu optim.cu eval.cu keyboard.cu)
 cd "$HERE"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --shared \

@@ -149,6 +149,9 @@ struct GemmP {
 };
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
+// tcgen05 / TMA engine for large "NT" contractions in the tensor-core math modes (gemm_tc.cu); gemm_launch routes to it
+bool gemm_tc_usable(const wgg_ctx* ctx, const GemmP& p);
+int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
 // workspace (floats) a split-K GEMM of this shape may need
 int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch);
 int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch);
