@@ -31,6 +31,10 @@ def log(msg: str) -> None:
     print(msg, flush=True)
 
 
+# A/B switch for the two-call critic-phase generator (see train_batch); on unless WGG_SPLIT_GEN=0
+_SPLIT_DEFAULT = __import__("os").environ.get("WGG_SPLIT_GEN", "1") != "0"
+
+
 def n_noise_draws(training_config) -> int:
     return 2 * training_config.n_critic + 3
 
@@ -83,6 +87,17 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
     # for the persistent recurrent kernel, a fifth of the launches.
     n = tc.n_critic
     fakes_1 = fakes_2 = None
+    # The D1 chain and the D2 chain are independent (different networks, optimisers and fake batches; they only read
+    # `real`), so D2's steps are issued on a second stream: its many small launches (Linear layers, spectral norm,
+    # reductions) overlap D1's bandwidth-bound conv kernels and vice versa.  Inside a captured CUDA graph the two
+    # chains become parallel branches.  Results are identical to the sequential order.
+    # Eager execution is bound by host launch issue, where a second stream only adds synchronisation calls, so the
+    # side stream is used under graph capture (and by the capture's warm-up) only.
+    main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+    par = getattr(trainer, "parallel_critics", "auto")
+    use_side = main is not None and n > 0 and (par is True or (par == "auto" and torch.cuda.is_current_stream_capturing()))
+    side = _critic_side_stream(trainer, dev) if use_side else None
+    capturing = main is not None and torch.cuda.is_current_stream_capturing()
     if n > 0:
         zs, epss = [], []
         for _ in range(n):
@@ -95,25 +110,29 @@ def train_batch(trainer, real_gesture: torch.Tensor, prototype: torch.Tensor, ma
                 z0, mu, log_var = trainer.encoder(real_gesture, epss[0])
                 std = torch.exp(0.5 * log_var)
                 z_enc = torch.cat([z0] + [torch.addcmul(mu, e, std) for e in epss[1:]], 0)
-                proto_rep = prototype.repeat(2 * n, 1, 1)
-                fake_all = trainer.generator(proto_rep, torch.cat(zs + [z_enc], 0))
             else:
                 z_enc, _, _ = trainer.encoder(real_gesture, epss[0])
-                fake_all = trainer.generator(prototype.repeat(2, 1, 1), torch.cat([zs[0], z_enc], 0))
-        fakes_1 = fake_all[:n * B].view(n, B, *fake_all.shape[1:])
-        fakes_2 = fake_all[n * B:].view(n, B, *fake_all.shape[1:])
-    # The D1 chain and the D2 chain are independent (different networks, optimisers and fake batches; they only read
-    # `real`), so D2's steps are issued on a second stream: its many small launches (Linear layers, spectral norm,
-    # reductions) overlap D1's bandwidth-bound conv kernels and vice versa.  Inside a captured CUDA graph the two
-    # chains become parallel branches.  Results are identical to the sequential order.
-    # Eager execution is bound by host launch issue, where a second stream only adds synchronisation calls, so the
-    # side stream is used under graph capture (and by the capture's warm-up) only.
-    main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
-    par = getattr(trainer, "parallel_critics", "auto")
-    use_side = main is not None and n > 0 and (par is True or (par == "auto" and torch.cuda.is_current_stream_capturing()))
-    side = _critic_side_stream(trainer, dev) if use_side else None
-    if side is not None:
-        side.wait_stream(main)
+            z_rand = torch.cat(zs, 0) if n > 1 else zs[0]
+            proto_rep = prototype.repeat(n, 1, 1) if n > 1 else prototype
+            if side is not None and getattr(trainer, "split_critic_generator", _SPLIT_DEFAULT):
+                # two generator calls of n*B gestures, one per critic chain, each on its chain's stream: a layer launch
+                # of the persistent recurrent kernel is (n*B/128) x 2 CTAs, rarely a whole number of waves of the 148
+                # SMs - with two independent calls in flight the tail wave of one call's layer is filled by the other
+                # call's CTAs (10 x 4096 gestures: 20 waves -> 17.3), and D1's chain starts as soon as ITS fakes exist
+                side.wait_stream(main)
+                fake_1 = trainer.generator(proto_rep, z_rand)
+                with torch.cuda.stream(side), _lib.lane(dev, 1):
+                    fake_2 = trainer.generator(proto_rep, z_enc)
+                if not capturing:
+                    for t_ in (proto_rep, z_enc):
+                        t_.record_stream(side)
+            else:
+                fake_all = trainer.generator(torch.cat([proto_rep, proto_rep], 0), torch.cat([z_rand, z_enc], 0))
+                fake_1, fake_2 = fake_all[:n * B], fake_all[n * B:]
+                if side is not None:
+                    side.wait_stream(main)
+        fakes_1 = fake_1.view(n, B, *fake_1.shape[1:])
+        fakes_2 = fake_2.view(n, B, *fake_2.shape[1:])
 
     def d_step(name, disc, opt, fake, critic_it):
         opt.zero_grad()
