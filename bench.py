@@ -30,6 +30,10 @@ PROFILE_CANDIDATES = ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel",
                       "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel")
 
 
+# scaled regime (--hidden > 64): input projections, the fused per-timestep recurrence (forward / BPTT), everything else
+SCALED_CANDIDATES = ("gemm_kernel", "gemm_tc_nt_kernel", "gemm_tc_lstm_fwd_kernel", "gemm_tc_lstm_bwd_kernel", "lstm_cell")
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -335,7 +339,7 @@ def main():
     prof_kernel = args.profile_kernel
     shares = {}
     if prof_kernel == "auto":
-        for cand in (PROFILE_CANDIDATES if not scaled else ("gemm_kernel", "lstm_cell")):
+        for cand in (PROFILE_CANDIDATES if not scaled else SCALED_CANDIDATES):
             _lib.profile_enable(dev, cand)
             step_eager()
             shares[cand] = _lib.profile_read(dev)["ms"]

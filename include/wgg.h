@@ -123,6 +123,17 @@ WGG_API int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
                          const float* eps, const float* log_var, int64_t B, const float* stash, const float* dz,
                          const float* dmu, const float* dlog_var, float* dparams, float* dx, float* ws,
                          int64_t ws_floats, void* stream);
+/* The same pass with the KL term fused in (KLDivergenceLoss.forward, src/gan/losses.py:174-175, on the mu / log_var the
+ * encoder just produced, trainer.py:161-171): both latent heads, the reparameterisation and the partial sums of
+ * mean_b[-0.5 sum_j(1 + lv - mu^2 - exp(lv))] are ONE kernel; *kl (device scalar, may be NULL) receives the mean.
+ * Backward: dkl (device scalar, may be NULL) is the upstream gradient of that scalar; mu is then required. */
+WGG_API int wgg_encoder_forward_kl(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                           const float* eps, int64_t B, float* z, float* mu, float* log_var, float* stash, float* kl,
+                           void* stream);
+WGG_API int wgg_encoder_backward_kl(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                            const float* eps, const float* mu, const float* log_var, int64_t B, const float* stash,
+                            const float* dz, const float* dmu, const float* dlog_var, const float* dkl, float* dparams,
+                            float* dx, float* ws, int64_t ws_floats, void* stream);
 
 /* ---- Discriminators: replace [Temporal]Discriminator.forward / get_all_features,
  * src/gan/models.py:202-243,293-353, including the spectral_norm pre-forward hook

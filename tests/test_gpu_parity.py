@@ -87,6 +87,37 @@ def test_encoder_forward_backward(ocfg, B, seed):
     assert torch.equal(z1, z2)
 
 
+@pytest.mark.parametrize("ocfg,B,seed", [(TINY, 3, 0), (ODD, 33, 2), (DEFAULT, 7, 1), (DEFAULT, 2500, 2)])
+def test_encoder_fused_latent_head_reparam_kl(ocfg, B, seed):
+    """forward_with_kl: both latent heads, z = mu + eps exp(0.5 lv) and the KL term in one kernel (csrc/encoder.cu).
+    Value and the gradients of  sum(dz * z) + 0.37 * kld  against the fp64 oracle (KL: losses.py:174-175), and
+    bit-equality of the KL scalar with the separate KLDivergenceLoss kernel path's formula on the same mu / log_var."""
+    torch.manual_seed(seed)
+    E = wgg.VariationalEncoder(model_cfg(ocfg)).to(DEV)
+    p = state_of(E)
+    real, _, eps = rand_inputs(ocfg, B, seed)
+    rng = np.random.default_rng(seed + 9)
+    dz = rng.standard_normal((B, ocfg.latent_dim))
+    z_ref, mu_ref, lv_ref, st = O.encoder_fwd(p, ocfg, real, eps)
+    kld_ref = float(np.mean(-0.5 * np.sum(1.0 + lv_ref - mu_ref ** 2 - np.exp(lv_ref), axis=1)))
+    w = 0.37
+    dmu_ref = w * mu_ref / B
+    dlv_ref = w * 0.5 * (np.exp(lv_ref) - 1.0) / B
+    g_ref = O.encoder_bwd(p, ocfg, st, dz, dmu_ref, dlv_ref)
+    z, mu, lv, kld = E.forward_with_kl(to_t(real), to_t(eps))
+    assert kld.shape == ()
+    for a, b in ((z, z_ref), (mu, mu_ref), (lv, lv_ref)):
+        assert max_abs_rel(to_np(a), b) <= FWD_TOL
+    assert abs(kld.item() - kld_ref) <= LOSS_TOL * max(1.0, abs(kld_ref))
+    sep = wgg.KLDivergenceLoss()(mu.detach(), lv.detach())
+    assert abs(sep.item() - kld.item()) <= 1e-5 * max(1.0, abs(kld_ref))
+    ((z * to_t(dz)).sum() + w * kld).backward()
+    check_grads(grads_of(E), g_ref, what="encoder+kl")
+    # the three-output call gives the same numbers and leaves the KL unused
+    z3, mu3, lv3 = E(to_t(real), to_t(eps))
+    assert torch.equal(z3, z.detach()) and torch.equal(mu3, mu.detach()) and torch.equal(lv3, lv.detach())
+
+
 @pytest.mark.parametrize("ocfg,B,seed", [(TINY, 3, 0), (TINY_MLP, 5, 1), (DEFAULT, 6, 2), (MLP_DEFAULT, 9, 3),
                                           (ODD, 33, 4)])
 def test_discriminator_schedule_forward_backward(ocfg, B, seed):

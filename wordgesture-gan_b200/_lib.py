@@ -55,6 +55,8 @@ _SIG = {
     "wgg_encoder_workspace_floats": (c_int64, [_CFG, c_int64]),
     "wgg_encoder_forward": (c_int, [_P, _CFG, _P, _P, _P, c_int64, _P, _P, _P, _P, _P]),
     "wgg_encoder_backward": (c_int, [_P, _CFG, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "wgg_encoder_forward_kl": (c_int, [_P, _CFG, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P]),
+    "wgg_encoder_backward_kl": (c_int, [_P, _CFG, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "wgg_disc_param_floats": (c_int64, [_CFG]),
     "wgg_disc_uv_floats": (c_int64, [_CFG]),
     "wgg_disc_sn_floats": (c_int64, [_CFG]),

@@ -149,9 +149,18 @@ struct GemmP {
 };
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
+// out (+)= scale * sum(partial[0..n)) in fixed order (loss.cu); second stage of every deterministic loss reduction
+int wgg_loss_finalize(wgg_ctx* ctx, const float* partial, int n, float scale, int accumulate, float* out, cudaStream_t st);
 // tcgen05 / TMA engine for large "NT" contractions in the tensor-core math modes (gemm_tc.cu); gemm_launch routes to it
 bool gemm_tc_usable(const wgg_ctx* ctx, const GemmP& p);
 int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
+// fused per-timestep kernels of the scaled recurrence (tcgen05 recurrent product + LSTM cell in the epilogue, gemm_tc.cu)
+bool lstm_step_tc_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
+                         int64_t dir_stride);
+int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                         float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st);
+int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
+                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st);
 // workspace (floats) a split-K GEMM of this shape may need
 int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch);
 int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch);

@@ -2,6 +2,7 @@
 // Replaces VariationalEncoder.forward / reparameterize (src/gan/models.py:52-86): flatten :64,
 // [Linear + LeakyReLU(0.2)] x n :67, fc_mu / fc_log_var :70-71, z = mu + eps * exp(0.5 log_var) :84-86.
 // eps is drawn by the caller with torch.randn (the RNG stream stays PyTorch's).
+// The latent head (both heads + reparameterisation + KL partial sums, losses.py:174-175) is one fused kernel.
 #include "common.cuh"
 
 namespace {
@@ -44,15 +45,80 @@ __global__ void reparam_kernel(const float* __restrict__ mu, const float* __rest
     z[i] = mu[i] + eps[i] * expf(0.5f * lv[i]);
 }
 
-// dmu_t = dz + dmu ; dlv_t = dz * eps * 0.5 * exp(0.5 lv) + dlv
+// Fused latent head: fc_mu and fc_log_var (models.py:70-71), the reparameterisation z = mu + eps * exp(0.5 log_var)
+// (:84-86) and the partial sums of the KL term  -0.5 * sum_j (1 + lv - mu^2 - exp(lv))  (losses.py:174-175) in ONE
+// launch: both weight matrices (2 * Z * K floats, 8 KB for the default model) are staged in shared memory, transposed to
+// [k][j] so that consecutive threads read consecutive words; a block walks over groups of R rows of the last hidden
+// activation (one warp-coalesced load per row), thread = (row, latent j).  The KL partials are block sums over a fixed
+// partition, summed in fixed order by finalize (deterministic).  kl_partial may be null (value not wanted).
+constexpr int kHeadRows = 8;
+__global__ void __launch_bounds__(256) enc_head_fused_kernel(const float* __restrict__ h, const float* __restrict__ wmu,
+                                                             const float* __restrict__ bmu, const float* __restrict__ wlv,
+                                                             const float* __restrict__ blv, const float* __restrict__ eps,
+                                                             int64_t B, int K, int Z, float* __restrict__ mu,
+                                                             float* __restrict__ lv, float* __restrict__ z,
+                                                             float* __restrict__ kl_partial) {
+  extern __shared__ float sm[];
+  float* s_wmu = sm;                   // [K][Z]
+  float* s_wlv = s_wmu + (size_t)K * Z;
+  float* s_h = s_wlv + (size_t)K * Z;  // [kHeadRows][K]
+  __shared__ float red[33];
+  for (int i = threadIdx.x; i < K * Z; i += blockDim.x) {
+    const int j = i / K, k = i - j * K;  // global [j][k] -> shared [k][j]
+    s_wmu[k * Z + j] = __ldg(wmu + i);
+    s_wlv[k * Z + j] = __ldg(wlv + i);
+  }
+  float acc = 0.f;
+  const int64_t groups = (B + kHeadRows - 1) / kHeadRows;
+  for (int64_t gidx = blockIdx.x; gidx < groups; gidx += gridDim.x) {
+    const int64_t r0 = gidx * kHeadRows;
+    __syncthreads();  // weights staged / previous group's rows consumed
+    for (int i = threadIdx.x; i < kHeadRows * K; i += blockDim.x) {
+      const int64_t r = r0 + i / K;
+      s_h[i] = r < B ? __ldg(h + r * K + (i % K)) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kHeadRows * Z; e += blockDim.x) {
+      const int rr = e / Z, j = e - rr * Z;
+      const int64_t r = r0 + rr;
+      if (r >= B) continue;
+      const float* hr = s_h + rr * K;
+      float m = __ldg(bmu + j), l = __ldg(blv + j);
+      for (int k = 0; k < K; ++k) {
+        const float hv = hr[k];
+        m = fmaf(hv, s_wmu[k * Z + j], m);
+        l = fmaf(hv, s_wlv[k * Z + j], l);
+      }
+      const int64_t o = r * Z + j;
+      const float el = expf(l);
+      mu[o] = m;
+      lv[o] = l;
+      z[o] = m + __ldg(eps + o) * expf(0.5f * l);
+      acc += 1.f + l - m * m - el;
+    }
+  }
+  const float sacc = block_sum(acc, red);
+  if (kl_partial && threadIdx.x == 0) kl_partial[blockIdx.x] = -0.5f * sacc;
+}
+
+// dmu_t = dz + dmu + gk * mu ; dlv_t = dz * eps * 0.5 * exp(0.5 lv) + dlv + gk * 0.5 * (exp(lv) - 1)
+// with gk = dkl * kl_coef the upstream gradient of the fused KL output (null: no KL term)
 __global__ void enc_head_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ dmu,
                                     const float* __restrict__ dlv, const float* __restrict__ eps,
-                                    const float* __restrict__ lv, float* __restrict__ dmu_t, float* __restrict__ dlv_t,
-                                    int64_t n) {
+                                    const float* __restrict__ lv, const float* __restrict__ mu,
+                                    const float* __restrict__ dkl, float kl_coef, float* __restrict__ dmu_t,
+                                    float* __restrict__ dlv_t, int64_t n) {
+  const float gk = dkl ? __ldg(dkl) * kl_coef : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float g = dz ? dz[i] : 0.f;
-    dmu_t[i] = g + (dmu ? dmu[i] : 0.f);
-    dlv_t[i] = g * eps[i] * 0.5f * expf(0.5f * lv[i]) + (dlv ? dlv[i] : 0.f);
+    float a = g + (dmu ? dmu[i] : 0.f);
+    float b = g * eps[i] * 0.5f * expf(0.5f * lv[i]) + (dlv ? dlv[i] : 0.f);
+    if (dkl) {
+      a = fmaf(gk, mu[i], a);
+      b = fmaf(gk * 0.5f, expf(lv[i]) - 1.f, b);
+    }
+    dmu_t[i] = a;
+    dlv_t[i] = b;
   }
 }
 
@@ -125,9 +191,9 @@ extern "C" int64_t wgg_encoder_workspace_floats(const wgg_model_cfg* cfg, int64_
   return 2 * B * e.Z + 2 * B * maxd + gemm_splitk_ws_floats(1, enc_max_wn(e), 1) + colsum_ws_floats(maxd, 1);
 }
 
-extern "C" int wgg_encoder_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
-                                   const float* eps, int64_t B, float* z, float* mu, float* log_var, float* stash,
-                                   void* stream) {
+extern "C" int wgg_encoder_forward_kl(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                                      const float* eps, int64_t B, float* z, float* mu, float* log_var, float* stash,
+                                      float* kl, void* stream) {
   EncLayout e;
   if (!ctx) return WGG_EINVAL;
   if (enc_layout(cfg, &e) != WGG_OK) return wgg_fail(ctx, WGG_EINVAL, "encoder: bad config%s");
@@ -144,17 +210,37 @@ extern "C" int wgg_encoder_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const
     ldin = e.dims[i + 1];
   }
   const int last = e.dims[e.n];
+  const size_t hsmem = ((size_t)2 * e.Z * last + (size_t)kHeadRows * last) * sizeof(float);
+  if (hsmem <= 48 * 1024) {
+    float* partial = kl ? wgg_next_partial(ctx) : nullptr;
+    const int64_t groups = cdiv64(B, kHeadRows);
+    const int nb = (int)(groups < kRedBlocks ? groups : kRedBlocks);
+    enc_head_fused_kernel<<<nb, 256, hsmem, st>>>(in, params + e.off_wmu, params + e.off_bmu, params + e.off_wlv,
+                                                  params + e.off_blv, eps, B, last, e.Z, mu, log_var, z, partial);
+    WGG_CHECK_LAUNCH(ctx, "enc_head_fused_kernel");
+    if (kl) WGG_TRY(wgg_loss_finalize(ctx, partial, nb, (float)(1.0 / (double)B), 0, kl, st));
+    return WGG_OK;
+  }
+  // latent heads too large for the shared-memory kernel: two GEMMs, the elementwise reparameterisation, the KL reduction
   WGG_TRY(linear_fwd(ctx, in, last, params + e.off_wmu, params + e.off_bmu, mu, e.Z, B, e.Z, last, ACT_NONE, st));
   WGG_TRY(linear_fwd(ctx, in, last, params + e.off_wlv, params + e.off_blv, log_var, e.Z, B, e.Z, last, ACT_NONE, st));
   reparam_kernel<<<ew_blocks(B * e.Z), 256, 0, st>>>(mu, log_var, eps, z, B * e.Z);
   WGG_CHECK_LAUNCH(ctx, "reparam_kernel");
+  if (kl) return wgg_kl(ctx, mu, log_var, B, e.Z, 1.f, 0, kl, stream);
   return WGG_OK;
 }
 
-extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
-                                    const float* eps, const float* log_var, int64_t B, const float* stash,
-                                    const float* dz, const float* dmu, const float* dlog_var, float* dparams,
-                                    float* dx, float* ws, int64_t ws_floats, void* stream) {
+extern "C" int wgg_encoder_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                                   const float* eps, int64_t B, float* z, float* mu, float* log_var, float* stash,
+                                   void* stream) {
+  return wgg_encoder_forward_kl(ctx, cfg, params, x, eps, B, z, mu, log_var, stash, nullptr, stream);
+}
+
+extern "C" int wgg_encoder_backward_kl(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                                       const float* eps, const float* mu, const float* log_var, int64_t B,
+                                       const float* stash, const float* dz, const float* dmu, const float* dlog_var,
+                                       const float* dkl, float* dparams, float* dx, float* ws, int64_t ws_floats,
+                                       void* stream) {
   EncLayout e;
   if (!ctx) return WGG_EINVAL;
   if (enc_layout(cfg, &e) != WGG_OK) return wgg_fail(ctx, WGG_EINVAL, "encoder: bad config%s");
@@ -170,7 +256,9 @@ extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, cons
   float* dh2 = dh + B * maxd;
   float* part = dh2 + B * maxd;
   float* csws = part + gemm_splitk_ws_floats(1, enc_max_wn(e), 1);
-  enc_head_bwd_kernel<<<ew_blocks(B * e.Z), 256, 0, st>>>(dz, dmu, dlog_var, eps, log_var, dmu_t, dlv_t, B * e.Z);
+  if (dkl && !mu) return wgg_fail(ctx, WGG_EINVAL, "encoder_backward: the KL gradient needs mu%s");
+  enc_head_bwd_kernel<<<ew_blocks(B * e.Z), 256, 0, st>>>(dz, dmu, dlog_var, eps, log_var, mu, dkl, (float)(1.0 / (double)B), dmu_t,
+                                                          dlv_t, B * e.Z);
   WGG_CHECK_LAUNCH(ctx, "enc_head_bwd_kernel");
   const int last = e.dims[e.n];
   const float* hl = stash + e.act_off[e.n - 1] * B;
@@ -192,6 +280,14 @@ extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, cons
     }
   }
   return WGG_OK;
+}
+
+extern "C" int wgg_encoder_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* x,
+                                    const float* eps, const float* log_var, int64_t B, const float* stash,
+                                    const float* dz, const float* dmu, const float* dlog_var, float* dparams,
+                                    float* dx, float* ws, int64_t ws_floats, void* stream) {
+  return wgg_encoder_backward_kl(ctx, cfg, params, x, eps, nullptr, log_var, B, stash, dz, dmu, dlog_var, nullptr, dparams, dx,
+                                 ws, ws_floats, stream);
 }
 
 extern "C" int wgg_linear(wgg_ctx* ctx, const float* A, const float* W, const float* bias, float* C, int64_t M,

@@ -7,9 +7,14 @@
 //     out-of-range rows / columns zero-filled by the hardware) into a 3-stage ring, completion on mbarriers;
 //   * one elected thread issues the MMAs (K-major SWIZZLE_128B shared-memory descriptors, K advanced by 32 bytes inside
 //     the swizzle atom), tcgen05.commit releases the stage;
-//   * four epilogue warps read the accumulators with tcgen05.ld and write C rows (bias add or read-modify-write).
+//   * eight epilogue warps (two per TMEM lane quarter, one per 128-column half) read the accumulators with tcgen05.ld and
+//     write C rows (bias - staged once in shared memory - add, or read-modify-write).
 // TF32 operands are 4 bytes each, so the tile has to be this large for the tensor pipe not to starve on L2 bandwidth.
 // Operand values are taken as they are (the tensor core reads the upper 19 bits of each fp32: truncation).
+//
+// The same pipeline carries the per-timestep recurrence of the scaled regime with the LSTM cell fused into the epilogue
+// (gemm_tc_lstm_fwd_kernel / gemm_tc_lstm_bwd_kernel below): one launch per timestep and layer instead of a GEMM that
+// read-modify-writes the gate buffer followed by a cell kernel.
 #include <cuda.h>
 
 #include "tc_common.cuh"
@@ -20,7 +25,8 @@ using namespace tcu;
 
 constexpr int BM = 256, BN = 256, BK = 32, NST = 3;
 constexpr int TILE_BYTES = 256 * BK * 4;  // 32 KB per operand and stage
-constexpr int THREADS = 192;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int THREADS = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int EPI_THREADS = 256;
 
 struct Params {
   CUtensorMap a[2], b[2];  // per batch entry (the two LSTM directions)
@@ -56,8 +62,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + NST * TILE_BYTES;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + NST * TILE_BYTES);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1);
+  static_assert(2 * NST + 1 <= 8, "barrier block is 64 bytes");
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 4);  // [BN] bias + bias2 of this column tile (16-byte aligned)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.z;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -110,30 +118,44 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
     if (ok && elect_one()) mma_commit(DONE);
     __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    // a warp may read the TMEM lanes 32 * (warp id % 4) ... + 31; the second group of four warps takes the upper column half
+    const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+    {
+      const int et = tid - 64, col = n0 + et;
+      float b = 0.f;
+      if (col < p.N) {
+        if (p.bias[z]) b += __ldg(p.bias[z] + col);
+        if (p.bias2[z]) b += __ldg(p.bias2[z] + col);
+      }
+      s_bias[et] = b;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    }
     if (mbar_wait(DONE, 0, s_abort, p.gerr, 73)) {
       tc_fence_after();
       float* C = p.c[z];
-      const float* bias = p.bias[z];
-      const float* bias2 = p.bias2[z];
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int row = m0 + half * 128 + quarter * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 256);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 256 + chalf * 128);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);  // warp-collective: every lane takes part, also for rows beyond M
-          if (row < p.M) {
-            float* crow = C + (int64_t)row * p.ldc + n0 + c0;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          const int colb = chalf * 128 + c0;  // column inside the tile
+          float* crow = C + (int64_t)row * p.ldc + n0 + colb;
+          float4 old[8];
+          if (p.accumulate && row < p.M) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int col = n0 + c0 + 4 * j;
-              if (col < p.N) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + col); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-                if (bias2) { const float4 b = *reinterpret_cast<const float4*>(bias2 + col); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-                if (p.accumulate) { const float4 c = *reinterpret_cast<const float4*>(crow + 4 * j); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+            for (int j = 0; j < 8; ++j)
+              old[j] = (n0 + colb + 4 * j < p.N) ? *reinterpret_cast<const float4*>(crow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float v[32];
+          tmem_ld32(taddr + c0, v);  // warp-collective: every lane takes part, also for rows beyond M
+          if (row < p.M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (n0 + colb + 4 * j < p.N) {
+                const float4 b = *reinterpret_cast<const float4*>(s_bias + colb + 4 * j);
+                float4 o = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+                if (p.accumulate) { o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w; }
                 *reinterpret_cast<float4*>(crow + 4 * j) = o;
               }
             }
@@ -177,6 +199,371 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t K, int64_
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One timestep of the recurrence of a scaled BiLSTM layer (H > 64: W_hh does not fit one SM), both directions:
+//     pre = gates[d][t] (input projection + biases)  +  h[d][t_prev] W_hh[d]^T          (tcgen05, TF32)
+//     i, f, o = sigmoid(.), g = tanh(.);  c = f c_prev + i g;  h = o tanh(c)           (epilogue, fp32)
+// (torch.nn.LSTM as called at src/gan/models.py:160).  CTA = 128 gestures x 64 hidden units x one direction: the B
+// operand is the four 64-row slices (one per gate) of W_hh for these units - four TMA boxes stacked into one 256-row
+// K-major tile - so the accumulator (256 TMEM columns) holds all four gates of a unit under the same lane and the cell
+// update needs no exchange.  A = h[t_prev] through a 3-D tensor map over hseq (k, gesture, t).  The eight epilogue warps
+// (lane quarter x 32-unit half) read the input projection / c_prev with 16-byte loads issued BEFORE the wait for the
+// tensor core, add the accumulator, and write h (rounded to TF32, as the persistent H = 48 kernel does: it is the next
+// step's and the next layer's MMA operand), c and - when the pass carries gradients - the activated gates in place.
+// Step 0 has no recurrent term: K = 0, no MMA, the accumulator counts as zero.
+// ---------------------------------------------------------------------------------------------
+constexpr int SBM = 128, SUN = 64, SNST = 3;
+constexpr int SA_BYTES = SBM * BK * 4;      // 16 KB
+constexpr int SB_BYTES = 4 * SUN * BK * 4;  // 32 KB
+constexpr int SBOX_BYTES = SUN * BK * 4;    // one gate's 64 rows
+
+struct StepFwdParams {
+  CUtensorMap a[2];  // per direction: h of that direction inside hseq, dims (H, B, T), strides (2H, B * 2H) floats
+  CUtensorMap b[2];  // per direction: W_hh [4H][H], boxes of 64 rows
+  float* gates;      // [2][T][B][4H]
+  float* hseq;       // [T][B][2H]
+  float* cseq;       // store: [2][T][B][H]
+  float* cstate;     // no store: [2][B][H]
+  int T, B, H, step, store;
+  int* gerr;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __grid_constant__ StepFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + SNST * SA_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + SNST * SB_BYTES);
+  static_assert(2 * SNST + 1 <= 8, "barrier block is 64 bytes");
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.z;
+  const int u0 = blockIdx.x * SUN, m0 = blockIdx.y * SBM;
+  const int t = dir ? p.T - 1 - p.step : p.step;
+  const int tp = dir ? t + 1 : t - 1;
+  const int H = p.H;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (SNST + s); };
+  const uint32_t DONE = bar0 + 8u * (2 * SNST);
+  if (tid == 0) {
+    for (int s = 0; s < SNST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(DONE, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int KT = p.step > 0 ? (H + BK - 1) / BK : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < KT; ++it) {
+        const int s = it % SNST;
+        if (!mbar_wait(EMPTY(s), (uint32_t)(((it / SNST) & 1) ^ 1), s_abort, p.gerr, 74)) break;
+        mbar_expect_tx(FULL(s), SA_BYTES + SB_BYTES);
+        tma_load_3d(smem_u32(s_a + s * SA_BYTES), &p.a[dir], it * BK, m0, tp, FULL(s));
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(smem_u32(s_b + s * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(s));
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, 256);
+    bool ok = true;
+    for (int it = 0; it < KT && ok; ++it) {
+      const int s = it % SNST;
+      if (!mbar_wait(FULL(s), (uint32_t)((it / SNST) & 1), s_abort, p.gerr, 75)) { ok = false; break; }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(s_a + s * SA_BYTES), b0 = smem_u32(s_b + s * SB_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks)
+          mma_tf32_ss(tmem_base, desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32), idesc, (it | ks) ? 1u : 0u);
+        mma_commit(EMPTY(s));
+      }
+      __syncwarp();
+    }
+    if (ok && KT > 0 && elect_one()) mma_commit(DONE);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3, uh = (warp - 2) >> 2;
+    const int row = m0 + quarter * 32 + lane;
+    const bool rok = row < p.B;
+    const int64_t TB = (int64_t)p.T * p.B;
+    float* gp = p.gates + (((int64_t)dir * p.T + t) * p.B + (rok ? row : 0)) * 4 * H;
+    float* hp = p.hseq + ((int64_t)t * p.B + (rok ? row : 0)) * 2 * H + dir * H;
+    const float* cprev = nullptr;
+    if (p.step > 0)
+      cprev = p.store ? p.cseq + (int64_t)dir * TB * H + ((int64_t)tp * p.B + (rok ? row : 0)) * H
+                      : p.cstate + ((int64_t)dir * p.B + (rok ? row : 0)) * H;
+    float* cout = p.store ? p.cseq + (int64_t)dir * TB * H + ((int64_t)t * p.B + (rok ? row : 0)) * H
+                          : p.cstate + ((int64_t)dir * p.B + (rok ? row : 0)) * H;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // operands of the first chunk are requested before the wait for the tensor core
+    float4 pre[4][2], cp[2];
+    auto load_chunk = [&](int c) {
+      const int u = u0 + uh * 32 + c * 8;
+      const bool ok = rok && u < H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        pre[g][0] = ok ? ld4(gp + g * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pre[g][1] = ok ? ld4(gp + g * H + u + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cp[0] = (ok && cprev) ? ld4(cprev + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cp[1] = (ok && cprev) ? ld4(cprev + u + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    load_chunk(0);
+    bool live = true;
+    if (KT > 0) {
+      live = mbar_wait(DONE, 0, s_abort, p.gerr, 76);
+      tc_fence_after();
+    }
+    if (live) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int u = u0 + uh * 32 + c * 8;
+        float acc[4][8];
+        if (KT > 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)(g * SUN + uh * 32 + c * 8), acc[g]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+        }
+        float a[4][8], cpv[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          a[g][0] = pre[g][0].x; a[g][1] = pre[g][0].y; a[g][2] = pre[g][0].z; a[g][3] = pre[g][0].w;
+          a[g][4] = pre[g][1].x; a[g][5] = pre[g][1].y; a[g][6] = pre[g][1].z; a[g][7] = pre[g][1].w;
+        }
+        cpv[0] = cp[0].x; cpv[1] = cp[0].y; cpv[2] = cp[0].z; cpv[3] = cp[0].w;
+        cpv[4] = cp[1].x; cpv[5] = cp[1].y; cpv[6] = cp[1].z; cpv[7] = cp[1].w;
+        if (c + 1 < 4) load_chunk(c + 1);  // next chunk's operands fly while this one is computed
+        if (rok && u < H) {
+          float hv[8], cv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ig = sigmoid_f(a[0][i] + acc[0][i]);
+            const float fg = sigmoid_f(a[1][i] + acc[1][i]);
+            const float gg = tanhf(a[2][i] + acc[2][i]);
+            const float og = sigmoid_f(a[3][i] + acc[3][i]);
+            cv[i] = fg * cpv[i] + ig * gg;
+            hv[i] = rna_tf32(og * tanhf(cv[i]));
+            a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
+          }
+          st4(hp + u, make_float4(hv[0], hv[1], hv[2], hv[3]));
+          st4(hp + u + 4, make_float4(hv[4], hv[5], hv[6], hv[7]));
+          st4(cout + u, make_float4(cv[0], cv[1], cv[2], cv[3]));
+          st4(cout + u + 4, make_float4(cv[4], cv[5], cv[6], cv[7]));
+          if (p.store) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              st4(gp + g * H + u, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
+              st4(gp + g * H + u + 4, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One timestep of back-propagation through time of the same layer (reverse scan, both directions):
+//     dh_rec = da[d][t_next] W_hh[d]                      (tcgen05; B operand = the transposed image W_hh^T [H][4H])
+//     dh = dh_out[t] + dh_rec;  do = dh tanh(c);  dc = dc_carry + dh o (1 - tanh^2 c)
+//     da_i = dc g i (1 - i), da_f = dc c_prev f (1 - f), da_g = dc i (1 - g^2), da_o = do o (1 - o);  dc_carry = dc f
+// CTA = 128 gestures x 64 hidden units x direction; the epilogue overwrites the activated gates of step t with da (the
+// next launch's A operand and the operand of the weight-gradient GEMMs).  The first launch (step T - 1) has K = 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int WNST = 4;
+constexpr int WB_BYTES = SUN * BK * 4;  // 8 KB
+
+struct StepBwdParams {
+  CUtensorMap a[2];  // per direction: gates[d] as (4H, B, T)
+  CUtensorMap b[2];  // per direction: W_hh^T [H][4H], boxes of 64 rows
+  float* gates;
+  const float* cseq;
+  const float* dh_out;  // [T][B][2H]
+  float* dcs;           // [2][B][H] carried dc
+  int T, B, H, step;
+  int* gerr;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __grid_constant__ StepBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + WNST * SA_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + WNST * WB_BYTES);
+  static_assert(2 * WNST + 1 <= 16, "barrier block is 128 bytes");
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.z;
+  const int u0 = blockIdx.x * SUN, m0 = blockIdx.y * SBM;
+  const int t = dir ? p.T - 1 - p.step : p.step;
+  const int tn = dir ? t - 1 : t + 1;  // the step processed by the previous launch (later in the sequence's own order)
+  const int tp = dir ? t + 1 : t - 1;  // the step whose cell state is c_prev
+  const int H = p.H;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (WNST + s); };
+  const uint32_t DONE = bar0 + 8u * (2 * WNST);
+  if (tid == 0) {
+    for (int s = 0; s < WNST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(DONE, 1);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const bool first = p.step == p.T - 1;
+  const int KT = first ? 0 : (4 * H + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < KT; ++it) {
+        const int s = it % WNST;
+        if (!mbar_wait(EMPTY(s), (uint32_t)(((it / WNST) & 1) ^ 1), s_abort, p.gerr, 77)) break;
+        mbar_expect_tx(FULL(s), SA_BYTES + WB_BYTES);
+        tma_load_3d(smem_u32(s_a + s * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(s));
+        tma_load_2d(smem_u32(s_b + s * WB_BYTES), &p.b[dir], it * BK, u0, FULL(s));
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, SUN);
+    bool ok = true;
+    for (int it = 0; it < KT && ok; ++it) {
+      const int s = it % WNST;
+      if (!mbar_wait(FULL(s), (uint32_t)((it / WNST) & 1), s_abort, p.gerr, 78)) { ok = false; break; }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(s_a + s * SA_BYTES), b0 = smem_u32(s_b + s * WB_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks)
+          mma_tf32_ss(tmem_base, desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32), idesc, (it | ks) ? 1u : 0u);
+        mma_commit(EMPTY(s));
+      }
+      __syncwarp();
+    }
+    if (ok && KT > 0 && elect_one()) mma_commit(DONE);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3, uh = (warp - 2) >> 2;
+    const int row = m0 + quarter * 32 + lane;
+    const bool rok = row < p.B;
+    const int64_t TB = (int64_t)p.T * p.B;
+    const int64_t r = rok ? row : 0;
+    float* gp = p.gates + (((int64_t)dir * p.T + t) * p.B + r) * 4 * H;
+    const float* cb = p.cseq + (int64_t)dir * TB * H;
+    const float* cc = cb + ((int64_t)t * p.B + r) * H;
+    const float* cpp = p.step > 0 ? cb + ((int64_t)tp * p.B + r) * H : nullptr;
+    const float* dho = p.dh_out + ((int64_t)t * p.B + r) * 2 * H + dir * H;
+    float* dcs = p.dcs + ((int64_t)dir * p.B + r) * H;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    bool live = true;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      const int u = u0 + uh * 32 + c * 4;
+      const bool ok = rok && u < H;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gi = ok ? ld4(gp + u) : z4, gf = ok ? ld4(gp + H + u) : z4, gg = ok ? ld4(gp + 2 * H + u) : z4,
+                   go = ok ? ld4(gp + 3 * H + u) : z4;
+      const float4 c4 = ok ? ld4(cc + u) : z4, cp4 = (ok && cpp) ? ld4(cpp + u) : z4, dh4 = ok ? ld4(dho + u) : z4;
+      const float4 dc4 = (ok && !first) ? ld4(dcs + u) : z4;
+      if (c == 0 && KT > 0) {
+        live = mbar_wait(DONE, 0, s_abort, p.gerr, 79);
+        tc_fence_after();
+      }
+      if (!live) break;
+      float rec[4] = {0.f, 0.f, 0.f, 0.f};
+      if (KT > 0) {
+        uint32_t rr[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3])
+                     : "r"(taddr + (uint32_t)(uh * 32 + c * 4)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rec[i] = __uint_as_float(rr[i]);
+      }
+      if (ok) {
+        const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w},
+                    ov[4] = {go.x, go.y, go.z, go.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w}, pv[4] = {cp4.x, cp4.y, cp4.z, cp4.w},
+                    dv[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, kv[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+        float di[4], df[4], dg[4], dO[4], dk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float tc = tanhf(cv[i]);
+          const float dh = dv[i] + rec[i];
+          const float d_o = dh * tc;
+          const float dct = kv[i] + dh * ov[i] * (1.f - tc * tc);
+          di[i] = dct * gv[i] * iv[i] * (1.f - iv[i]);
+          df[i] = dct * pv[i] * fv[i] * (1.f - fv[i]);
+          dg[i] = dct * iv[i] * (1.f - gv[i] * gv[i]);
+          dO[i] = d_o * ov[i] * (1.f - ov[i]);
+          dk[i] = dct * fv[i];
+        }
+        st4(gp + u, make_float4(di[0], di[1], di[2], di[3]));
+        st4(gp + H + u, make_float4(df[0], df[1], df[2], df[3]));
+        st4(gp + 2 * H + u, make_float4(dg[0], dg[1], dg[2], dg[3]));
+        st4(gp + 3 * H + u, make_float4(dO[0], dO[1], dO[2], dO[3]));
+        st4(dcs + u, make_float4(dk[0], dk[1], dk[2], dk[3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// W^T image: out[d][k][n] = in[d][n][k]   (n < N rows, k < K columns), 32 x 32 tiles through shared memory
+__global__ void transpose_image_kernel(const float* __restrict__ in, int64_t in_bs, float* __restrict__ out, int N, int K) {
+  __shared__ float tile[32][33];
+  const float* src = in + (int64_t)blockIdx.z * in_bs;
+  float* dst = out + (int64_t)blockIdx.z * N * K;
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && k < K) ? src[(int64_t)n * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    if (k < K && n < N) dst[(int64_t)k * N + n] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace gtc
 
 // Can this contraction go through the tcgen05 GEMM?  (fully contiguous-K operands, 16-byte aligned rows, unit column
@@ -204,7 +591,7 @@ int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   }
   prm.M = (int)p.M; prm.N = (int)p.N; prm.K = (int)p.K; prm.ldc = (int)p.scm; prm.accumulate = p.accumulate;
   prm.gerr = ctx->async_err;
-  constexpr size_t smem = (size_t)2 * gtc::NST * gtc::TILE_BYTES + (2 * gtc::NST + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)2 * gtc::NST * gtc::TILE_BYTES + 64 + 16 + gtc::BN * 4 + 1024;
   if (!wgg_smem_ok(ctx, gtc::gemm_tc_nt_kernel, smem)) return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_nt_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(p.N, gtc::BN), (unsigned)cdiv64(p.M, gtc::BM), (unsigned)p.nbatch);
   ProfScope prof(ctx, "gemm_tc_nt_kernel", st, 2.0 * p.M * (double)p.N * p.K * p.nbatch,
@@ -212,5 +599,106 @@ int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
                  p.tag ? p.tag : "gemm_tc_nt_kernel");
   gtc::gemm_tc_nt_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
   WGG_CHECK_LAUNCH(ctx, "gemm_tc_nt_kernel");
+  return WGG_OK;
+}
+
+namespace gtc {
+
+// 2-D map over a [rows, K] matrix (row stride ld floats) with boxes of box_rows x 32 floats
+bool make_map_rows(CUtensorMap* m, const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 3-D map (k, gesture, t) over a time-major activation: K columns of each row, row stride ld floats, B rows per timestep
+bool make_map_time(CUtensorMap* m, const float* base, int64_t K, int64_t B, int64_t T, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)B, (cuuint64_t)T};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)B * ld * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)SBM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gtc
+
+// The fused per-step kernels take the scaled recurrence in the tensor-core math modes when every 16-byte access they make
+// is aligned (H a multiple of 8) and the driver exposes cuTensorMapEncodeTiled.
+bool lstm_step_tc_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
+                         int64_t dir_stride) {
+  if (ctx->math_mode < 1 || (H & 7) || H < 32) return false;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al(gates) || !al(hseq) || !al(lp + off_whh) || (dir_stride & 3)) return false;
+  return gtc::encode_fn() != nullptr;
+}
+
+int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                         float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
+  gtc::StepFwdParams prm;
+  memset(&prm, 0, sizeof(prm));
+  for (int d = 0; d < 2; ++d) {
+    if (!gtc::make_map_time(&prm.a[d], hseq + d * H, H, B, T, 2 * H) ||
+        !gtc::make_map_rows(&prm.b[d], lp + off_whh + d * dir_stride, 4 * H, H, H, gtc::SUN))
+      return wgg_fail(ctx, WGG_ECUDA, "lstm_step_tc_forward: cuTensorMapEncodeTiled failed%s");
+  }
+  prm.gates = gates; prm.hseq = hseq; prm.cseq = cseq; prm.cstate = cstate;
+  prm.T = T; prm.B = (int)B; prm.H = H; prm.store = store; prm.gerr = ctx->async_err;
+  constexpr size_t smem = (size_t)gtc::SNST * (gtc::SA_BYTES + gtc::SB_BYTES) + 64 + 16 + 1024;
+  if (!wgg_smem_ok(ctx, gtc::gemm_tc_lstm_fwd_kernel, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_fwd_kernel: cannot reserve shared memory%s");
+  dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);
+  for (int step = 0; step < T; ++step) {
+    prm.step = step;
+    ProfScope prof(ctx, "gemm_tc_lstm_fwd_kernel", st, step > 0 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
+                   4.0 * 2 * ((double)B * (step > 0 ? H : 0) + (double)B * 4 * H * (store ? 2 : 1) + 3.0 * B * H),
+                   "gemm_tc_lstm_fwd_kernel");
+    gtc::gemm_tc_lstm_fwd_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
+    WGG_CHECK_LAUNCH(ctx, "gemm_tc_lstm_fwd_kernel");
+  }
+  return WGG_OK;
+}
+
+// scratch: dcs [2][B][H] | W_hh^T images [2][H][4H]
+int64_t lstm_step_tc_bwd_scratch_floats(int H, int64_t B) { return 2 * B * (int64_t)H + 8 * (int64_t)H * H + 64; }
+
+int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
+                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st) {
+  float* dcs = scratch;
+  float* wt = scratch + ((2 * B * (int64_t)H + 3) & ~(int64_t)3);  // keep the image 16-byte aligned
+  if (reinterpret_cast<uintptr_t>(wt) & 15) wt += 4 - ((reinterpret_cast<uintptr_t>(wt) & 15) >> 2);
+  {
+    dim3 g((unsigned)cdiv64(H, 32), (unsigned)cdiv64(4 * H, 32), 2);
+    gtc::transpose_image_kernel<<<g, dim3(32, 8), 0, st>>>(lp + off_whh, dir_stride, wt, 4 * H, H);
+    WGG_CHECK_LAUNCH(ctx, "transpose_image_kernel");
+  }
+  const int64_t TB = (int64_t)T * B;
+  gtc::StepBwdParams prm;
+  memset(&prm, 0, sizeof(prm));
+  for (int d = 0; d < 2; ++d) {
+    if (!gtc::make_map_time(&prm.a[d], gates + d * TB * 4 * H, 4 * H, B, T, 4 * H) ||
+        !gtc::make_map_rows(&prm.b[d], wt + (int64_t)d * 4 * H * H, H, 4 * H, 4 * H, gtc::SUN))
+      return wgg_fail(ctx, WGG_ECUDA, "lstm_step_tc_backward: cuTensorMapEncodeTiled failed%s");
+  }
+  prm.gates = gates; prm.cseq = cseq; prm.dh_out = dh_out; prm.dcs = dcs;
+  prm.T = T; prm.B = (int)B; prm.H = H; prm.gerr = ctx->async_err;
+  constexpr size_t smem = (size_t)gtc::WNST * (gtc::SA_BYTES + gtc::WB_BYTES) + 128 + 16 + 1024;
+  if (!wgg_smem_ok(ctx, gtc::gemm_tc_lstm_bwd_kernel, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_bwd_kernel: cannot reserve shared memory%s");
+  dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);
+  for (int step = T - 1; step >= 0; --step) {
+    prm.step = step;
+    ProfScope prof(ctx, "gemm_tc_lstm_bwd_kernel", st, step < T - 1 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
+                   4.0 * 2 * ((double)B * 4 * H * (step < T - 1 ? 3 : 2) + 5.0 * B * H), "gemm_tc_lstm_bwd_kernel");
+    gtc::gemm_tc_lstm_bwd_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
+    WGG_CHECK_LAUNCH(ctx, "gemm_tc_lstm_bwd_kernel");
+  }
   return WGG_OK;
 }

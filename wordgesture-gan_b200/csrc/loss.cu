@@ -216,6 +216,12 @@ extern "C" int wgg_feature_matching_backward(wgg_ctx* ctx, const wgg_model_cfg* 
   return WGG_OK;
 }
 
+int wgg_loss_finalize(wgg_ctx* ctx, const float* partial, int n, float scale, int accumulate, float* out, cudaStream_t st) {
+  finalize_kernel<<<1, 256, 0, st>>>(partial, n, scale, accumulate, out);
+  WGG_CHECK_LAUNCH(ctx, "finalize_kernel");
+  return WGG_OK;
+}
+
 extern "C" int wgg_kl(wgg_ctx* ctx, const float* mu, const float* log_var, int64_t B, int32_t Z, float scale,
                       int accumulate, float* out, void* stream) {
   if (!ctx || B <= 0) return WGG_EINVAL;

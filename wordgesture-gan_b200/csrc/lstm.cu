@@ -375,13 +375,17 @@ bool rec_has_persistent_kernel(int H) { return H == 8 || H == 16 || H == 32 || H
 // backward keeps dh_rec and dc [2][B][H] each
 int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
   if (rec_has_persistent_kernel(H)) return 0;
-  return (backward ? 4 : 2) * B * (int64_t)H;
+  // backward: dh_rec | dc, or (fused tcgen05 step kernels) dc | the W_hh^T images
+  return backward ? 4 * B * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * B * (int64_t)H;
 }
 
 int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                     float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
   const int64_t TB = (int64_t)T * B;
   const int H4 = 4 * H;
+  // tensor-core math modes: one fused launch per timestep (tcgen05 recurrent product + cell update, gemm_tc.cu)
+  if (lstm_step_tc_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride))
+    return lstm_step_tc_forward(ctx, H, gates, lp, dir_stride, off_whh, hseq, cseq, cstate, T, B, store, st);
   for (int step = 0; step < T; ++step) {
     if (step > 0) {
       // direction 0 consumes h at t - 1 and writes gates at t = step; direction 1 consumes h at t + 1, writes t = T-1-step
@@ -407,6 +411,8 @@ int rec_bwd_generic(wgg_ctx* ctx, int H, float* gates, const float* cseq, const 
                     int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st) {
   const int64_t TB = (int64_t)T * B;
   const int H4 = 4 * H;
+  if (lstm_step_tc_usable(ctx, H, gates, dh_out, lp, off_whh, dir_stride))
+    return lstm_step_tc_backward(ctx, H, gates, cseq, lp, dir_stride, off_whh, dh_out, scratch, T, B, st);
   float* dhrec = scratch;
   float* dcs = scratch + 2 * B * H;
   for (int step = T - 1; step >= 0; --step) {

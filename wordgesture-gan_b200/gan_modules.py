@@ -310,6 +310,9 @@ class Generator(FlatModule):
 # Variational encoder
 # ------------------------------------------------------------------------------------------------
 class _EncoderFn(torch.autograd.Function):
+    """(z, mu, log_var, kld): the fourth output is the batch-mean KL term of (mu, log_var), produced by the same fused
+    kernel as the latent heads and the reparameterisation (csrc/encoder.cu: enc_head_fused_kernel)."""
+
     @staticmethod
     def forward(ctx, module, x, eps, *params):
         lib = _lib.lib()
@@ -322,19 +325,22 @@ class _EncoderFn(torch.autograd.Function):
         z = torch.empty(B, Z, dtype=torch.float32, device=dev)
         mu = torch.empty_like(z)
         log_var = torch.empty_like(z)
+        want_kl = bool(getattr(module, "_want_kl", False)) and B > 0
+        kld = torch.empty((), dtype=torch.float32, device=dev) if want_kl else torch.zeros((), dtype=torch.float32, device=dev)
         stash = torch.empty(lib.wgg_encoder_stash_floats(cfg, B), dtype=torch.float32, device=dev)
-        _lib.check(lib.wgg_encoder_forward(c, cfg, _lib.ptr(flat), _lib.ptr(x), _lib.ptr(eps), B, _lib.ptr(z),
-                                           _lib.ptr(mu), _lib.ptr(log_var), _lib.ptr(stash), _lib.stream(dev)), c)
+        _lib.check(lib.wgg_encoder_forward_kl(c, cfg, _lib.ptr(flat), _lib.ptr(x), _lib.ptr(eps), B, _lib.ptr(z),
+                                              _lib.ptr(mu), _lib.ptr(log_var), _lib.ptr(stash),
+                                              _lib.ptr(kld) if want_kl else None, _lib.stream(dev)), c)
         ctx.module = module
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(x, eps, log_var, stash)
-        return z, mu, log_var
+        ctx.save_for_backward(x, eps, mu, log_var, stash)
+        return z, mu, log_var, kld
 
     @staticmethod
-    def backward(ctx, dz, dmu, dlv):
+    def backward(ctx, dz, dmu, dlv, dkl):
         module = ctx.module
         lib = _lib.lib()
-        x, eps, log_var, stash = ctx.saved_tensors
+        x, eps, mu, log_var, stash = ctx.saved_tensors
         dev = x.device
         c = _lib.ctx(dev)
         cfg = _lib.c_cfg(module.config)
@@ -345,10 +351,11 @@ class _EncoderFn(torch.autograd.Function):
         nws = lib.wgg_encoder_workspace_floats(cfg, B)
         ws = _lib.workspace(dev, nws)
         cont = lambda t: None if t is None else t.contiguous()
-        _lib.check(lib.wgg_encoder_backward(c, cfg, _lib.ptr(flat), _lib.ptr(x), _lib.ptr(eps), _lib.ptr(log_var), B,
-                                            _lib.ptr(stash), _lib.ptr(cont(dz)), _lib.ptr(cont(dmu)),
-                                            _lib.ptr(cont(dlv)), _lib.ptr(dflat), _lib.ptr(dx), _lib.ptr(ws),
-                                            ws.numel(), _lib.stream(dev)), c)
+        _lib.check(lib.wgg_encoder_backward_kl(c, cfg, _lib.ptr(flat), _lib.ptr(x), _lib.ptr(eps), _lib.ptr(mu),
+                                               _lib.ptr(log_var), B, _lib.ptr(stash), _lib.ptr(cont(dz)),
+                                               _lib.ptr(cont(dmu)), _lib.ptr(cont(dlv)), _lib.ptr(cont(dkl)),
+                                               _lib.ptr(dflat), _lib.ptr(dx), _lib.ptr(ws), ws.numel(),
+                                               _lib.stream(dev)), c)
         return (None, dx, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
@@ -365,8 +372,9 @@ class VariationalEncoder(FlatModule):
         self.fc_log_var = _Dense(dims[-1], config.latent_dim)
         self._flatten()
 
-    def _run(self, x: torch.Tensor, eps: torch.Tensor):
+    def _run(self, x: torch.Tensor, eps: torch.Tensor, want_kl: bool = False):
         params = _param_list(self)
+        self._want_kl = want_kl  # read by _EncoderFn.forward: the KL finalisation launch is skipped when unused
         if not torch.is_grad_enabled():
             return _EncoderFn.apply(self, x.detach(), eps, *[p.detach() for p in params])
         return _EncoderFn.apply(self, x, eps, *params)
@@ -382,7 +390,20 @@ class VariationalEncoder(FlatModule):
             eps = torch.randn(B, self.config.latent_dim, dtype=torch.float32, device=x.device)
         else:
             eps = _check_input(eps, "eps")
-        return self._run(x, eps)
+        return self._run(x, eps)[:3]
+
+    def forward_with_kl(self, x: torch.Tensor, eps: torch.Tensor = None):
+        """(z, mu, log_var, kld) with kld = KLDivergenceLoss()(mu, log_var) (src/gan/losses.py:174-175) computed by the
+        fused latent-head kernel - what cycle 2 needs (trainer.py:161-171) in one pass."""
+        x = _check_input(x, "x")
+        B = x.shape[0]
+        if x.numel() != B * self.config.seq_length * self.config.input_dim:
+            raise ValueError(f"x must be (B, {self.config.seq_length}, {self.config.input_dim}), got {tuple(x.shape)}")
+        if eps is None:
+            eps = torch.randn(B, self.config.latent_dim, dtype=torch.float32, device=x.device)
+        else:
+            eps = _check_input(eps, "eps")
+        return self._run(x, eps, want_kl=True)
 
     def reparameterize(self, mu: torch.Tensor, log_var: torch.Tensor) -> torch.Tensor:
         """z = mu + eps * exp(0.5 log_var), eps ~ N(0, I)   (models.py:78-86)."""

@@ -69,6 +69,15 @@ class WordGestureGANTrainer:
         feat = feature_matching_from_stash(real_stash, fake_stash, self.model_config, fake.shape[0])
         return wgan, feat
 
+    def _encode_with_kl(self, real_gesture, eps):
+        """Encoder pass of cycle 2 (trainer.py:161-162) together with its KL term (:171): the stock pair
+        (VariationalEncoder, KLDivergenceLoss) runs as the fused latent-head kernel; a user-replaced encoder or KL
+        module is called the reference's way."""
+        if isinstance(self.kl_divergence_loss, KLDivergenceLoss) and hasattr(self.encoder, "forward_with_kl"):
+            return self.encoder.forward_with_kl(real_gesture, eps)
+        z_enc, mu, log_var = self.encoder(real_gesture, eps)
+        return z_enc, mu, log_var, self.kl_divergence_loss(mu, log_var)
+
     def cycle1_tensors(self, prototype, real_gesture, z: Optional[torch.Tensor] = None,
                        eps_recover: Optional[torch.Tensor] = None):
         """Cycle 1 (z -> X' -> z').  Returns (fake, total, dict of 0-dim device tensors) without host syncs.
@@ -92,11 +101,10 @@ class WordGestureGANTrainer:
         tc = self.training_config
         if eps is None:
             eps = self._randn(prototype.size(0))
-        z_enc, mu, log_var = self.encoder(real_gesture, eps)
+        z_enc, mu, log_var, kld = self._encode_with_kl(real_gesture, eps)
         fake = self.generator(prototype, z_enc)
         wgan, feat = self._adversarial_terms(self.discriminator_2, fake, real_gesture)
         rec = self.reconstruction_loss(real_gesture, fake)
-        kld = self.kl_divergence_loss(mu, log_var)
         total = wgan + tc.lambda_feat * feat + tc.lambda_rec * rec + tc.lambda_kld * kld
         return fake, total, {"cycle2_wgan": wgan, "cycle2_feat": feat, "cycle2_rec": rec, "cycle2_kld": kld,
                              "cycle2_total": total}
@@ -117,7 +125,7 @@ class WordGestureGANTrainer:
             eps_recover = self._randn(B)
         if eps is None:
             eps = self._randn(B)
-        z_enc, mu, log_var = self.encoder(real_gesture, eps)
+        z_enc, mu, log_var, kld = self._encode_with_kl(real_gesture, eps)
         fake = self.generator(torch.cat([prototype, prototype], 0), torch.cat([z, z_enc], 0))
         fake1, fake2 = fake[:B], fake[B:]
         wgan1, feat1 = self._adversarial_terms(self.discriminator_1, fake1, real_gesture)
@@ -127,7 +135,6 @@ class WordGestureGANTrainer:
         total1 = wgan1 + tc.lambda_feat * feat1 + tc.lambda_lat * lat
         wgan2, feat2 = self._adversarial_terms(self.discriminator_2, fake2, real_gesture)
         rec = self.reconstruction_loss(real_gesture, fake2)
-        kld = self.kl_divergence_loss(mu, log_var)
         total2 = wgan2 + tc.lambda_feat * feat2 + tc.lambda_rec * rec + tc.lambda_kld * kld
         d1 = {"cycle1_wgan": wgan1, "cycle1_feat": feat1, "cycle1_lat": lat, "cycle1_total": total1}
         d2 = {"cycle2_wgan": wgan2, "cycle2_feat": feat2, "cycle2_rec": rec, "cycle2_kld": kld, "cycle2_total": total2}
