@@ -213,7 +213,7 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t K, int64_
 // step's and the next layer's MMA operand), c and - when the pass carries gradients - the activated gates in place.
 // Step 0 has no recurrent term: K = 0, no MMA, the accumulator counts as zero.
 // ---------------------------------------------------------------------------------------------
-constexpr int SBM = 128, SUN = 64, SNST = 3;
+constexpr int SBM = 128, SUN = 64;  // ring depth SNST is a template parameter (2, 3 or 4 stages of 48 KB)
 constexpr int SA_BYTES = SBM * BK * 4;      // 16 KB
 constexpr int SB_BYTES = 4 * SUN * BK * 4;  // 32 KB
 constexpr int SBOX_BYTES = SUN * BK * 4;    // one gate's 64 rows
@@ -236,17 +236,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// Programmatic dependent launch: consecutive timestep kernels are launched with the programmatic-serialisation attribute,
+// so a step's CTAs may start (barrier init, TMEM allocation, the weight slabs of the first ring stages, the input
+// projection) while the previous step's epilogue is still running; everything the previous step produces is touched only
+// after pdl_wait() (which returns once the previous grid has completed and its writes are visible).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
+template <int SNST>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __grid_constant__ StepFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + SNST * SA_BYTES;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + SNST * SB_BYTES);
-  static_assert(2 * SNST + 1 <= 8, "barrier block is 64 bytes");
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  static_assert(2 * SNST + 1 <= 16, "barrier block is 128 bytes");
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.z;
@@ -273,7 +281,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < KT; ++it) {
+      // weight slabs of the first ring stages do not depend on the previous timestep: request them, then wait for it
+      const int npre = KT < SNST ? KT : SNST;
+      for (int it = 0; it < npre; ++it) {
+        mbar_expect_tx(FULL(it), SA_BYTES + SB_BYTES);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(smem_u32(s_b + it * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(it));
+      }
+      pdl_wait();
+      pdl_launch_dependents();
+      for (int it = 0; it < npre; ++it) tma_load_3d(smem_u32(s_a + it * SA_BYTES), &p.a[dir], it * BK, m0, tp, FULL(it));
+      for (int it = npre; it < KT; ++it) {
         const int s = it % SNST;
         if (!mbar_wait(EMPTY(s), (uint32_t)(((it / SNST) & 1) ^ 1), s_abort, p.gerr, 74)) break;
         mbar_expect_tx(FULL(s), SA_BYTES + SB_BYTES);
@@ -315,58 +334,76 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
     float* cout = p.store ? p.cseq + (int64_t)dir * TB * H + ((int64_t)t * p.B + (rok ? row : 0)) * H
                           : p.cstate + ((int64_t)dir * p.B + (rok ? row : 0)) * H;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // operands of the first chunk are requested before the wait for the tensor core
-    float4 pre[4][2], cp[2];
-    auto load_chunk = [&](int c) {
+    // four chunks of 8 hidden units per thread (two adjacent 16-byte accesses = one full 32-byte sector per row and gate); a
+    // chunk's operands (the four pre-activations, c_prev: ten 16-byte loads) are requested two chunks ahead of their use,
+    // the first two before the wait for the tensor core.  The input projection does not depend on the previous timestep
+    // and is requested before pdl_wait(), c_prev after it.
+    float4 pre[2][4][2], cp[2][2];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_pre = [&](int c, int slot) {
       const int u = u0 + uh * 32 + c * 8;
       const bool ok = rok && u < H;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        pre[g][0] = ok ? ld4(gp + g * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        pre[g][1] = ok ? ld4(gp + g * H + u + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pre[slot][g][0] = ok ? ld4(gp + g * H + u) : z4;
+        pre[slot][g][1] = ok ? ld4(gp + g * H + u + 4) : z4;
       }
-      cp[0] = (ok && cprev) ? ld4(cprev + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-      cp[1] = (ok && cprev) ? ld4(cprev + u + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    load_chunk(0);
+    auto load_c = [&](int c, int slot) {
+      const int u = u0 + uh * 32 + c * 8;
+      const bool ok = rok && u < H && cprev;
+      cp[slot][0] = ok ? ld4(cprev + u) : z4;
+      cp[slot][1] = ok ? ld4(cprev + u + 4) : z4;
+    };
+    load_pre(0, 0);
+    load_pre(1, 1);
+    pdl_wait();
+    load_c(0, 0);
+    load_c(1, 1);
     bool live = true;
     if (KT > 0) {
       live = mbar_wait(DONE, 0, s_abort, p.gerr, 76);
       tc_fence_after();
     }
     if (live) {
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
+        const int slot = c & 1;
         const int u = u0 + uh * 32 + c * 8;
-        float acc[4][8];
+        float a[4][8];
         if (KT > 0) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)(g * SUN + uh * 32 + c * 8), acc[g]);
+          for (int g = 0; g < 4; ++g) {
+            uint32_t rr[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "r"(taddr + (uint32_t)(g * SUN + uh * 32 + c * 8)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[g][i] = __uint_as_float(rr[i]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[g][i] = 0.f;
+            for (int i = 0; i < 8; ++i) a[g][i] = 0.f;
         }
-        float a[4][8], cpv[8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          a[g][0] = pre[g][0].x; a[g][1] = pre[g][0].y; a[g][2] = pre[g][0].z; a[g][3] = pre[g][0].w;
-          a[g][4] = pre[g][1].x; a[g][5] = pre[g][1].y; a[g][6] = pre[g][1].z; a[g][7] = pre[g][1].w;
+          const float4 lo = pre[slot][g][0], hi = pre[slot][g][1];
+          a[g][0] += lo.x; a[g][1] += lo.y; a[g][2] += lo.z; a[g][3] += lo.w;
+          a[g][4] += hi.x; a[g][5] += hi.y; a[g][6] += hi.z; a[g][7] += hi.w;
         }
-        cpv[0] = cp[0].x; cpv[1] = cp[0].y; cpv[2] = cp[0].z; cpv[3] = cp[0].w;
-        cpv[4] = cp[1].x; cpv[5] = cp[1].y; cpv[6] = cp[1].z; cpv[7] = cp[1].w;
-        if (c + 1 < 4) load_chunk(c + 1);  // next chunk's operands fly while this one is computed
+        const float cpv[8] = {cp[slot][0].x, cp[slot][0].y, cp[slot][0].z, cp[slot][0].w,
+                              cp[slot][1].x, cp[slot][1].y, cp[slot][1].z, cp[slot][1].w};
+        if (c + 2 < 4) { load_pre(c + 2, slot); load_c(c + 2, slot); }
         if (rok && u < H) {
           float hv[8], cv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float ig = sigmoid_f(a[0][i] + acc[0][i]);
-            const float fg = sigmoid_f(a[1][i] + acc[1][i]);
-            const float gg = tanhf(a[2][i] + acc[2][i]);
-            const float og = sigmoid_f(a[3][i] + acc[3][i]);
-            cv[i] = fg * cpv[i] + ig * gg;
-            hv[i] = rna_tf32(og * tanhf(cv[i]));
+            float ig, fg, gg, og, hh;
+            lstm_cell_fast(a[0][i], a[1][i], a[2][i], a[3][i], cpv[i], ig, fg, gg, og, cv[i], hh);
+            hv[i] = rna_tf32(hh);
             a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
           }
           st4(hp + u, make_float4(hv[0], hv[1], hv[2], hv[3]));
@@ -450,7 +487,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < KT; ++it) {
+      const int npre = KT < WNST ? KT : WNST;
+      for (int it = 0; it < npre; ++it) {
+        mbar_expect_tx(FULL(it), SA_BYTES + WB_BYTES);
+        tma_load_2d(smem_u32(s_b + it * WB_BYTES), &p.b[dir], it * BK, u0, FULL(it));
+      }
+      pdl_wait();
+      pdl_launch_dependents();
+      for (int it = 0; it < npre; ++it) tma_load_3d(smem_u32(s_a + it * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(it));
+      for (int it = npre; it < KT; ++it) {
         const int s = it % WNST;
         if (!mbar_wait(EMPTY(s), (uint32_t)(((it / WNST) & 1) ^ 1), s_abort, p.gerr, 77)) break;
         mbar_expect_tx(FULL(s), SA_BYTES + WB_BYTES);
@@ -489,53 +534,82 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
     const float* dho = p.dh_out + ((int64_t)t * p.B + r) * 2 * H + dir * H;
     float* dcs = p.dcs + ((int64_t)dir * p.B + r) * H;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    bool live = true;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      const int u = u0 + uh * 32 + c * 4;
+    // four chunks of 8 hidden units per thread (two adjacent 16-byte accesses = one full 32-byte sector per row and
+    // tensor), operands requested one chunk ahead; everything but the carried dc is independent of the previous launch and
+    // is requested before pdl_wait()
+    struct Ops { float4 gi[2], gf[2], gg[2], go[2], c4[2], cp4[2], dh4[2]; };
+    struct Dc { float4 v[2]; };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_ops = [&](int c) {
+      const int u = u0 + uh * 32 + c * 8;
       const bool ok = rok && u < H;
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 gi = ok ? ld4(gp + u) : z4, gf = ok ? ld4(gp + H + u) : z4, gg = ok ? ld4(gp + 2 * H + u) : z4,
-                   go = ok ? ld4(gp + 3 * H + u) : z4;
-      const float4 c4 = ok ? ld4(cc + u) : z4, cp4 = (ok && cpp) ? ld4(cpp + u) : z4, dh4 = ok ? ld4(dho + u) : z4;
-      const float4 dc4 = (ok && !first) ? ld4(dcs + u) : z4;
-      if (c == 0 && KT > 0) {
-        live = mbar_wait(DONE, 0, s_abort, p.gerr, 79);
-        tc_fence_after();
-      }
-      if (!live) break;
-      float rec[4] = {0.f, 0.f, 0.f, 0.f};
-      if (KT > 0) {
-        uint32_t rr[4];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3])
-                     : "r"(taddr + (uint32_t)(uh * 32 + c * 4)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      Ops o;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rec[i] = __uint_as_float(rr[i]);
+      for (int q = 0; q < 2; ++q) {
+        const int uq = u + 4 * q;
+        o.gi[q] = ok ? ld4(gp + uq) : z4; o.gf[q] = ok ? ld4(gp + H + uq) : z4; o.gg[q] = ok ? ld4(gp + 2 * H + uq) : z4;
+        o.go[q] = ok ? ld4(gp + 3 * H + uq) : z4;
+        o.c4[q] = ok ? ld4(cc + uq) : z4; o.cp4[q] = (ok && cpp) ? ld4(cpp + uq) : z4; o.dh4[q] = ok ? ld4(dho + uq) : z4;
       }
-      if (ok) {
-        const float iv[4] = {gi.x, gi.y, gi.z, gi.w}, fv[4] = {gf.x, gf.y, gf.z, gf.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w},
-                    ov[4] = {go.x, go.y, go.z, go.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w}, pv[4] = {cp4.x, cp4.y, cp4.z, cp4.w},
-                    dv[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, kv[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
-        float di[4], df[4], dg[4], dO[4], dk[4];
+      return o;
+    };
+    auto load_dc = [&](int c) {
+      const int u = u0 + uh * 32 + c * 8;
+      const bool ok = rok && u < H && !first;
+      Dc d;
+      d.v[0] = ok ? ld4(dcs + u) : z4;
+      d.v[1] = ok ? ld4(dcs + u + 4) : z4;
+      return d;
+    };
+    Ops cur = load_ops(0);
+    pdl_wait();
+    Dc dc_cur = load_dc(0);
+    bool live = true;
+    if (KT > 0) {
+      live = mbar_wait(DONE, 0, s_abort, p.gerr, 79);
+      tc_fence_after();
+    }
+    if (live) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float tc = tanhf(cv[i]);
-          const float dh = dv[i] + rec[i];
-          const float d_o = dh * tc;
-          const float dct = kv[i] + dh * ov[i] * (1.f - tc * tc);
-          di[i] = dct * gv[i] * iv[i] * (1.f - iv[i]);
-          df[i] = dct * pv[i] * fv[i] * (1.f - fv[i]);
-          dg[i] = dct * iv[i] * (1.f - gv[i] * gv[i]);
-          dO[i] = d_o * ov[i] * (1.f - ov[i]);
-          dk[i] = dct * fv[i];
+      for (int c = 0; c < 4; ++c) {
+        const int u = u0 + uh * 32 + c * 8;
+        const bool ok = rok && u < H;
+        Ops nxt = cur;
+        Dc dc_nxt = dc_cur;
+        if (c + 1 < 4) { nxt = load_ops(c + 1); dc_nxt = load_dc(c + 1); }
+        float rec[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (KT > 0) tmem_ld8(taddr + (uint32_t)(uh * 32 + c * 8), rec);
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float iv[4] = {cur.gi[q].x, cur.gi[q].y, cur.gi[q].z, cur.gi[q].w}, fv[4] = {cur.gf[q].x, cur.gf[q].y, cur.gf[q].z, cur.gf[q].w},
+                        gv[4] = {cur.gg[q].x, cur.gg[q].y, cur.gg[q].z, cur.gg[q].w}, ov[4] = {cur.go[q].x, cur.go[q].y, cur.go[q].z, cur.go[q].w},
+                        cv[4] = {cur.c4[q].x, cur.c4[q].y, cur.c4[q].z, cur.c4[q].w}, pv[4] = {cur.cp4[q].x, cur.cp4[q].y, cur.cp4[q].z, cur.cp4[q].w},
+                        dv[4] = {cur.dh4[q].x, cur.dh4[q].y, cur.dh4[q].z, cur.dh4[q].w},
+                        kv[4] = {dc_cur.v[q].x, dc_cur.v[q].y, dc_cur.v[q].z, dc_cur.v[q].w};
+            float di[4], df[4], dg[4], dO[4], dk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float tc = tanh_ex2(cv[i]);
+              const float dh = dv[i] + rec[4 * q + i];
+              const float d_o = dh * tc;
+              const float dct = kv[i] + dh * ov[i] * (1.f - tc * tc);
+              di[i] = dct * gv[i] * iv[i] * (1.f - iv[i]);
+              df[i] = dct * pv[i] * fv[i] * (1.f - fv[i]);
+              dg[i] = dct * iv[i] * (1.f - gv[i] * gv[i]);
+              dO[i] = d_o * ov[i] * (1.f - ov[i]);
+              dk[i] = dct * fv[i];
+            }
+            const int uq = u + 4 * q;
+            st4(gp + uq, make_float4(di[0], di[1], di[2], di[3]));
+            st4(gp + H + uq, make_float4(df[0], df[1], df[2], df[3]));
+            st4(gp + 2 * H + uq, make_float4(dg[0], dg[1], dg[2], dg[3]));
+            st4(gp + 3 * H + uq, make_float4(dO[0], dO[1], dO[2], dO[3]));
+            st4(dcs + uq, make_float4(dk[0], dk[1], dk[2], dk[3]));
+          }
         }
-        st4(gp + u, make_float4(di[0], di[1], di[2], di[3]));
-        st4(gp + H + u, make_float4(df[0], df[1], df[2], df[3]));
-        st4(gp + 2 * H + u, make_float4(dg[0], dg[1], dg[2], dg[3]));
-        st4(gp + 3 * H + u, make_float4(dO[0], dO[1], dO[2], dO[3]));
-        st4(dcs + u, make_float4(dk[0], dk[1], dk[2], dk[3]));
+        cur = nxt;
+        dc_cur = dc_nxt;
       }
     }
   }
@@ -628,6 +702,22 @@ bool make_map_time(CUtensorMap* m, const float* base, int64_t K, int64_t B, int6
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Launch of one timestep kernel with programmatic stream serialisation (the kernels call griddepcontrol.wait before they
+// touch anything the previous launch wrote); WGG_PDL=0 falls back to ordinary stream order.
+template <class P>
+int launch_step(wgg_ctx* ctx, void (*kernel)(const P), dim3 grid, size_t smem, cudaStream_t st, const P& prm, const char* name) {
+  static const bool pdl = [] { const char* e = getenv("WGG_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, prm);
+  return wgg_check_launch(ctx, name);
+}
+
 }  // namespace gtc
 
 // The fused per-step kernels take the scaled recurrence in the tensor-core math modes when every 16-byte access they make
@@ -651,8 +741,10 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
   }
   prm.gates = gates; prm.hseq = hseq; prm.cseq = cseq; prm.cstate = cstate;
   prm.T = T; prm.B = (int)B; prm.H = H; prm.store = store; prm.gerr = ctx->async_err;
-  constexpr size_t smem = (size_t)gtc::SNST * (gtc::SA_BYTES + gtc::SB_BYTES) + 64 + 16 + 1024;
-  if (!wgg_smem_ok(ctx, gtc::gemm_tc_lstm_fwd_kernel, smem))
+  static const int nst = [] { const char* e = getenv("WGG_STEP_NST"); const int v = e ? atoi(e) : 3; return v == 2 || v == 4 ? v : 3; }();
+  const size_t smem = (size_t)nst * (gtc::SA_BYTES + gtc::SB_BYTES) + 128 + 16 + 1024;
+  void (*kernel)(const gtc::StepFwdParams) = nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4> : gtc::gemm_tc_lstm_fwd_kernel<3>;
+  if (!wgg_smem_ok(ctx, kernel, smem))
     return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);
   for (int step = 0; step < T; ++step) {
@@ -660,8 +752,7 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
     ProfScope prof(ctx, "gemm_tc_lstm_fwd_kernel", st, step > 0 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
                    4.0 * 2 * ((double)B * (step > 0 ? H : 0) + (double)B * 4 * H * (store ? 2 : 1) + 3.0 * B * H),
                    "gemm_tc_lstm_fwd_kernel");
-    gtc::gemm_tc_lstm_fwd_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
-    WGG_CHECK_LAUNCH(ctx, "gemm_tc_lstm_fwd_kernel");
+    WGG_TRY(gtc::launch_step(ctx, kernel, grid, smem, st, prm, "gemm_tc_lstm_fwd_kernel"));
   }
   return WGG_OK;
 }
@@ -697,8 +788,7 @@ int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, 
     prm.step = step;
     ProfScope prof(ctx, "gemm_tc_lstm_bwd_kernel", st, step < T - 1 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
                    4.0 * 2 * ((double)B * 4 * H * (step < T - 1 ? 3 : 2) + 5.0 * B * H), "gemm_tc_lstm_bwd_kernel");
-    gtc::gemm_tc_lstm_bwd_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
-    WGG_CHECK_LAUNCH(ctx, "gemm_tc_lstm_bwd_kernel");
+    WGG_TRY(gtc::launch_step(ctx, gtc::gemm_tc_lstm_bwd_kernel, grid, smem, st, prm, "gemm_tc_lstm_bwd_kernel"));
   }
   return WGG_OK;
 }

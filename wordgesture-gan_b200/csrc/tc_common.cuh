@@ -125,6 +125,37 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// LSTM cell from the four pre-activations with 5 EX2 + 2 RCP: sigma(x) = 1/(1+E), E = 2^(-x log2 e); tanh(x) = (1-E2)/(1+E2),
+// E2 = 2^(-2x log2 e); the sigmoids / tanh of a unit share their reciprocals (exponents capped at 40 so that products of
+// three (1+E) stay finite; 2^-40 is below fp32 resolution of the gate values).  Accurate to ~1e-7.
+__device__ __forceinline__ void lstm_cell_fast(float xi, float xf, float xg, float xo, float c_prev, float& ig, float& fg,
+                                               float& gg, float& og, float& c, float& h) {
+  const float Ei = ex2_fast(fminf(xi * -kLog2e, 40.f));
+  const float Ef = ex2_fast(fminf(xf * -kLog2e, 40.f));
+  const float Eg = ex2_fast(fminf(xg * (-2.f * kLog2e), 40.f));
+  const float Eo = ex2_fast(fminf(xo * -kLog2e, 40.f));
+  const float pi = 1.f + Ei, pf = 1.f + Ef, pg = 1.f + Eg, po = 1.f + Eo;
+  const float pfpi = pf * pi;
+  const float r1 = rcp_fast(pfpi * pg);
+  const float tg = r1 * pg;
+  ig = tg * pf;
+  fg = tg * pi;
+  const float qg = r1 * pfpi;  // 1 / (1 + Eg)
+  gg = fmaf(-Eg, qg, qg);      // tanh
+  c = fmaf(fg, c_prev, ig * gg);
+  const float Ec = ex2_fast(fminf(c * (-2.f * kLog2e), 40.f));
+  const float pc = 1.f + Ec;
+  const float r2 = rcp_fast(po * pc);
+  og = r2 * pc;
+  h = fmaf(-Ec, r2, r2);       // og * tanh(c)
+}
+// tanh(x) = (1 - E) / (1 + E), E = 2^(-2x log2 e)
+__device__ __forceinline__ float tanh_ex2(float x) {
+  const float E = ex2_fast(fminf(x * (-2.f * kLog2e), 40.f));
+  const float r = rcp_fast(1.f + E);
+  return fmaf(-E, r, r);
+}
+
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
