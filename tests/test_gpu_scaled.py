@@ -49,13 +49,14 @@ def test_generator_any_hidden_size(mode, ocfg, B, seed):
     assert worst <= grad_tol and e_dz <= grad_tol, (worst, e_dz)
 
 
-@pytest.mark.parametrize("H,B,T", [(128, 300, 12), (256, 129, 6), (64, 520, 10)])
-def test_generator_large_batch_tcgen05_gemm(H, B, T):
+@pytest.mark.parametrize("H,B,T,L", [(128, 300, 12, 2), (256, 129, 6, 2), (64, 520, 10, 2), (128, 260, 9, 3), (256, 132, 8, 2)])
+def test_generator_large_batch_tcgen05_gemm(H, B, T, L):
     """Batches large enough (M >= 128) for the TMA-fed tcgen05 GEMM (csrc/gemm_tc.cu) to take the input projection and
     the per-step recurrent product in mode tf32: ragged M tiles (B not a multiple of 256), N = 4H in {256, 512, 1024},
-    K in {64 ... 512}; forward and gradients against the fp64 oracle."""
+    K in {64 ... 512}; forward and gradients against the fp64 oracle.  With B a multiple of 4 the weight and input
+    gradients of layers >= 1 also run on it (split-K over K = T * B, transposed TF32 operand images, csrc/lstm.cu)."""
     from wgg_b200 import _lib
-    ocfg = O.ModelCfg(seq_length=T, gen_hidden_dim=H, gen_num_layers=2)
+    ocfg = O.ModelCfg(seq_length=T, gen_hidden_dim=H, gen_num_layers=L)
     wgg.set_math_mode("tf32")
     try:
         torch.manual_seed(H)
@@ -69,10 +70,14 @@ def test_generator_large_batch_tcgen05_gemm(H, B, T):
         zt = to_t(z).requires_grad_(True)
         y = G(to_t(proto), zt)
         used = _lib.profile_read(DEV)["launches"]
-        _lib.profile_enable(DEV, None)
+        _lib.profile_enable(DEV, "gemm_tc_nt")
         y.backward(to_t(dy))
         torch.cuda.synchronize()
+        bwd_tags = {r["tag"] for r in _lib.profile_report(DEV)}
+        _lib.profile_enable(DEV, None)
         assert _lib.async_error(DEV) == 0
+        if H >= 128 and B % 4 == 0:
+            assert {"gemm_tc/lstm_dWih", "gemm_tc/lstm_dWhh", "gemm_tc/lstm_dx"} <= bwd_tags, bwd_tags
         # H = 64 keeps its persistent recurrent kernel: only layer 1's input projection qualifies there
         assert used >= (1 if H <= 64 else T), f"the tcgen05 GEMM / fused step kernels took only {used} launches"
         e_fwd = max_abs_rel(to_np(y), y_ref)

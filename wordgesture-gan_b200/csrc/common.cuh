@@ -161,6 +161,11 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
                          float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st);
 int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
                           int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st);
+// K-major (transposed, TF32-rounded) operand images + tcgen05 split-K GEMMs for the weight / input gradients of the scaled path
+bool lstm_wgrad_tc_usable(const wgg_ctx* ctx, int H, int64_t B, int T);
+int transpose_tf32_launch(wgg_ctx* ctx, const float* in, int64_t ld_in, int64_t bs_in, float* out, int64_t ld_out,
+                          int64_t bs_out, int64_t R, int C, int nbatch, cudaStream_t st);
+int transpose_image_launch(wgg_ctx* ctx, const float* in, int64_t in_bs, float* out, int N, int K, int nbatch, cudaStream_t st);
 // workspace (floats) a split-K GEMM of this shape may need
 int64_t gemm_splitk_ws_floats(int64_t M, int64_t N, int nbatch);
 int gemm_choose_splitk(wgg_ctx* ctx, int64_t M, int64_t N, int64_t K, int nbatch);

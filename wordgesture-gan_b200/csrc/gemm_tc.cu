@@ -34,6 +34,9 @@ struct Params {
   const float* bias[2];
   const float* bias2[2];
   int M, N, K, ldc, accumulate;
+  // split-K: blockIdx.z = batch entry * splits + split; a split contracts k in [split * k_len, (split + 1) * k_len) (k_len a
+  // multiple of BK) and writes its own dense [M][N] slice of the partial buffer (c[z] + split * M * N); splits == 1: plain
+  int splits, k_len;
   int* gerr;
 };
 
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
   volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
   float* s_bias = reinterpret_cast<float*>(s_tmem + 4);  // [BN] bias + bias2 of this column tile (16-byte aligned)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int z = blockIdx.z;
+  const int z = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const uint32_t bar0 = smem_u32(s_bar);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -84,7 +87,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int KT = (p.K + BK - 1) / BK;
+  const int k_begin = split * p.k_len;
+  const int k_end = k_begin + p.k_len < p.K ? k_begin + p.k_len : p.K;  // the last split's ragged tail is zero-filled by TMA
+  const int KT = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
         const int s = it % NST;
         if (!mbar_wait(EMPTY(s), (uint32_t)(((it / NST) & 1) ^ 1), s_abort, p.gerr, 71)) break;
         mbar_expect_tx(FULL(s), 2 * TILE_BYTES);
-        tma_load_2d(smem_u32(s_a + s * TILE_BYTES), &p.a[z], it * BK, m0, FULL(s));
-        tma_load_2d(smem_u32(s_b + s * TILE_BYTES), &p.b[z], it * BK, n0, FULL(s));
+        tma_load_2d(smem_u32(s_a + s * TILE_BYTES), &p.a[z], k_begin + it * BK, m0, FULL(s));
+        tma_load_2d(smem_u32(s_b + s * TILE_BYTES), &p.b[z], k_begin + it * BK, n0, FULL(s));
       }
     }
   } else if (warp == 1) {
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
       }
       __syncwarp();
     }
-    if (ok && elect_one()) mma_commit(DONE);
+    if (ok && KT > 0 && elect_one()) mma_commit(DONE);
     __syncwarp();
   } else {
     // a warp may read the TMEM lanes 32 * (warp id % 4) ... + 31; the second group of four warps takes the upper column half
@@ -130,9 +135,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
       s_bias[et] = b;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
     }
-    if (mbar_wait(DONE, 0, s_abort, p.gerr, 73)) {
+    if (KT == 0 || mbar_wait(DONE, 0, s_abort, p.gerr, 73)) {
       tc_fence_after();
-      float* C = p.c[z];
+      float* C = p.c[z] + (int64_t)split * p.M * p.N;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int row = m0 + half * 128 + quarter * 32 + lane;
@@ -149,6 +154,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
           }
           float v[32];
           tmem_ld32(taddr + c0, v);  // warp-collective: every lane takes part, also for rows beyond M
+          if (KT == 0) {             // an empty split (cannot happen with the launcher's split choice) contributes zeros
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
           if (row < p.M) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -594,10 +603,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
               const float dh = dv[i] + rec[4 * q + i];
               const float d_o = dh * tc;
               const float dct = kv[i] + dh * ov[i] * (1.f - tc * tc);
-              di[i] = dct * gv[i] * iv[i] * (1.f - iv[i]);
-              df[i] = dct * pv[i] * fv[i] * (1.f - fv[i]);
-              dg[i] = dct * iv[i] * (1.f - gv[i] * gv[i]);
-              dO[i] = d_o * ov[i] * (1.f - ov[i]);
+              // da is an MMA operand three times over (next launch, dx, dW): round to nearest instead of letting the
+              // tensor core truncate
+              di[i] = rna_tf32(dct * gv[i] * iv[i] * (1.f - iv[i]));
+              df[i] = rna_tf32(dct * pv[i] * fv[i] * (1.f - fv[i]));
+              dg[i] = rna_tf32(dct * iv[i] * (1.f - gv[i] * gv[i]));
+              dO[i] = rna_tf32(d_o * ov[i] * (1.f - ov[i]));
               dk[i] = dct * fv[i];
             }
             const int uq = u + 4 * q;
@@ -634,21 +645,84 @@ __global__ void transpose_image_kernel(const float* __restrict__ in, int64_t in_
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int k = k0 + i, n = n0 + threadIdx.x;
-    if (k < K && n < N) dst[(int64_t)k * N + n] = tile[threadIdx.x][i];
+    if (k < K && n < N) dst[(int64_t)k * N + n] = rna_tf32(tile[threadIdx.x][i]);
+  }
+}
+
+// out[b][c][r] = tf32_rna(in[b][r][c])  (r < R rows of stride ld_in, c < C; out rows of stride ld_out): the K-major images of
+// the weight-gradient operands (K = T * B runs along the rows of da / the layer input, the transpose of what TMA +
+// tcgen05.mma kind::tf32 can take at full rate).  64 x 64 tiles, 16-byte accesses on both sides.
+__global__ void __launch_bounds__(256) transpose_tf32_kernel(const float* __restrict__ in, int64_t ld_in, int64_t bs_in,
+                                                             float* __restrict__ out, int64_t ld_out, int64_t bs_out, int64_t R,
+                                                             int C) {
+  __shared__ float tile[64][65];
+  const float* src = in + (int64_t)blockIdx.z * bs_in;
+  float* dst = out + (int64_t)blockIdx.z * bs_out;
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 floats each along the contiguous side
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 16 * i;
+    const int c = c0 + 4 * tx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R && c < C) v = *reinterpret_cast<const float4*>(src + r * ld_in + c);  // C % 4 == 0
+    tile[ty + 16 * i][4 * tx] = v.x; tile[ty + 16 * i][4 * tx + 1] = v.y;
+    tile[ty + 16 * i][4 * tx + 2] = v.z; tile[ty + 16 * i][4 * tx + 3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 16 * i;
+    const int64_t r = r0 + 4 * tx;
+    if (c < C && r < R) {  // R % 4 == 0
+      const float4 v = make_float4(rna_tf32(tile[4 * tx][ty + 16 * i]), rna_tf32(tile[4 * tx + 1][ty + 16 * i]),
+                                   rna_tf32(tile[4 * tx + 2][ty + 16 * i]), rna_tf32(tile[4 * tx + 3][ty + 16 * i]));
+      *reinterpret_cast<float4*>(dst + (int64_t)c * ld_out + r) = v;
+    }
   }
 }
 
 }  // namespace gtc
 
+int transpose_tf32_launch(wgg_ctx* ctx, const float* in, int64_t ld_in, int64_t bs_in, float* out, int64_t ld_out,
+                          int64_t bs_out, int64_t R, int C, int nbatch, cudaStream_t st) {
+  if ((R & 3) || (C & 3) || (ld_in & 3) || (ld_out & 3) || (bs_in & 3) || (bs_out & 3) ||
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return wgg_fail(ctx, WGG_EINVAL, "transpose_tf32: operands must be 16-byte aligned with dimensions %% 4 == 0%s");
+  dim3 grid((unsigned)cdiv64(R, 64), (unsigned)cdiv64(C, 64), (unsigned)nbatch);
+  ProfScope prof(ctx, "transpose_tf32_kernel", st, 0.0, 8.0 * (double)R * C * nbatch, "transpose_tf32_kernel");
+  gtc::transpose_tf32_kernel<<<grid, 256, 0, st>>>(in, ld_in, bs_in, out, ld_out, bs_out, R, C);
+  WGG_CHECK_LAUNCH(ctx, "transpose_tf32_kernel");
+  return WGG_OK;
+}
+
+// W^T images for the input-gradient GEMM: out[d][k][n] = in[d][n][k] (n < N rows, k < K columns of a row-major weight)
+int transpose_image_launch(wgg_ctx* ctx, const float* in, int64_t in_bs, float* out, int N, int K, int nbatch, cudaStream_t st) {
+  dim3 g((unsigned)cdiv64(K, 32), (unsigned)cdiv64(N, 32), (unsigned)nbatch);
+  gtc::transpose_image_kernel<<<g, dim3(32, 8), 0, st>>>(in, in_bs, out, N, K);
+  WGG_CHECK_LAUNCH(ctx, "transpose_image_kernel");
+  return WGG_OK;
+}
+
+// The weight-gradient / input-gradient GEMMs of the step-by-step (scaled) LSTM path can take the tcgen05 engine when the
+// transposed images are 16-byte addressable: T * B and B multiples of 4 (time shifts are column offsets of B floats).
+bool lstm_wgrad_tc_usable(const wgg_ctx* ctx, int H, int64_t B, int T) {
+  return ctx->math_mode >= 1 && H >= 32 && (H & 7) == 0 && (B & 3) == 0 && (int64_t)T * B >= 1024 && gtc::encode_fn() != nullptr;
+}
+
 // Can this contraction go through the tcgen05 GEMM?  (fully contiguous-K operands, 16-byte aligned rows, unit column
 // stride of C, no activation, no conv window, no split-K)
 bool gemm_tc_usable(const wgg_ctx* ctx, const GemmP& p) {
-  if (ctx->math_mode < 1 || p.force_fp32 || p.conv_mode || p.splitk > 1 || p.act != ACT_NONE || p.rowsum) return false;
+  if (ctx->math_mode < 1 || p.force_fp32 || p.conv_mode || p.act != ACT_NONE || p.rowsum) return false;
+  // split-K (the weight gradients: K = T * B) goes through the dense partial buffer and the fixed-order reduction
+  if (p.splitk > 1 && (!p.partial || p.bias || p.bias2 || p.scm != p.N)) return false;
   if (p.sak != 1 || p.sbk != 1 || p.scn != 1 || p.nbatch > 2) return false;
   if ((p.sam & 3) || (p.sbn & 3) || (p.scm & 3) || (p.N & 3) || (p.K & 3)) return false;
   if (p.M < 128 || p.N < 128 || p.K < 32) return false;  // small problems stay on the mma.sync engine
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al(p.A) || !al(p.B) || !al(p.C) || (p.bias && !al(p.bias)) || (p.bias2 && !al(p.bias2))) return false;
+  if (p.splitk > 1 && !al(p.partial)) return false;
   if (p.nbatch == 2 && ((p.bsA & 3) || (p.bsB & 3) || (p.bsC & 3) || (p.bsBias & 3))) return false;
   return gtc::encode_fn() != nullptr;
 }
@@ -656,23 +730,45 @@ bool gemm_tc_usable(const wgg_ctx* ctx, const GemmP& p) {
 int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   gtc::Params prm;
   memset(&prm, 0, sizeof(prm));
+  // split-K: the caller's split count was chosen for the mma.sync tiling; this engine picks its own (one wave of 256 x 256
+  // tiles, at least 8 k-slabs per split, within the partial buffer's capacity of 128 slices)
+  int splits = 1;
+  int64_t k_len = ((p.K + gtc::BK - 1) / gtc::BK) * gtc::BK;
+  if (p.splitk > 1) {
+    const int64_t tiles = cdiv64(p.N, gtc::BN) * cdiv64(p.M, gtc::BM) * p.nbatch;
+    const int64_t kt = cdiv64(p.K, gtc::BK);
+    int64_t want = cdiv64(ctx->sm_count, tiles);
+    if (want > kt / 8) want = kt / 8;
+    if (want > 128) want = 128;
+    if (want < 1) want = 1;
+    k_len = cdiv64(kt, want) * gtc::BK;
+    splits = (int)cdiv64(p.K, k_len);  // no empty split
+  }
+  const bool split = p.splitk > 1;
   for (int z = 0; z < p.nbatch; ++z) {
     if (!gtc::make_map(&prm.a[z], p.A + z * p.bsA, p.M, p.K, p.sam) || !gtc::make_map(&prm.b[z], p.B + z * p.bsB, p.N, p.K, p.sbn))
       return wgg_fail(ctx, WGG_ECUDA, "gemm_tc: cuTensorMapEncodeTiled failed%s");
-    prm.c[z] = p.C + z * p.bsC;
+    prm.c[z] = split ? p.partial + (int64_t)z * splits * p.M * p.N : p.C + z * p.bsC;
     prm.bias[z] = p.bias ? p.bias + z * p.bsBias : nullptr;
     prm.bias2[z] = p.bias2 ? p.bias2 + z * p.bsBias : nullptr;
   }
-  prm.M = (int)p.M; prm.N = (int)p.N; prm.K = (int)p.K; prm.ldc = (int)p.scm; prm.accumulate = p.accumulate;
+  prm.M = (int)p.M; prm.N = (int)p.N; prm.K = (int)p.K; prm.ldc = split ? (int)p.N : (int)p.scm;
+  prm.accumulate = split ? 0 : p.accumulate;
+  prm.splits = splits; prm.k_len = (int)k_len;
   prm.gerr = ctx->async_err;
   constexpr size_t smem = (size_t)2 * gtc::NST * gtc::TILE_BYTES + 64 + 16 + gtc::BN * 4 + 1024;
   if (!wgg_smem_ok(ctx, gtc::gemm_tc_nt_kernel, smem)) return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_nt_kernel: cannot reserve shared memory%s");
-  dim3 grid((unsigned)cdiv64(p.N, gtc::BN), (unsigned)cdiv64(p.M, gtc::BM), (unsigned)p.nbatch);
-  ProfScope prof(ctx, "gemm_tc_nt_kernel", st, 2.0 * p.M * (double)p.N * p.K * p.nbatch,
-                 4.0 * p.nbatch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * (p.accumulate ? 2 : 1)),
-                 p.tag ? p.tag : "gemm_tc_nt_kernel");
-  gtc::gemm_tc_nt_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
-  WGG_CHECK_LAUNCH(ctx, "gemm_tc_nt_kernel");
+  dim3 grid((unsigned)cdiv64(p.N, gtc::BN), (unsigned)cdiv64(p.M, gtc::BM), (unsigned)(p.nbatch * splits));
+  {
+    ProfScope prof(ctx, "gemm_tc_nt_kernel", st, 2.0 * p.M * (double)p.N * p.K * p.nbatch,
+                   4.0 * p.nbatch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * (p.accumulate ? 2 : 1)),
+                   p.tag ? p.tag : "gemm_tc_nt_kernel");
+    gtc::gemm_tc_nt_kernel<<<grid, gtc::THREADS, smem, st>>>(prm);
+    WGG_CHECK_LAUNCH(ctx, "gemm_tc_nt_kernel");
+  }
+  if (split)
+    WGG_TRY(reduce_partials_launch(ctx, p.partial, splits, p.M * p.N, p.nbatch, (int64_t)splits * p.M * p.N, p.C, nullptr,
+                                   p.bsC, p.accumulate, st));
   return WGG_OK;
 }
 
@@ -765,11 +861,7 @@ int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, 
   float* dcs = scratch;
   float* wt = scratch + ((2 * B * (int64_t)H + 3) & ~(int64_t)3);  // keep the image 16-byte aligned
   if (reinterpret_cast<uintptr_t>(wt) & 15) wt += 4 - ((reinterpret_cast<uintptr_t>(wt) & 15) >> 2);
-  {
-    dim3 g((unsigned)cdiv64(H, 32), (unsigned)cdiv64(4 * H, 32), 2);
-    gtc::transpose_image_kernel<<<g, dim3(32, 8), 0, st>>>(lp + off_whh, dir_stride, wt, 4 * H, H);
-    WGG_CHECK_LAUNCH(ctx, "transpose_image_kernel");
-  }
+  WGG_TRY(transpose_image_launch(ctx, lp + off_whh, dir_stride, wt, 4 * H, H, 2, st));
   const int64_t TB = (int64_t)T * B;
   gtc::StepBwdParams prm;
   memset(&prm, 0, sizeof(prm));

@@ -66,6 +66,41 @@ __global__ void build_x0_kernel(const float* __restrict__ proto, const float* __
   }
 }
 
+// Input projection of layer 0 in the scaled regime.  x0[t][b] = [proto[b][t][0..pd) | z[b]] (models.py:147-157): the latent
+// part does not depend on t, so  gates[d][t][b][n] = zb[d][b][n] + sum_{c < pd} proto[b][t][c] W_ih[d][n][c]  with
+// zb = z W_ih[:, pd:]^T + b_ih + b_hh computed once per gesture (a B x Z x 4H GEMM) - a write-bound fp32 pass over the gate
+// buffer instead of a K = pd + Z GEMM whose rows (35 floats) no 16-byte access or TMA box can address.
+// block = 128 threads over 4-gate-column groups of one direction; blockIdx.z strides over the (t, b) rows.
+__global__ void __launch_bounds__(128) xproj0_kernel(const float* __restrict__ proto, const float* __restrict__ zb,
+                                                     const float* __restrict__ w, int64_t dir_stride, float* __restrict__ gates,
+                                                     int T, int64_t B, int C, int pd, int I0, int H4) {
+  const int n = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (n >= H4) return;
+  const int d = blockIdx.y;
+  const int64_t TB = (int64_t)T * B;
+  float wv[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) wv[j][c] = c < pd ? __ldg(w + d * dir_stride + (int64_t)(n + j) * I0 + c) : 0.f;
+  const float* zbd = zb + (int64_t)d * B * H4 + n;
+  float* gd = gates + (int64_t)d * TB * H4 + n;
+  for (int64_t r = blockIdx.z; r < TB; r += gridDim.z) {
+    const int64_t b = r % B;
+    const int t = (int)(r / B);
+    const float* pp = proto + (b * T + t) * C;
+    float x[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = c < pd ? __ldg(pp + c) : 0.f;
+    float4 o = *reinterpret_cast<const float4*>(zbd + b * H4);
+    o.x += x[0] * wv[0][0] + x[1] * wv[0][1] + x[2] * wv[0][2] + x[3] * wv[0][3];
+    o.y += x[0] * wv[1][0] + x[1] * wv[1][1] + x[2] * wv[1][2] + x[3] * wv[1][3];
+    o.z += x[0] * wv[2][0] + x[1] * wv[2][1] + x[2] * wv[2][2] + x[3] * wv[2][3];
+    o.w += x[0] * wv[3][0] + x[1] * wv[3][1] + x[2] * wv[3][2] + x[3] * wv[3][3];
+    *reinterpret_cast<float4*>(gd + r * H4) = o;
+  }
+}
+
 // dpre[t][b][c] = dy[b][t][c] * (1 - y[b][t][c]^2)                (backward of tanh, models.py:163)
 __global__ void head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dpre,
                                 int T, int64_t B, int C) {
@@ -379,6 +414,13 @@ int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
   return backward ? 4 * B * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * B * (int64_t)H;
 }
 
+// K-major operand images of the tcgen05 weight / input-gradient GEMMs of the step-by-step path (backward only):
+// da^T [2][4H][T B] | two ping-pong h^T / input^T buffers [2H][T B] | W_ih^T [2][maxI][4H]  (+ alignment slack)
+int64_t wgrad_tc_scratch_floats(int H, int64_t TB, int64_t maxI) {
+  if (rec_has_persistent_kernel(H)) return 0;
+  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + 16;
+}
+
 int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                     float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
   const int64_t TB = (int64_t)T * B;
@@ -508,14 +550,17 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   if (gen_layout(cfg, &g) != WGG_OK) return -1;
   const int64_t TB = (int64_t)g.T * B;
   if (!backward) {  // no-grad forward: x0 + two hseq + gates (FMA path) or the tcgen05 path's buffers
-    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0);
+    // + zb [2][B][4H] of the scaled regime's layer-0 input projection (xproj0_kernel)
+    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0) +
+                         (rec_has_persistent_kernel(g.H) ? 0 : 8 * B * (int64_t)g.H + 8);
     const int64_t tcw = generator_tc_workspace_floats(cfg, B);
     return simt > tcw ? simt : tcw;
   }
   const int64_t maxI = g.I0 > 2 * g.H ? g.I0 : 2 * g.H;
   // dpre | dh | dx | split-K partials | column-sum scratch | (tcgen05 path: its own backward workspace)
   return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2) +
-         generator_tc_bwd_workspace_floats(cfg, B) + rec_generic_scratch_floats(g.H, B, 1);
+         generator_tc_bwd_workspace_floats(cfg, B) + rec_generic_scratch_floats(g.H, B, 1) +
+         wgrad_tc_scratch_floats(g.H, TB, maxI);
 }
 
 extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
@@ -550,8 +595,19 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     gates_ws = hbuf[1] + TB * 2 * g.H;
     rec_scratch = gates_ws + TB * 8 * g.H;
   }
-  build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sv.x0, g.T, B, g.C, g.pd, g.Z);
-  WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
+  // scaled regime: layer 0's input projection without materialising x0 (the stash still gets x0: the backward reads it)
+  float* zb = nullptr;
+  if (!rec_has_persistent_kernel(g.H) && g.pd <= 4 && ws) {
+    const int64_t base = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0);
+    float* q = ws + base;
+    if (reinterpret_cast<uintptr_t>(q) & 15) q += 4 - ((reinterpret_cast<uintptr_t>(q) & 15) >> 2);
+    const float* g0 = stash ? sv.gates[0] : gates_ws;
+    if (q + 8 * B * (int64_t)g.H <= ws + ws_floats && (reinterpret_cast<uintptr_t>(g0) & 15) == 0) zb = q;
+  }
+  if (stash || !zb) {
+    build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sv.x0, g.T, B, g.C, g.pd, g.Z);
+    WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
+  }
   const float* in = sv.x0;
   float* hout = nullptr;
   for (int l = 0; l < g.L; ++l) {
@@ -560,14 +616,30 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     float* gates = stash ? sv.gates[l] : gates_ws;
     float* cseq = stash ? sv.cseq[l] : nullptr;
     hout = stash ? sv.hseq[l] : hbuf[l & 1];
-    GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
-    p.tag = "gemm_kernel/lstm_xproj";
-    p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
-    p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
-    p.C = gates; p.scm = 4 * g.H; p.scn = 1;
-    p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
-    p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
-    WGG_TRY(gemm_launch(ctx, p, st));
+    if (l == 0 && zb) {
+      GemmP q;  // zb[d] (B x 4H) = z * W_ih[d][:, pd:]^T + b_ih[d] + b_hh[d]     (fp32)
+      q.tag = "gemm_kernel/lstm_xproj0_z";
+      q.A = z; q.M = B; q.K = g.Z; q.sam = g.Z; q.sak = 1;
+      q.B = lp + g.pd; q.N = 4 * g.H; q.sbk = 1; q.sbn = I;
+      q.C = zb; q.scm = 4 * g.H; q.scn = 1;
+      q.nbatch = 2; q.bsA = 0; q.bsB = g.dir_stride[l]; q.bsC = B * 4 * g.H; q.bsBias = g.dir_stride[l];
+      q.bias = lp + g.off_bih[l]; q.bias2 = lp + g.off_bhh[l]; q.force_fp32 = 1;
+      WGG_TRY(gemm_launch(ctx, q, st));
+      int64_t gz = TB < 4096 ? TB : 4096;
+      dim3 grid((unsigned)cdiv64(g.H, 128), 2, (unsigned)gz);
+      ProfScope prof(ctx, "xproj0_kernel", st, 2.0 * TB * 8.0 * g.H * g.pd, 4.0 * TB * 8.0 * g.H, "xproj0_kernel");
+      xproj0_kernel<<<grid, 128, 0, st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C, g.pd, I, 4 * g.H);
+      WGG_CHECK_LAUNCH(ctx, "xproj0_kernel");
+    } else {
+      GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
+      p.tag = "gemm_kernel/lstm_xproj";
+      p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
+      p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
+      p.C = gates; p.scm = 4 * g.H; p.scn = 1;
+      p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
+      p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
+      WGG_TRY(gemm_launch(ctx, p, st));
+    }
     WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, rec_scratch, g.T, B, stash ? 1 : 0, st));
     in = hout;
   }
@@ -604,6 +676,13 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
   float* tcws = csws + colsum_ws_floats(H4, 2);
   float* rec_scratch = tcws + generator_tc_bwd_workspace_floats(cfg, B);  // dh_rec | dc of the step-by-step recurrence
+  // scaled regime, tensor-core modes: weight / input gradients as K-major tcgen05 GEMMs over transposed operand images
+  const bool wtc = !tcp && !rec_has_persistent_kernel(H) && lstm_wgrad_tc_usable(ctx, H, B, g.T);
+  float* daT = rec_scratch + rec_generic_scratch_floats(H, B, 1);
+  if (reinterpret_cast<uintptr_t>(daT) & 15) daT += 4 - ((reinterpret_cast<uintptr_t>(daT) & 15) >> 2);
+  float* hT[2] = {daT + TB * 2 * H4, daT + TB * 2 * H4 + TB * 2 * H};  // [2H][T B] each
+  float* wihT = hT[1] + TB * 2 * H;                                    // [2][I][4H]
+  int hcur = 0;                                                        // hT[hcur] = transposed output of the current layer
 
   if (tcp) {
     // head and LSTM stack backward run entirely on the tcgen05 path (fused head, BPTT, dx and dW/db kernels)
@@ -637,7 +716,23 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     float* da = sv.gates[l];
     const float* in = l == 0 ? sv.x0 : sv.hseq[l - 1];
     WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, st));
-    {
+    const bool tc_ih = wtc && I >= 128 && (I & 3) == 0;   // layer 0 (I0 = C + Z columns) stays on the mma.sync engine
+    const bool tc_hh = wtc && H >= 128 && g.T > 1;
+    if (tc_ih || tc_hh) {
+      WGG_TRY(transpose_tf32_launch(ctx, da, H4, TB * H4, daT, TB, TB * H4, TB, H4, 2, st));
+      if (l == g.L - 1 && tc_hh) WGG_TRY(transpose_tf32_launch(ctx, sv.hseq[l], 2 * H, 0, hT[hcur], TB, 0, TB, 2 * H, 1, st));
+      if (tc_ih) WGG_TRY(transpose_tf32_launch(ctx, in, I, 0, hT[hcur ^ 1], TB, 0, TB, I, 1, st));
+    }
+    if (tc_ih) {
+      GemmP p;  // dW_ih[d] (4H x I) += da[d]^T (4H x TB, K-major image) * in^T (I x TB)^T
+      p.tag = "gemm_tc/lstm_dWih";
+      p.A = daT; p.M = H4; p.K = TB; p.sam = TB; p.sak = 1;
+      p.B = hT[hcur ^ 1]; p.N = I; p.sbk = 1; p.sbn = TB;
+      p.C = dlp; p.scm = I; p.scn = 1; p.accumulate = 1;
+      p.nbatch = 2; p.bsA = TB * H4; p.bsB = 0; p.bsC = g.dir_stride[l];
+      p.splitk = 2; p.partial = part;  // > 1: the tcgen05 engine chooses its own split count
+      WGG_TRY(gemm_launch(ctx, p, st));
+    } else {
       GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
       p.tag = "gemm_kernel/lstm_dWih";
       p.A = da; p.M = H4; p.K = TB; p.sam = 1; p.sak = H4;
@@ -647,7 +742,18 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 2); p.partial = part;
       WGG_TRY(gemm_launch(ctx, p, st));
     }
-    if (g.T > 1) {
+    if (tc_hh) {
+      // dW_hh[d] (4H x H) += da[d][t]^T * h[d][t_prev]: in the transposed images the time shift is a column offset of B
+      // (direction 0: da columns from B on against h columns from 0; direction 1 the other way round, h rows H..2H-1)
+      GemmP p;
+      p.tag = "gemm_tc/lstm_dWhh";
+      p.A = daT + B; p.M = H4; p.K = (int64_t)(g.T - 1) * B; p.sam = TB; p.sak = 1;
+      p.B = hT[hcur]; p.N = H; p.sbk = 1; p.sbn = TB;
+      p.C = dlp + g.off_whh[l]; p.scm = H; p.scn = 1; p.accumulate = 1;
+      p.nbatch = 2; p.bsA = TB * H4 - B; p.bsB = (int64_t)H * TB + B; p.bsC = g.dir_stride[l];
+      p.splitk = 2; p.partial = part;
+      WGG_TRY(gemm_launch(ctx, p, st));
+    } else if (g.T > 1) {
       GemmP p;  // dW_hh[d] (4H x H) += da[d][t]^T * h[d][t_prev]; time shift = pointer offset
       p.tag = "gemm_kernel/lstm_dWhh";
       p.A = da + B * H4; p.M = H4; p.K = (int64_t)(g.T - 1) * B; p.sam = 1; p.sak = H4;
@@ -657,15 +763,20 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       p.splitk = gemm_choose_splitk(ctx, p.M, p.N, p.K, 2); p.partial = part;
       WGG_TRY(gemm_launch(ctx, p, st));
     }
+    if (tc_ih) hcur ^= 1;  // the input's image is the next (lower) layer's output image
     // db_ih[d] = db_hh[d] += column sums of da[d]
     WGG_TRY(colsum_launch(ctx, da, TB, H4, H4, 2, TB * H4, dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1,
                           csws, st));
     if (l > 0 || dz) {
+      const bool tc_dx = wtc && I >= 128 && (I & 3) == 0;
+      if (tc_dx) WGG_TRY(transpose_image_launch(ctx, lp, g.dir_stride[l], wihT, H4, I, 2, st));  // W_ih^T [d][I][4H]
       for (int d = 0; d < 2; ++d) {
         GemmP p;  // dx (TB x I) (+)= da[d] * W_ih[d]
-        p.tag = "gemm_kernel/lstm_dx";
+        p.tag = tc_dx ? "gemm_tc/lstm_dx" : "gemm_kernel/lstm_dx";
         p.A = da + (int64_t)d * TB * H4; p.M = TB; p.K = H4; p.sam = H4; p.sak = 1;
-        p.B = lp + d * g.dir_stride[l]; p.N = I; p.sbk = I; p.sbn = 1;
+        if (tc_dx) { p.B = wihT + (int64_t)d * I * H4; p.sbk = 1; p.sbn = H4; }
+        else { p.B = lp + d * g.dir_stride[l]; p.sbk = I; p.sbn = 1; }
+        p.N = I;
         p.C = dx; p.scm = I; p.scn = 1; p.accumulate = d;
         WGG_TRY(gemm_launch(ctx, p, st));
       }
