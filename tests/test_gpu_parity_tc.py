@@ -302,11 +302,17 @@ def test_tc_train_batch_with_updates(tc_mode, B):
 # ring wraps (and its mbarrier phases flip) on every SM
 # ------------------------------------------------------------------------------------------------------------
 @functools.lru_cache(maxsize=None)
-def disc_reference(B):
+def disc_reference(B, T=128):
+    # the critic's parameters do not depend on the sequence length: the default model's seed-42 state serves T = 256 / 384 too
+    DEFAULT = O.ModelCfg(seq_length=T)
     p = seed42_states()["D1"]
     real, fake, _ = rand_inputs(DEFAULT, B + spare(B), 70 + B)
     tp = torch_port.TorchPortTrainer(seed=0, cfg=DEFAULT, dtype=torch.float64)
-    tp.load_state(seed42_states())
+    if T == 128:
+        tp.load_state(seed42_states())
+    else:  # the encoder's first layer is (T * 3)-wide: load the critics only
+        for m in ("D1", "D2"):
+            tp.mods[m].load_state_dict({n: torch.as_tensor(v, dtype=torch.float64) for n, v in seed42_states()[m].items()})
     rt, ft_ = torch.from_numpy(real), torch.from_numpy(fake)
 
     def calls():  # the call schedule of the test below (each call advances the power iteration)
@@ -328,9 +334,12 @@ def disc_reference(B):
     return seed42_states()["D1"], real, fake, rs, fs, grads, dx, ff, fm, dx_fm, uv
 
 
-@pytest.mark.parametrize("B", [445, 3 * 148 + 149])
-def test_tc_discriminator_ring_wrap(tc_mode, B):
-    p0, real, fake, rs_ref, fs_ref, g_ref, dx_ref, ff_ref, fm_ref, dx_fm_ref, uv_ref = disc_reference(B)
+@pytest.mark.parametrize("B,T", [(445, 128), (3 * 148 + 149, 128), (300, 256), (150, 384)])
+def test_tc_discriminator_ring_wrap(tc_mode, B, T):
+    """T = 256 (BASELINE configs[3]) / 384: a gesture is two / three 128-row MMA tiles with halo rows from the neighbouring
+    tile; with three tiles per gesture every CTA's ring stages see first, middle and last tiles in turn."""
+    DEFAULT = O.ModelCfg(seq_length=T)
+    p0, real, fake, rs_ref, fs_ref, g_ref, dx_ref, ff_ref, fm_ref, dx_fm_ref, uv_ref = disc_reference(B, T)
     D = wgg.TemporalDiscriminator(model_cfg(DEFAULT)).to(DEV).train()
     load_state(D, p0)
     ft = to_t(fake).requires_grad_(True)
@@ -352,9 +361,9 @@ def test_tc_discriminator_ring_wrap(tc_mode, B):
     with torch.no_grad():
         feats = D.get_all_features(to_t(fake))   # eval: no power iteration -> same weights as the last call above
     worst = max(per, key=per.get)
-    report(f"discriminator/{tc_mode}/B{B}", dict(fwd=e_fwd, grad_worst=per[worst], grad_worst_tensor=worst, dx=e_dx,
+    report(f"discriminator/{tc_mode}/B{B}" + (f"_T{T}" if T != 128 else ""), dict(fwd=e_fwd, grad_worst=per[worst], grad_worst_tensor=worst, dx=e_dx,
                                                  fm_loss=e_fm, fm_dx=e_dx_fm, uv=e_uv, per_tensor=per))
-    assert len(feats) == 5 and tuple(feats[0].shape) == (B, 8192)
+    assert len(feats) == 5 and tuple(feats[0].shape) == (B, 64 * T)
     assert e_fwd <= FWD_TOL, e_fwd
     assert per[worst] <= DISC_W_TOL[tc_mode], (worst, per[worst])
     assert e_dx <= DISC_DX_TOL[tc_mode] and e_dx_fm <= DISC_DX_TOL[tc_mode], (e_dx, e_dx_fm)

@@ -108,3 +108,34 @@ def test_train_batch_h128_t256():
     out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise])
     for k in LOSS_KEYS:
         assert abs(out[k].item() - ref[k]) <= 2e-3 * max(abs(ref[k]), 1e-2), (k, out[k].item(), ref[k])
+
+
+def test_train_batch_h128_t256_tf32_lr0():
+    """The same batch in mode tf32 - fused tcgen05 step kernels, split-K tcgen05 weight-gradient GEMMs and the tcgen05 conv
+    kernels on 256-point gestures (two 128-row tiles per gesture) - at learning rate 0 (the first Adam steps are sign-like
+    and would amplify TF32-level differences between critic iterations): all 11 losses at the TF32 tolerance
+    of tests/test_gpu_parity_tc.py (5e-3)."""
+    from wgg_b200 import _lib
+    ocfg = O.ModelCfg(seq_length=256, gen_hidden_dim=128, gen_num_layers=2)
+    B = 132
+    wgg.set_math_mode("tf32")
+    try:
+        wgg.seed_everything(11)
+        tr = wgg.WordGestureGANTrainer(model_cfg(ocfg), wgg.TrainingConfig(learning_rate=0.0), DEV)
+        tp = torch_port.TorchPortTrainer(seed=0, cfg=ocfg, tc=O.TrainCfg(learning_rate=0.0), dtype=torch.float64)
+        tp.load_state({m: state_of(getattr(tr, ATTR[m])) for m in ("G", "E", "D1", "D2")})
+        for m in ("G", "E", "D1", "D2"):
+            getattr(tr, ATTR[m]).train()
+        rng = np.random.default_rng(5)
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)
+        real = f32(rng.uniform(-1, 1, (B, 256, 3)))
+        proto = f32(rng.uniform(-1, 1, (B, 256, 3)))
+        noise = [f32(rng.standard_normal((B, 32))) for _ in range(13)]
+        ref = tp.train_batch(torch.from_numpy(real), torch.from_numpy(proto), noise=noise)
+        out = wgg.train_batch(tr, to_t(real), to_t(proto), 1.0, [to_t(n) for n in noise])
+        torch.cuda.synchronize()
+        assert _lib.async_error(DEV) == 0
+        for k in LOSS_KEYS:
+            assert abs(out[k].item() - ref[k]) <= 5e-3 * max(abs(ref[k]), 1e-2), (k, out[k].item(), ref[k])
+    finally:
+        wgg.set_math_mode("fp32")

@@ -261,14 +261,16 @@ int generator_backward_tc_layers(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
 // ----------------------------------------------------------------------------------------------
 // tcgen05 conv1d layers of the TemporalDiscriminator (conv_tc.cu)
 // ----------------------------------------------------------------------------------------------
+// T = sequence length: a multiple of 128 (conv_tc_seq_ok); one MMA tile = 128 time steps of one gesture
+bool conv_tc_seq_ok(int T);
 int conv_tc_fwd_launch(wgg_ctx* ctx, const float* in, const float* wimg, const float* bias, float* out,
-                       const float* act_lower, const float* dfeat, int64_t B, int CinC, int taps, int pad, int N,
+                       const float* act_lower, const float* dfeat, int64_t B, int T, int CinC, int taps, int pad, int N,
                        int mode, const char* tag, cudaStream_t st);
 int64_t conv_tc_wgrad_ws_floats(wgg_ctx* ctx, int ncols_max);
-int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int Cout, int Cin, int taps,
+int conv_tc_wgrad_launch(wgg_ctx* ctx, const float* dpre, const float* in, int64_t B, int T, int Cout, int Cin, int taps,
                          int pad, float* G, float* db, float* ws, cudaStream_t st);
-int pack_x4_launch(wgg_ctx* ctx, const float* x, float* x4, int64_t B, int C, cudaStream_t st);
-int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B, int C, cudaStream_t st);
+int pack_x4_launch(wgg_ctx* ctx, const float* x, float* x4, int64_t B, int T, int C, cudaStream_t st);
+int pool_fwd_chunk_launch(wgg_ctx* ctx, const float* a, float* pooled, int64_t B, int T, int C, cudaStream_t st);
 int unpool_leaky_chunk_launch(wgg_ctx* ctx, const float* dpool, const float* a3, const float* dfeat, float* dpre,
-                              int64_t B, int C, cudaStream_t st);
-int chunk_to_rows_launch(wgg_ctx* ctx, const float* in, float* out, int64_t B, int C, cudaStream_t st);
+                              int64_t B, int T, int C, cudaStream_t st);
+int chunk_to_rows_launch(wgg_ctx* ctx, const float* in, float* out, int64_t B, int T, int C, cudaStream_t st);

@@ -348,9 +348,10 @@ __global__ void transpose_tc_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
-// tcgen05 conv path: TemporalDiscriminator with T == 128 (= UMMA M) and <= 4 input channels, in tf32 mode
+// tcgen05 conv path: TemporalDiscriminator with T a multiple of 128 (= UMMA M; T = 256 in the scaled regime of
+// BASELINE configs[3]) and <= 4 input channels, in tf32 mode
 bool disc_use_tc(const wgg_ctx* ctx, const DLayout& d) {
-  return ctx->math_mode == 1 && d.temporal && d.T == 128 && d.C <= 4;
+  return ctx->math_mode == 1 && d.temporal && conv_tc_seq_ok(d.T) && d.C <= 4;
 }
 
 void fill_sn_args(const DLayout& d, SnArgs* a) {
@@ -450,16 +451,16 @@ extern "C" int wgg_disc_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const fl
   if (tc) {
     // conv stack on tcgen05: activations channel-chunked [B][C/4][T][4] (see conv_tc.cu)
     float* x4 = stash + d.x4_off * B;
-    WGG_TRY(pack_x4_launch(ctx, x, x4, B, d.C, st));
+    WGG_TRY(pack_x4_launch(ctx, x, x4, B, d.T, d.C, st));
     const float* in = x4;
     for (int i = 0; i < d.first_linear; ++i) {
       const DLayer& l = d.L[i];
       float* out = stash + l.out_off * B;
-      WGG_TRY(conv_tc_fwd_launch(ctx, in, sn + l.sn_tcf, params + l.off_b, out, nullptr, nullptr, B, (l.Cin + 3) / 4, l.ks,
+      WGG_TRY(conv_tc_fwd_launch(ctx, in, sn + l.sn_tcf, params + l.off_b, out, nullptr, nullptr, B, d.T, (l.Cin + 3) / 4, l.ks,
                                  l.pad, l.rows, 0, "conv_tc_fwd_kernel/fwd", st));
       in = out;
     }
-    WGG_TRY(pool_fwd_chunk_launch(ctx, in, stash + d.pooled_off * B, B, d.L[d.first_linear - 1].rows, st));
+    WGG_TRY(pool_fwd_chunk_launch(ctx, in, stash + d.pooled_off * B, B, d.T, d.L[d.first_linear - 1].rows, st));
   }
   for (int i = tc ? d.first_linear : 0; i < d.nl; ++i) {
     const DLayer& l = d.L[i];
@@ -566,22 +567,22 @@ extern "C" int wgg_disc_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const f
             const DLayer& c3 = d.L[i - 1];
             // dnext (d pooled) is consumed into dcur (dpre of the last conv layer)
             WGG_TRY(unpool_leaky_chunk_launch(ctx, dnext, stash + c3.out_off * B, dfeat ? dfeat + c3.out_off * B : nullptr,
-                                              dp_hi, B, c3.rows, st));
+                                              dp_hi, B, d.T, c3.rows, st));
           }
           for (int j = i - 1; j >= 0; --j) {
             const DLayer& c = d.L[j];
             const float* cin = j == 0 ? x4 : stash + d.L[j - 1].out_off * B;
             if (dparams)
-              WGG_TRY(conv_tc_wgrad_launch(ctx, dp_hi, cin, B, c.rows, c.Cin, c.ks, c.pad, G + c.g_off, dparams + c.off_b,
+              WGG_TRY(conv_tc_wgrad_launch(ctx, dp_hi, cin, B, d.T, c.rows, c.Cin, c.ks, c.pad, G + c.g_off, dparams + c.off_b,
                                            part, st));
             if (j > 0) {
               const DLayer& lo = d.L[j - 1];
               WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dp_lo, stash + lo.out_off * B,
-                                         dfeat ? dfeat + lo.out_off * B : nullptr, B, c.rows / 4, c.ks, c.ks - 1 - c.pad,
+                                         dfeat ? dfeat + lo.out_off * B : nullptr, B, d.T, c.rows / 4, c.ks, c.ks - 1 - c.pad,
                                          c.tc_nd, 1, "conv_tc_fwd_kernel/dgrad", st));
               float* t = dp_hi; dp_hi = dp_lo; dp_lo = t;
             } else if (dx) {
-              WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dx, nullptr, nullptr, B, c.rows / 4, c.ks,
+              WGG_TRY(conv_tc_fwd_launch(ctx, dp_hi, sn + c.sn_tcd, nullptr, dx, nullptr, nullptr, B, d.T, c.rows / 4, c.ks,
                                          c.ks - 1 - c.pad, c.tc_nd, 2, "conv_tc_fwd_kernel/dx", st));
             }
           }
