@@ -30,8 +30,12 @@ PROFILE_CANDIDATES = ("gemm_kernel", "lstm_tc_fwd_kernel", "lstm_tc_bwd_kernel",
                       "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "lstm_rec_fwd_kernel", "lstm_rec_bwd_kernel")
 
 
-# scaled regime (--hidden > 64): input projections, the fused per-timestep recurrence (forward / BPTT), everything else
-SCALED_CANDIDATES = ("gemm_kernel", "gemm_tc_nt_kernel", "gemm_tc_lstm_fwd_kernel", "gemm_tc_lstm_bwd_kernel", "lstm_cell")
+# scaled regime (--hidden > 64): input projections / weight and input gradients (tcgen05 GEMM), the persistent H = 128
+# recurrence of the no-grad passes, the fused per-timestep recurrence (forward with stash / BPTT), the critics' conv kernels,
+# operand transposes, the layer-0 projection, and what stays on the mma.sync / FMA engine
+SCALED_CANDIDATES = ("gemm_kernel", "gemm_tc_nt_kernel", "lstm128_tc_fwd_kernel", "gemm_tc_lstm_fwd_kernel",
+                     "gemm_tc_lstm_bwd_kernel", "conv_tc_fwd_kernel", "conv_tc_wgrad_kernel", "transpose_tf32_kernel",
+                     "xproj0_kernel", "lstm_cell")
 
 
 def load_peaks():

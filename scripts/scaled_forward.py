@@ -22,7 +22,7 @@ with torch.no_grad():
     e0.record(); y = G(proto, z); e1.record(); torch.cuda.synchronize()
     eager = e0.elapsed_time(e1)
     parts = []
-    for k in ("gemm_tc_nt_kernel", "gemm_tc_lstm_fwd_kernel"):
+    for k in ("gemm_tc_nt_kernel", "gemm_tc_lstm_fwd_kernel", "lstm128_tc_fwd_kernel", "xproj0_kernel"):
         _lib.profile_enable(dev, k)
         G(proto, z); torch.cuda.synchronize()
         pr = _lib.profile_read(dev)

@@ -66,10 +66,11 @@ def test_generator_large_batch_tcgen05_gemm(H, B, T, L):
         dy = np.random.default_rng(H).standard_normal((B, T, 3)).astype(np.float32).astype(np.float64)
         y_ref, stash = O.generator_fwd(p, ocfg, proto, z)
         g_ref, dz_ref = O.generator_bwd(p, ocfg, stash, dy)
-        _lib.profile_enable(DEV, "gemm_tc_")
+        _lib.profile_enable(DEV, "tc_")
         zt = to_t(z).requires_grad_(True)
         y = G(to_t(proto), zt)
-        used = _lib.profile_read(DEV)["launches"]
+        fwd_rows = {r["tag"]: r["launches"] for r in _lib.profile_report(DEV)}
+        used = sum(fwd_rows.values())
         _lib.profile_enable(DEV, "gemm_tc_nt")
         y.backward(to_t(dy))
         torch.cuda.synchronize()
@@ -78,8 +79,19 @@ def test_generator_large_batch_tcgen05_gemm(H, B, T, L):
         assert _lib.async_error(DEV) == 0
         if H >= 128 and B % 4 == 0:
             assert {"gemm_tc/lstm_dWih", "gemm_tc/lstm_dWhh", "gemm_tc/lstm_dx"} <= bwd_tags, bwd_tags
-        # H = 64 keeps its persistent recurrent kernel: only layer 1's input projection qualifies there
+        # H = 64 keeps its persistent FMA recurrent kernel: only layer 1's input projection qualifies there; H = 128 has the
+        # persistent tcgen05 kernel (one launch per layer); larger H: one fused tcgen05 launch per timestep and layer
         assert used >= (1 if H <= 64 else T), f"the tcgen05 GEMM / fused step kernels took only {used} launches"
+        if H == 128:
+            # no-grad passes (sampling, the critic phase's generations): the persistent kernel, one launch per layer, on the
+            # chunked gate buffer written by the input-projection GEMM / the layer-0 projection kernels
+            _lib.profile_enable(DEV, "tc_")
+            with torch.no_grad():
+                y_ng = G(to_t(proto), to_t(z))
+            ng_rows = {r["tag"]: r["launches"] for r in _lib.profile_report(DEV)}
+            _lib.profile_enable(DEV, None)
+            assert ng_rows.get("lstm128_tc_fwd_kernel") == L and "gemm_tc_lstm_fwd_kernel" not in ng_rows, ng_rows
+            assert max_abs_rel(to_np(y_ng), y_ref) <= 3e-3
         e_fwd = max_abs_rel(to_np(y), y_ref)
         worst = max(rel_l2(v, g_ref[k]) for k, v in grads_of(G).items())
         print(f"H={H} B={B} T={T}: {used} tcgen05 GEMM launches, fwd {e_fwd:.2e}, grads {worst:.2e}")

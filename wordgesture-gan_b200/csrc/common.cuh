@@ -146,6 +146,10 @@ struct GemmP {
   // fp32 kernels only (nbatch == 1): rowsum[m] += sum_k A(m,k) in the same pass (bias gradient of a Linear layer's
   // weight-gradient GEMM); with split-K the partial buffer holds M extra floats per split.
   float* rowsum = nullptr;
+  // tcgen05 engine only: write C (row m = t * chunk_B + b; bsC between batch entries) in the gate-buffer order of the
+  // persistent H = 128 recurrence, [t][b / 128][N / 4][b % 128][4] - callers check gemm_tc_usable() first
+  int out_chunk = 0;
+  int64_t chunk_B = 0;
 };
 
 int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
@@ -159,6 +163,13 @@ bool lstm_step_tc_usable(const wgg_ctx* ctx, int H, const float* gates, const fl
                          int64_t dir_stride);
 int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                          float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st);
+// persistent recurrence for gen_hidden_dim = 128 (one launch per layer; gemm_tc.cu)
+bool lstm128_persist_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
+                            int64_t dir_stride);
+bool lstm128_persist_rowmajor();
+// chunked = 1 (no-grad passes): gates is [2][T][ceil(B/128)][4H/4][128][4] as written by GemmP::out_chunk / xproj0_chunk
+int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                            float* cseq, int T, int64_t B, int store, int chunked, cudaStream_t st);
 int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
                           int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st);
 // K-major (transposed, TF32-rounded) operand images + tcgen05 split-K GEMMs for the weight / input gradients of the scaled path

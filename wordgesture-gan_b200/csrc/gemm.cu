@@ -697,6 +697,7 @@ int gemm_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
     return wgg_fail(ctx, WGG_EINVAL, "gemm: split-K needs a partial buffer and a plain epilogue%s");
   // large contiguous-K contractions of the tensor-core modes: tcgen05 + TMA engine (gemm_tc.cu)
   if (gemm_tc_usable(ctx, p)) return gemm_tc_launch(ctx, p, st);
+  if (p.out_chunk) return wgg_fail(ctx, WGG_EUNSUPPORTED, "gemm: the chunked gate-buffer output exists on the tcgen05 engine only%s");
   const bool tf32 = ctx->math_mode >= 1 && !p.force_fp32 && p.K >= 8 && p.M * p.N >= 4096;
   if (p.rowsum && (tf32 || p.nbatch != 1 || p.conv_mode != 0 || p.M > 2048))
     return wgg_fail(ctx, WGG_EINVAL, "gemm: row sums are only carried by the plain fp32 kernels%s");

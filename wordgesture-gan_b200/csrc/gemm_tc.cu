@@ -37,6 +37,9 @@ struct Params {
   // split-K: blockIdx.z = batch entry * splits + split; a split contracts k in [split * k_len, (split + 1) * k_len) (k_len a
   // multiple of BK) and writes its own dense [M][N] slice of the partial buffer (c[z] + split * M * N); splits == 1: plain
   int splits, k_len;
+  // out_chunk: C is the gate buffer of the persistent H = 128 recurrence, row m = t * chunk_B + b, written in the order
+  // its epilogue reads: [t][b / 128][N / 4][b % 128][4 floats] (lane = gesture: coalesced 16-byte accesses on both sides)
+  int out_chunk, chunk_B, chunk_tiles;
   int* gerr;
 };
 
@@ -146,6 +149,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_nt_kernel(const __grid_con
         for (int c0 = 0; c0 < 128; c0 += 32) {
           const int colb = chalf * 128 + c0;  // column inside the tile
           float* crow = C + (int64_t)row * p.ldc + n0 + colb;
+          if (p.out_chunk) {  // plain store, bias added; row -> (t, tile, row in tile)
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            if (row < p.M) {
+              const int t = row / p.chunk_B, b = row - t * p.chunk_B;
+              float4* dst = reinterpret_cast<float4*>(C) +
+                            (((int64_t)t * p.chunk_tiles + (b >> 7)) * (p.N >> 2) + ((n0 + colb) >> 2)) * 128 + (b & 127);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (n0 + colb + 4 * j < p.N) {
+                  const float4 bb = *reinterpret_cast<const float4*>(s_bias + colb + 4 * j);
+                  dst[(int64_t)j * 128] = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+                }
+              }
+            }
+            continue;
+          }
           float4 old[8];
           if (p.accumulate && row < p.M) {
 #pragma unroll
@@ -632,6 +652,314 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent recurrence for gen_hidden_dim = 128 (first rung of BASELINE configs[3]; torch.nn.LSTM as called at
+// src/gan/models.py:160): ONE launch per layer instead of one per timestep.  CTA = 128 gestures x one direction x all T
+// steps; the four gates of all 128 units are 512 accumulator columns = the whole TMEM of the SM, as two halves (units
+// 0..63 / 64..127, each N = 256) so that the cell math of the first half overlaps the tensor-core work of the second.
+//   * h_{t-1} never leaves the SM: the epilogue writes h_t (TF32-rounded) straight into the K-major SWIZZLE_128B operand
+//     tile of the next step (two tiles, ping-pong: the second half's MMAs of step t still read h_{t-1} while the first
+//     half's epilogue already produces h_t), besides the copy in hseq that the next layer reads;
+//   * c stays in registers (64 per epilogue thread) for all T steps;
+//   * W_hh (256 KB in fp32 containers) does not fit next to the h tiles, so it streams from L2 every step through a 3-stage
+//     TMA ring of [4 gates x 64 units] x 32-float slabs - the same boxes the per-timestep kernel uses; the ring runs ahead
+//     of the recurrence (the weights depend on nothing);
+//   * the input projection (+ biases) is read from the gate buffer with 16-byte loads issued before the wait for the tensor
+//     core; the grad-carrying variant overwrites it with the activated gates and stores c, as the per-timestep kernel does.
+// Per step the tensor pipe works 2 x 16 MMAs (M128 x N256 x K8), the XU pipe 7 MUFU per cell; the two are about balanced
+// at H = 128, and only the first half's MMAs are exposed.
+// ---------------------------------------------------------------------------------------------
+constexpr int PH = 128;                   // hidden units
+constexpr int P_HBUF = 128 * PH * 4;      // 64 KB: one h tile = 4 k-slabs of [128 rows][128 bytes]
+constexpr int P_SLAB = 128 * BK * 4;      // 16 KB
+constexpr int P_WST = 4 * SUN * BK * 4;   // 32 KB: one weight stage (4 gates x 64 units, one k-slab)
+constexpr int P_NST = 3;
+constexpr int P_KT = PH / BK;             // 4 k-slabs
+constexpr int P_THREADS = 384;            // warpgroup 0: warp 0 TMA producer, warp 1 MMA issuer; warpgroups 1, 2: epilogue
+
+struct PersistParams {
+  CUtensorMap b[2];   // per direction: W_hh [4H][H], boxes of 64 rows
+  CUtensorMap hs[2];  // per direction: h of that direction inside hseq as (k, gesture, t) - the TMA store of each h_t tile
+  float* gates;       // CHUNK: [2][T][tiles][4H / 4][128][4]; else [2][T][B][4H]
+  float* cseq;        // STORE: [2][T][B][H]
+  int T, B;
+  int l2pf;           // > 0: L2 prefetch distance (steps) for the gate blocks
+  int* gerr;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(src)
+               : "memory");
+}
+
+// STORE = 1: grad-carrying pass (row-major gate buffer overwritten with the activated gates, c stored) - BPTT and the
+// weight-gradient GEMMs read that buffer as a K-major matrix.  CHUNK = 1 (no-grad passes: sampling, the critic phase's
+// generations): the gate buffer is private scratch in the chunked order the input-projection GEMM wrote for this kernel.
+template <int STORE, int CHUNK>
+__global__ void __launch_bounds__(P_THREADS, 1) lstm128_tc_fwd_kernel(const __grid_constant__ PersistParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_h = smem;                      // two h tiles
+  uint8_t* s_w = smem + 2 * P_HBUF;         // weight ring
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + P_NST * P_WST);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(s_tmem + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int m0 = blockIdx.x * SBM;
+  const int T = p.T;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto WFULL = [&](int s) { return bar0 + 8u * s; };
+  auto WEMPTY = [&](int s) { return bar0 + 8u * (P_NST + s); };
+  auto ACC_FULL = [&](int h) { return bar0 + 8u * (2 * P_NST + h); };
+  auto H_FULL = [&](int h) { return bar0 + 8u * (2 * P_NST + 2 + h); };  // h_t units of half h are in the operand tile
+  if (tid == 0) {
+    for (int s = 0; s < P_NST; ++s) { mbar_init(WFULL(s), 1); mbar_init(WEMPTY(s), 1); }
+    mbar_init(ACC_FULL(0), 1);
+    mbar_init(ACC_FULL(1), 1);
+    mbar_init(H_FULL(0), 8);  // the 8 epilogue warps, once per half and step
+    mbar_init(H_FULL(1), 8);
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  // Register budget: 384 threads start with 168 registers each; the first warpgroup (TMA producer, MMA issuer, two idle warps)
+  // hands 112 per thread back, the two epilogue warpgroups (64 cell states + two prefetched items + the accumulator chunk per
+  // thread) take 224 - at 168 the epilogue spilled ~0.5 KB per thread into an L1 that the 224 KB of shared memory leaves at
+  // 32 KB, and the local-memory round trips to L2 were the largest stall of the kernel (ncu: long scoreboard).
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 0) {
+    if (lane == 0) {
+      // weight ring: (step, half, k-slab) in the order the issuer consumes them; no step-0 product (h_{-1} = 0)
+      int n = 0;
+      bool ok = true;
+      // the tile's input projection of one timestep is one contiguous block (256 KB for a full tile) in either layout;
+      // optionally (PersistParams::l2pf = distance in steps, off by default) it is pulled into L2 ahead of the epilogue.
+      // Measured with every SM busy: distance 2 doubles the DRAM reads (148 x 256 KB x 3 blocks in flight do not survive in
+      // L2 until they are used) and is slower than no prefetch.
+      const int tile_rows = p.B - m0 < SBM ? p.B - m0 : SBM;
+      const uint32_t blk_bytes = (uint32_t)(CHUNK ? SBM : tile_rows) * 4 * PH * 4;
+      auto gate_block = [&](int step) -> const uint8_t* {
+        const int t = dir ? T - 1 - step : step;
+        const int64_t tiles = (p.B + SBM - 1) / SBM;
+        const int64_t row = CHUNK ? (((int64_t)dir * T + t) * tiles + blockIdx.x) * SBM : ((int64_t)dir * T + t) * p.B + m0;
+        return reinterpret_cast<const uint8_t*>(p.gates) + row * (4 * PH * 4);
+      };
+      auto l2_prefetch = [&](int step) {
+        if (step >= T) return;
+        const uint8_t* src = gate_block(step);
+        for (uint32_t off = 0; off < blk_bytes; off += 32768) {
+          const uint32_t nb = blk_bytes - off < 32768 ? blk_bytes - off : 32768;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(nb) : "memory");
+        }
+      };
+      if (p.l2pf > 0)
+        for (int d = 1; d <= p.l2pf; ++d) l2_prefetch(d);
+      for (int step = 1; step < T && ok; ++step) {
+        if (p.l2pf > 0) l2_prefetch(step + p.l2pf);
+        for (int half = 0; half < 2 && ok; ++half)
+          for (int k = 0; k < P_KT; ++k, ++n) {
+            const int s = n % P_NST;
+            if (!mbar_wait(WEMPTY(s), (uint32_t)(((n / P_NST) & 1) ^ 1), s_abort, p.gerr, 81)) { ok = false; break; }
+            mbar_expect_tx(WFULL(s), P_WST);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              tma_load_2d(smem_u32(s_w + s * P_WST + g * SBOX_BYTES), &p.b[dir], k * BK, g * PH + half * SUN, WFULL(s));
+          }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, 256);
+    int n = 0;
+    bool ok = true;
+    // Issue order per step: the first two k-slabs of the first accumulator half only need the first half of h_{step-1}
+    // (units 0..63, published on H_FULL(0)) and run while the epilogue still works on the second half of the previous step;
+    // accumulator half 1 is still being read then and is touched only after H_FULL(1).
+    auto issue = [&](int half, int k0, int k1, uint32_t a0) -> bool {
+      for (int k = k0; k < k1; ++k, ++n) {
+        const int s = n % P_NST;
+        if (!mbar_wait(WFULL(s), (uint32_t)((n / P_NST) & 1), s_abort, p.gerr, 83)) return false;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b0 = smem_u32(s_w + s * P_WST);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks)
+            mma_tf32_ss(tmem_base + (uint32_t)(half * 256), desc_sw128(a0 + k * P_SLAB + ks * 32), desc_sw128(b0 + ks * 32),
+                        idesc, (k | ks) ? 1u : 0u);
+          mma_commit(WEMPTY(s));
+        }
+        __syncwarp();
+      }
+      return true;
+    };
+    for (int step = 1; step <= T && ok; ++step) {
+      const uint32_t par = (uint32_t)((step - 1) & 1);
+      const uint32_t a0 = smem_u32(s_h + ((step - 1) & 1) * P_HBUF);
+      if (!mbar_wait(H_FULL(0), par, s_abort, p.gerr, 82)) break;
+      tc_fence_after();
+      if (step < T && !issue(0, 0, 2, a0)) break;
+      // h_{step-1} complete in tile (step-1) & 1 (and with it: every accumulator read of the previous step)
+      if (!mbar_wait(H_FULL(1), par, s_abort, p.gerr, 85)) break;
+      tc_fence_after();
+      if (lane == 0) {
+        // the finished tile goes to hseq (the next layer's input) by TMA: four [128 gestures x 32 units] boxes; rows beyond
+        // the batch are clipped by the map.  The tile is overwritten by the epilogue of step + 1, which cannot start before
+        // this warp has committed that step's first accumulator half - after the wait below.
+        const int tprev = dir ? T - step : step - 1;
+#pragma unroll
+        for (int k = 0; k < P_KT; ++k) tma_store_3d(&p.hs[dir], k * BK, m0, tprev, a0 + k * P_SLAB);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued one step earlier has read its tile
+      }
+      __syncwarp();
+      if (step == T) break;
+      if (!issue(0, 2, P_KT, a0)) break;
+      if (elect_one()) mma_commit(ACC_FULL(0));
+      __syncwarp();
+      if (!issue(1, 0, P_KT, a0)) break;
+      if (elect_one()) mma_commit(ACC_FULL(1));
+      __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quarter = warp & 3, uh = (warp - 4) >> 2;
+    const int rl = quarter * 32 + lane;  // row inside the tile
+    const int row = m0 + rl;
+    const bool rok = row < p.B;
+    const int64_t r = rok ? row : 0;
+    const int64_t TB = (int64_t)T * p.B;
+    const int tiles = (p.B + SBM - 1) / SBM;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // gate-buffer row of this thread at sequence position t
+    auto gate_ptr = [&](int t) -> float* {
+      if (CHUNK) return p.gates + ((((int64_t)dir * T + t) * tiles + blockIdx.x) * (4 * PH / 4) * 128 + rl) * 4;
+      return p.gates + (((int64_t)dir * T + t) * p.B + r) * 4 * PH;
+    };
+    // 8 items per step: item q = (half q >> 2, chunk q & 3) = units [u, u + 8) of this warp's share of the half; an item's
+    // input projection (eight 16-byte loads) is requested two items ahead, across the half and the step boundary (issuing
+    // the loads only after the half's proxy fence - which waits for outstanding loads - was measured slower)
+    float4 pre[2][4][2];
+    auto load_item = [&](const float* gp, int q, int slot) {
+      const int u = (q >> 2) * SUN + uh * 32 + (q & 3) * 8;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (CHUNK) {
+          const float* a = gp + (int64_t)((g * PH + u) >> 2) * 512;
+          pre[slot][g][0] = ld4(a);
+          pre[slot][g][1] = ld4(a + 512);
+        } else {
+          pre[slot][g][0] = rok ? ld4(gp + g * PH + u) : z4;
+          pre[slot][g][1] = rok ? ld4(gp + g * PH + u + 4) : z4;
+        }
+      }
+    };
+    float creg[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) creg[a][i] = 0.f;
+    float* gp = gate_ptr(dir ? T - 1 : 0);
+    load_item(gp, 0, 0);
+    load_item(gp, 1, 1);
+    bool live = true;
+#pragma unroll 1
+    for (int step = 0; step < T && live; ++step) {
+      const int t = dir ? T - 1 - step : step;
+      float* gp_next = step + 1 < T ? gate_ptr(dir ? t - 1 : t + 1) : gp;
+      float* cout = STORE ? p.cseq + (int64_t)dir * TB * PH + ((int64_t)t * p.B + r) * PH : nullptr;
+      uint8_t* hb = s_h + (step & 1) * P_HBUF + rl * 128;  // this row inside each k-slab of the tile being produced
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int half = q >> 2, slot = q & 1;
+        const int u = half * SUN + uh * 32 + (q & 3) * 8;
+        if ((q & 3) == 0 && step > 0) {
+          live = mbar_wait(ACC_FULL(half), (uint32_t)((step - 1) & 1), s_abort, p.gerr, 84);
+          tc_fence_after();
+        }
+        if (!live) break;
+        float a[4][8];
+        if (step > 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t rr[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "r"(taddr + (uint32_t)(half * 256 + g * SUN + uh * 32 + (q & 3) * 8)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[g][i] = __uint_as_float(rr[i]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[g][i] = 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 lo = pre[slot][g][0], hi = pre[slot][g][1];
+          a[g][0] += lo.x; a[g][1] += lo.y; a[g][2] += lo.z; a[g][3] += lo.w;
+          a[g][4] += hi.x; a[g][5] += hi.y; a[g][6] += hi.z; a[g][7] += hi.w;
+        }
+        if (q + 2 < 8) load_item(gp, q + 2, slot);
+        else if (step + 1 < T) load_item(gp_next, q + 2 - 8, slot);
+        float hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float ig, fg, gg, og, hh, cn;
+          lstm_cell_fast(a[0][i], a[1][i], a[2][i], a[3][i], creg[q][i], ig, fg, gg, og, cn, hh);
+          creg[q][i] = cn;
+          hv[i] = rna_tf32(hh);
+          a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
+        }
+        // next step's A operand (and the source of the TMA store to hseq): K-major SWIZZLE_128B - the 16-byte chunk index
+        // is XOR-ed with (row & 7) inside the row's 128 bytes
+        {
+          uint8_t* slab = hb + (u >> 5) * P_SLAB;
+          const int ch = (u & 31) >> 2;  // even
+          *reinterpret_cast<float4*>(slab + ((ch ^ (rl & 7)) << 4)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(slab + (((ch + 1) ^ (rl & 7)) << 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        }
+        if (STORE && rok) {
+          st4(cout + u, make_float4(creg[q][0], creg[q][1], creg[q][2], creg[q][3]));
+          st4(cout + u + 4, make_float4(creg[q][4], creg[q][5], creg[q][6], creg[q][7]));
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            st4(gp + g * PH + u, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
+            st4(gp + g * PH + u + 4, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+          }
+        }
+        if ((q & 3) == 3) {
+          // this warp's share of h_t (units of this half) is in the operand tile and its accumulator reads are done
+          tc_fence_before();
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(H_FULL(half));
+        }
+      }
+      gp = gp_next;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // W^T image: out[d][k][n] = in[d][n][k]   (n < N rows, k < K columns), 32 x 32 tiles through shared memory
 __global__ void transpose_image_kernel(const float* __restrict__ in, int64_t in_bs, float* __restrict__ out, int N, int K) {
   __shared__ float tile[32][33];
@@ -723,6 +1051,7 @@ bool gemm_tc_usable(const wgg_ctx* ctx, const GemmP& p) {
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al(p.A) || !al(p.B) || !al(p.C) || (p.bias && !al(p.bias)) || (p.bias2 && !al(p.bias2))) return false;
   if (p.splitk > 1 && !al(p.partial)) return false;
+  if (p.out_chunk && (p.splitk > 1 || p.accumulate || p.chunk_B <= 0)) return false;
   if (p.nbatch == 2 && ((p.bsA & 3) || (p.bsB & 3) || (p.bsC & 3) || (p.bsBias & 3))) return false;
   return gtc::encode_fn() != nullptr;
 }
@@ -755,6 +1084,7 @@ int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st) {
   prm.M = (int)p.M; prm.N = (int)p.N; prm.K = (int)p.K; prm.ldc = split ? (int)p.N : (int)p.scm;
   prm.accumulate = split ? 0 : p.accumulate;
   prm.splits = splits; prm.k_len = (int)k_len;
+  prm.out_chunk = p.out_chunk; prm.chunk_B = (int)p.chunk_B; prm.chunk_tiles = (int)cdiv64(p.chunk_B > 0 ? p.chunk_B : 1, 128);
   prm.gerr = ctx->async_err;
   constexpr size_t smem = (size_t)2 * gtc::NST * gtc::TILE_BYTES + 64 + 16 + gtc::BN * 4 + 1024;
   if (!wgg_smem_ok(ctx, gtc::gemm_tc_nt_kernel, smem)) return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_nt_kernel: cannot reserve shared memory%s");
@@ -850,6 +1180,50 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
                    "gemm_tc_lstm_fwd_kernel");
     WGG_TRY(gtc::launch_step(ctx, kernel, grid, smem, st, prm, "gemm_tc_lstm_fwd_kernel"));
   }
+  return WGG_OK;
+}
+
+// gen_hidden_dim = 128 in the tensor-core modes: the persistent kernel above.  WGG_LSTM128_PERSIST = 0 keeps the
+// per-timestep launches everywhere, 1 (default) uses the persistent kernel where the gate buffer is chunked (no-grad passes:
+// sampling and the critic phase's generations, 10 of the 12 generator batches of a step), 2 also for the row-major
+// grad-carrying passes - measured slower there than the per-timestep kernels (lane-strided 16-byte accesses to the gate
+// buffer: 134 vs 108 ms per H = 128 / T = 256 / B = 1024 step), kept for A/B measurements.
+static int lstm128_mode() {
+  static const int m = [] { const char* e = getenv("WGG_LSTM128_PERSIST"); return e ? atoi(e) : 1; }();
+  return m;
+}
+bool lstm128_persist_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
+                            int64_t dir_stride) {
+  return lstm128_mode() >= 1 && H == gtc::PH && lstm_step_tc_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride);
+}
+bool lstm128_persist_rowmajor() { return lstm128_mode() >= 2; }
+
+int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
+                            float* cseq, int T, int64_t B, int store, int chunked, cudaStream_t st) {
+  constexpr int H = gtc::PH;
+  if (store && chunked) return wgg_fail(ctx, WGG_EINVAL, "lstm128_persist_forward: the stashing pass keeps the row-major gate buffer%s");
+  gtc::PersistParams prm;
+  memset(&prm, 0, sizeof(prm));
+  for (int d = 0; d < 2; ++d)
+    if (!gtc::make_map_rows(&prm.b[d], lp + off_whh + d * dir_stride, 4 * H, H, H, gtc::SUN) ||
+        !gtc::make_map_time(&prm.hs[d], hseq + d * H, H, B, T, 2 * H))
+      return wgg_fail(ctx, WGG_ECUDA, "lstm128_persist_forward: cuTensorMapEncodeTiled failed%s");
+  prm.gates = gates; prm.cseq = cseq; prm.T = T; prm.B = (int)B; prm.gerr = ctx->async_err;
+  // L2 prefetch of the next step's gate block: pays when at most ~half of the SMs run this kernel (measured 7.9 vs 9.1 ms per
+  // 4-layer forward at 64 CTAs), hurts with every SM busy (14.6 vs 10.6 ms at 148 CTAs: the blocks do not survive in L2)
+  static const int l2pf_env = [] { const char* e = getenv("WGG_LSTM128_L2PF"); return e ? atoi(e) : -1; }();
+  prm.l2pf = l2pf_env >= 0 ? l2pf_env : (2 * cdiv64(B, gtc::SBM) <= 64 ? 1 : 0);
+  constexpr size_t smem = (size_t)2 * gtc::P_HBUF + gtc::P_NST * gtc::P_WST + 128 + 16 + 1024;
+  void (*kernel)(const gtc::PersistParams) =
+      store ? gtc::lstm128_tc_fwd_kernel<1, 0> : chunked ? gtc::lstm128_tc_fwd_kernel<0, 1> : gtc::lstm128_tc_fwd_kernel<0, 0>;
+  if (!wgg_smem_ok(ctx, kernel, smem))
+    return wgg_fail(ctx, WGG_ECUDA, "lstm128_tc_fwd_kernel: cannot reserve shared memory%s");
+  dim3 grid((unsigned)cdiv64(B, gtc::SBM), 2);
+  const double TB = (double)T * B;
+  ProfScope prof(ctx, "lstm128_tc_fwd_kernel", st, 2.0 * (T - 1) * (double)B * 4.0 * H * H * 2,
+                 4.0 * 2 * (TB * 4 * H * (store ? 2 : 1) + TB * H * (store ? 2 : 1)), "lstm128_tc_fwd_kernel");
+  kernel<<<grid, gtc::P_THREADS, smem, st>>>(prm);
+  WGG_CHECK_LAUNCH(ctx, "lstm128_tc_fwd_kernel");
   return WGG_OK;
 }
 

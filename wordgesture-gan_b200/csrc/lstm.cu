@@ -101,6 +101,66 @@ __global__ void __launch_bounds__(128) xproj0_kernel(const float* __restrict__ p
   }
 }
 
+// The same projection in the chunked gate-buffer order of the persistent H = 128 recurrence (gemm_tc.cu:
+// [dir][t][tile of 128 gestures][4H / 4][128 rows][4 floats], thread = gesture, so every access below is a coalesced
+// 16-byte access).  zb_chunk_kernel: the per-gesture latent term + biases; xproj0_chunk_kernel: + the prototype term.
+__global__ void __launch_bounds__(128) zb_chunk_kernel(const float* __restrict__ z, const float* __restrict__ w, int64_t dir_stride,
+                                                       int64_t off_bih, int64_t off_bhh, float* __restrict__ zbc, int64_t B, int Z,
+                                                       int pd, int I0, int H4) {
+  const int tile = blockIdx.x, d = blockIdx.y, rl = threadIdx.x;
+  const int64_t b = (int64_t)tile * 128 + rl;
+  float zr[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) zr[k] = (k < Z && b < B) ? __ldg(z + b * Z + k) : 0.f;
+  const float* wd = w + d * dir_stride;
+  float* out = zbc + (((int64_t)d * gridDim.x + tile) * (H4 / 4) * 128 + rl) * 4;
+  for (int n4 = 0; n4 < H4 / 4; ++n4) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = 4 * n4 + j;
+      const float* wr = wd + (int64_t)n * I0 + pd;
+      float acc = __ldg(wd + off_bih + n) + __ldg(wd + off_bhh + n);
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < Z) acc = fmaf(zr[k], __ldg(wr + k), acc);
+      o[j] = acc;
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)n4 * 512) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(128) xproj0_chunk_kernel(const float* __restrict__ proto, const float* __restrict__ zbc,
+                                                           const float* __restrict__ w, int64_t dir_stride,
+                                                           float* __restrict__ gates, int T, int64_t B, int C, int pd, int I0,
+                                                           int H4) {
+  extern __shared__ float4 s_w3[];  // [H4]: the pd (<= 4) prototype columns of W_ih[d][n]
+  const int tile = blockIdx.x, d = blockIdx.y, rl = threadIdx.x, tiles = gridDim.x;
+  for (int n = threadIdx.x; n < H4; n += 128) {
+    const float* wr = w + d * dir_stride + (int64_t)n * I0;
+    s_w3[n] = make_float4(__ldg(wr), pd > 1 ? __ldg(wr + 1) : 0.f, pd > 2 ? __ldg(wr + 2) : 0.f, pd > 3 ? __ldg(wr + 3) : 0.f);
+  }
+  __syncthreads();
+  const int64_t b = (int64_t)tile * 128 + rl;
+  if (b >= B) return;
+  const float* zb = zbc + (((int64_t)d * tiles + tile) * (H4 / 4) * 128 + rl) * 4;
+  for (int t = blockIdx.z; t < T; t += gridDim.z) {
+    const float* pp = proto + (b * T + t) * C;
+    const float x0 = __ldg(pp), x1 = pd > 1 ? __ldg(pp + 1) : 0.f, x2 = pd > 2 ? __ldg(pp + 2) : 0.f, x3 = pd > 3 ? __ldg(pp + 3) : 0.f;
+    float* g = gates + ((((int64_t)d * T + t) * tiles + tile) * (H4 / 4) * 128 + rl) * 4;
+#pragma unroll 4
+    for (int n4 = 0; n4 < H4 / 4; ++n4) {
+      float4 o = *reinterpret_cast<const float4*>(zb + (int64_t)n4 * 512);
+      const float4 w0 = s_w3[4 * n4], w1 = s_w3[4 * n4 + 1], w2 = s_w3[4 * n4 + 2], w3 = s_w3[4 * n4 + 3];
+      o.x += x0 * w0.x + x1 * w0.y + x2 * w0.z + x3 * w0.w;
+      o.y += x0 * w1.x + x1 * w1.y + x2 * w1.z + x3 * w1.w;
+      o.z += x0 * w2.x + x1 * w2.y + x2 * w2.z + x3 * w2.w;
+      o.w += x0 * w3.x + x1 * w3.y + x2 * w3.z + x3 * w3.w;
+      *reinterpret_cast<float4*>(g + (int64_t)n4 * 512) = o;
+    }
+  }
+}
+
 // dpre[t][b][c] = dy[b][t][c] * (1 - y[b][t][c]^2)                (backward of tanh, models.py:163)
 __global__ void head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dpre,
                                 int T, int64_t B, int C) {
@@ -425,7 +485,10 @@ int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t 
                     float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
   const int64_t TB = (int64_t)T * B;
   const int H4 = 4 * H;
-  // tensor-core math modes: one fused launch per timestep (tcgen05 recurrent product + cell update, gemm_tc.cu)
+  // tensor-core math modes: H = 128 has a persistent kernel (one launch per layer); otherwise one fused launch per
+  // timestep (tcgen05 recurrent product + cell update, gemm_tc.cu)
+  if (lstm128_persist_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride) && lstm128_persist_rowmajor())
+    return lstm128_persist_forward(ctx, gates, lp, dir_stride, off_whh, hseq, cseq, T, B, store, 0, st);
   if (lstm_step_tc_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride))
     return lstm_step_tc_forward(ctx, H, gates, lp, dir_stride, off_whh, hseq, cseq, cstate, T, B, store, st);
   for (int step = 0; step < T; ++step) {
@@ -515,6 +578,12 @@ struct StashView {
   float* cseq[WGG_MAX_HIDDEN_LAYERS];
 };
 
+inline int64_t pad128(int64_t B) { return (B + 127) / 128 * 128; }
+// gate buffer of a no-grad forward: [2][T][B][4H], in the scaled regime with B padded to whole tiles
+int64_t fwd_gate_floats(const GenLayout& g, int64_t B) {
+  return (int64_t)g.T * (rec_has_persistent_kernel(g.H) ? B : pad128(B)) * 8 * g.H;
+}
+
 int64_t stash_floats(const GenLayout& g, int64_t B) {
   const int64_t TB = (int64_t)g.T * B;
   return TB * (g.I0 + (int64_t)g.L * 12 * g.H);
@@ -550,9 +619,10 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   if (gen_layout(cfg, &g) != WGG_OK) return -1;
   const int64_t TB = (int64_t)g.T * B;
   if (!backward) {  // no-grad forward: x0 + two hseq + gates (FMA path) or the tcgen05 path's buffers
-    // + zb [2][B][4H] of the scaled regime's layer-0 input projection (xproj0_kernel)
-    const int64_t simt = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0) +
-                         (rec_has_persistent_kernel(g.H) ? 0 : 8 * B * (int64_t)g.H + 8);
+    // scaled regime: the gate buffer is padded to whole 128-gesture tiles (chunked order of the persistent H = 128
+    // recurrence) + zb [2][B padded][4H] of the layer-0 input projection (xproj0 kernels)
+    const int64_t simt = TB * (g.I0 + 4 * g.H) + fwd_gate_floats(g, B) + rec_generic_scratch_floats(g.H, B, 0) +
+                         (rec_has_persistent_kernel(g.H) ? 0 : 8 * pad128(B) * (int64_t)g.H + 8);
     const int64_t tcw = generator_tc_workspace_floats(cfg, B);
     return simt > tcw ? simt : tcw;
   }
@@ -593,17 +663,18 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     hbuf[0] = ws + TB * g.I0;
     hbuf[1] = hbuf[0] + TB * 2 * g.H;
     gates_ws = hbuf[1] + TB * 2 * g.H;
-    rec_scratch = gates_ws + TB * 8 * g.H;
+    rec_scratch = gates_ws + fwd_gate_floats(g, B);
   }
   // scaled regime: layer 0's input projection without materialising x0 (the stash still gets x0: the backward reads it)
   float* zb = nullptr;
   if (!rec_has_persistent_kernel(g.H) && g.pd <= 4 && ws) {
-    const int64_t base = TB * (g.I0 + 4 * g.H + 8 * g.H) + rec_generic_scratch_floats(g.H, B, 0);
+    const int64_t base = TB * (g.I0 + 4 * g.H) + fwd_gate_floats(g, B) + rec_generic_scratch_floats(g.H, B, 0);
     float* q = ws + base;
     if (reinterpret_cast<uintptr_t>(q) & 15) q += 4 - ((reinterpret_cast<uintptr_t>(q) & 15) >> 2);
     const float* g0 = stash ? sv.gates[0] : gates_ws;
-    if (q + 8 * B * (int64_t)g.H <= ws + ws_floats && (reinterpret_cast<uintptr_t>(g0) & 15) == 0) zb = q;
+    if (q + 8 * pad128(B) * (int64_t)g.H <= ws + ws_floats && (reinterpret_cast<uintptr_t>(g0) & 15) == 0) zb = q;
   }
+  const int64_t tiles = pad128(B) / 128;
   if (stash || !zb) {
     build_x0_kernel<<<ew_grid(TB * g.I0), 256, 0, st>>>(proto, z, sv.x0, g.T, B, g.C, g.pd, g.Z);
     WGG_CHECK_LAUNCH(ctx, "build_x0_kernel");
@@ -616,7 +687,33 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     float* gates = stash ? sv.gates[l] : gates_ws;
     float* cseq = stash ? sv.cseq[l] : nullptr;
     hout = stash ? sv.hseq[l] : hbuf[l & 1];
-    if (l == 0 && zb) {
+    // no-grad pass at H = 128 (tensor-core modes): the persistent recurrence reads the gate buffer in chunked order
+    bool chunked = !stash && zb && g.Z <= 64 && lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l]);
+    GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
+    p.tag = "gemm_kernel/lstm_xproj";
+    p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
+    p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
+    p.C = gates; p.scm = 4 * g.H; p.scn = 1;
+    p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
+    p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
+    if (chunked && l > 0) {
+      GemmP pc = p;
+      pc.out_chunk = 1; pc.chunk_B = B; pc.bsC = (int64_t)g.T * tiles * 128 * 4 * g.H;
+      if (gemm_tc_usable(ctx, pc)) p = pc;
+      else chunked = false;
+    }
+    if (l == 0 && zb && chunked) {
+      dim3 gz((unsigned)tiles, 2);
+      zb_chunk_kernel<<<gz, 128, 0, st>>>(z, lp, g.dir_stride[l], g.off_bih[l], g.off_bhh[l], zb, B, g.Z, g.pd, I, 4 * g.H);
+      WGG_CHECK_LAUNCH(ctx, "zb_chunk_kernel");
+      int zs = (int)(4 * (int64_t)ctx->sm_count / (2 * tiles) + 1);
+      if (zs > g.T) zs = g.T;
+      dim3 grid((unsigned)tiles, 2, (unsigned)zs);
+      ProfScope prof(ctx, "xproj0_kernel", st, 2.0 * TB * 8.0 * g.H * g.pd, 4.0 * TB * 8.0 * g.H, "xproj0_kernel");
+      xproj0_chunk_kernel<<<grid, 128, (size_t)4 * g.H * sizeof(float4), st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C,
+                                                                                g.pd, I, 4 * g.H);
+      WGG_CHECK_LAUNCH(ctx, "xproj0_chunk_kernel");
+    } else if (l == 0 && zb) {
       GemmP q;  // zb[d] (B x 4H) = z * W_ih[d][:, pd:]^T + b_ih[d] + b_hh[d]     (fp32)
       q.tag = "gemm_kernel/lstm_xproj0_z";
       q.A = z; q.M = B; q.K = g.Z; q.sam = g.Z; q.sak = 1;
@@ -631,14 +728,12 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
       xproj0_kernel<<<grid, 128, 0, st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C, g.pd, I, 4 * g.H);
       WGG_CHECK_LAUNCH(ctx, "xproj0_kernel");
     } else {
-      GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
-      p.tag = "gemm_kernel/lstm_xproj";
-      p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
-      p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
-      p.C = gates; p.scm = 4 * g.H; p.scn = 1;
-      p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
-      p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
       WGG_TRY(gemm_launch(ctx, p, st));
+    }
+    if (chunked) {
+      WGG_TRY(lstm128_persist_forward(ctx, gates, lp, g.dir_stride[l], g.off_whh[l], hout, nullptr, g.T, B, 0, 1, st));
+      in = hout;
+      continue;
     }
     WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, rec_scratch, g.T, B, stash ? 1 : 0, st));
     in = hout;
