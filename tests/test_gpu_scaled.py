@@ -81,10 +81,14 @@ def test_generator_large_batch_tcgen05_gemm(H, B, T, L):
             assert {"gemm_tc/lstm_dWih", "gemm_tc/lstm_dWhh", "gemm_tc/lstm_dx"} <= bwd_tags, bwd_tags
         # H = 64 keeps its persistent FMA recurrent kernel: only layer 1's input projection qualifies there; H = 128 has the
         # persistent tcgen05 kernel (one launch per layer); larger H: one fused tcgen05 launch per timestep and layer
-        assert used >= (1 if H <= 64 else T), f"the tcgen05 GEMM / fused step kernels took only {used} launches"
         if H == 128:
-            # no-grad passes (sampling, the critic phase's generations): the persistent kernel, one launch per layer, on the
-            # chunked gate buffer written by the input-projection GEMM / the layer-0 projection kernels
+            # persistent kernel, one launch per layer, on the chunked gate buffer written by the input-projection GEMM / the
+            # layer-0 projection kernels - in the grad-carrying pass (chunked stash, read by the chunked BPTT kernel) ...
+            assert fwd_rows.get("lstm128_tc_fwd_kernel") == L and "gemm_tc_lstm_fwd_kernel" not in fwd_rows, fwd_rows
+        else:
+            assert used >= (1 if H <= 64 else T), f"the tcgen05 GEMM / fused step kernels took only {used} launches"
+        if H == 128:
+            # ... and in the no-grad passes (sampling, the critic phase's generations)
             _lib.profile_enable(DEV, "tc_")
             with torch.no_grad():
                 y_ng = G(to_t(proto), to_t(z))

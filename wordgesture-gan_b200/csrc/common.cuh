@@ -170,8 +170,9 @@ bool lstm128_persist_rowmajor();
 // chunked = 1 (no-grad passes): gates is [2][T][ceil(B/128)][4H/4][128][4] as written by GemmP::out_chunk / xproj0_chunk
 int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                             float* cseq, int T, int64_t B, int store, int chunked, cudaStream_t st);
+// chunked = 1: gates / cseq in the chunked stash order of the persistent H = 128 forward
 int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
-                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st);
+                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, int chunked, cudaStream_t st);
 // K-major (transposed, TF32-rounded) operand images + tcgen05 split-K GEMMs for the weight / input gradients of the scaled path
 bool lstm_wgrad_tc_usable(const wgg_ctx* ctx, int H, int64_t B, int T);
 int transpose_tf32_launch(wgg_ctx* ctx, const float* in, int64_t ld_in, int64_t bs_in, float* out, int64_t ld_out,

@@ -480,6 +480,10 @@ struct StepBwdParams {
   int* gerr;
 };
 
+// CHUNK = 1 (H = 128 with the chunked stash of the persistent forward): gates / c / the carried dc are
+// [..][tile][columns / 4][128 rows][4 floats]; a k-slab (32 columns) of da is then one contiguous 16 KB block in UMMA
+// core-matrix order (no swizzle: k-chunks 2 KB apart, 8-row groups 128 B apart) and arrives by one plain bulk copy.
+template <int CHUNK>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __grid_constant__ StepBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -496,6 +500,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
   const int tn = dir ? t - 1 : t + 1;  // the step processed by the previous launch (later in the sequence's own order)
   const int tp = dir ? t + 1 : t - 1;  // the step whose cell state is c_prev
   const int H = p.H;
+  const int tiles = (p.B + SBM - 1) / SBM;
+  // chunked gate block of this tile at sequence position tt: [4H / 4 chunks][128 rows][4 floats], 256 KB
+  auto gate_blk = [&](int tt) -> float* { return p.gates + (((int64_t)dir * p.T + tt) * tiles + blockIdx.y) * (int64_t)(4 * H) * SBM; };
   const uint32_t bar0 = smem_u32(s_bar);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (WNST + s); };
@@ -523,12 +530,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
       }
       pdl_wait();
       pdl_launch_dependents();
-      for (int it = 0; it < npre; ++it) tma_load_3d(smem_u32(s_a + it * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(it));
+      const uint8_t* ablk = CHUNK ? reinterpret_cast<const uint8_t*>(gate_blk(tn)) : nullptr;
+      for (int it = 0; it < npre; ++it) {
+        if (CHUNK) bulk_g2s(smem_u32(s_a + it * SA_BYTES), ablk + (int64_t)it * SA_BYTES, SA_BYTES, FULL(it));
+        else tma_load_3d(smem_u32(s_a + it * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(it));
+      }
       for (int it = npre; it < KT; ++it) {
         const int s = it % WNST;
         if (!mbar_wait(EMPTY(s), (uint32_t)(((it / WNST) & 1) ^ 1), s_abort, p.gerr, 77)) break;
         mbar_expect_tx(FULL(s), SA_BYTES + WB_BYTES);
-        tma_load_3d(smem_u32(s_a + s * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(s));
+        if (CHUNK) bulk_g2s(smem_u32(s_a + s * SA_BYTES), ablk + (int64_t)it * SA_BYTES, SA_BYTES, FULL(s));
+        else tma_load_3d(smem_u32(s_a + s * SA_BYTES), &p.a[dir], it * BK, m0, tn, FULL(s));
         tma_load_2d(smem_u32(s_b + s * WB_BYTES), &p.b[dir], it * BK, u0, FULL(s));
       }
     }
@@ -543,7 +555,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
         const uint32_t a0 = smem_u32(s_a + s * SA_BYTES), b0 = smem_u32(s_b + s * WB_BYTES);
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks)
-          mma_tf32_ss(tmem_base, desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32), idesc, (it | ks) ? 1u : 0u);
+          mma_tf32_ss(tmem_base, CHUNK ? make_desc(a0 + ks * 4096, 2048, 128) : desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32),
+                      idesc, (it | ks) ? 1u : 0u);
         mma_commit(EMPTY(s));
       }
       __syncwarp();
@@ -556,12 +569,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
     const bool rok = row < p.B;
     const int64_t TB = (int64_t)p.T * p.B;
     const int64_t r = rok ? row : 0;
-    float* gp = p.gates + (((int64_t)dir * p.T + t) * p.B + r) * 4 * H;
+    const int rl = quarter * 32 + lane;
+    // CHUNK: element (column n, this row) of a [columns / 4][128][4] block sits at block + (n >> 2) * 512 + rl * 4 + (n & 3)
+    float* gp = CHUNK ? gate_blk(t) + rl * 4 : p.gates + (((int64_t)dir * p.T + t) * p.B + r) * 4 * H;
+    auto cblk = [&](int tt) -> const float* {
+      return p.cseq + ((((int64_t)dir * p.T + tt) * tiles + blockIdx.y) * (H / 4) * SBM + rl) * 4;
+    };
     const float* cb = p.cseq + (int64_t)dir * TB * H;
-    const float* cc = cb + ((int64_t)t * p.B + r) * H;
-    const float* cpp = p.step > 0 ? cb + ((int64_t)tp * p.B + r) * H : nullptr;
+    const float* cc = CHUNK ? cblk(t) : cb + ((int64_t)t * p.B + r) * H;
+    const float* cpp = p.step > 0 ? (CHUNK ? cblk(tp) : cb + ((int64_t)tp * p.B + r) * H) : nullptr;
     const float* dho = p.dh_out + ((int64_t)t * p.B + r) * 2 * H + dir * H;
-    float* dcs = p.dcs + ((int64_t)dir * p.B + r) * H;
+    float* dcs = CHUNK ? p.dcs + ((((int64_t)dir * tiles + blockIdx.y) * (H / 4)) * SBM + rl) * 4 : p.dcs + ((int64_t)dir * p.B + r) * H;
+    // address of the 4 columns [n, n + 4) of this row (n a multiple of 4)
+    auto at = [&](const float* base, int n) -> const float* { return CHUNK ? base + (int64_t)(n >> 2) * 512 : base + n; };
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // four chunks of 8 hidden units per thread (two adjacent 16-byte accesses = one full 32-byte sector per row and
     // tensor), operands requested one chunk ahead; everything but the carried dc is independent of the previous launch and
@@ -576,9 +596,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int uq = u + 4 * q;
-        o.gi[q] = ok ? ld4(gp + uq) : z4; o.gf[q] = ok ? ld4(gp + H + uq) : z4; o.gg[q] = ok ? ld4(gp + 2 * H + uq) : z4;
-        o.go[q] = ok ? ld4(gp + 3 * H + uq) : z4;
-        o.c4[q] = ok ? ld4(cc + uq) : z4; o.cp4[q] = (ok && cpp) ? ld4(cpp + uq) : z4; o.dh4[q] = ok ? ld4(dho + uq) : z4;
+        o.gi[q] = ok ? ld4(at(gp, uq)) : z4; o.gf[q] = ok ? ld4(at(gp, H + uq)) : z4; o.gg[q] = ok ? ld4(at(gp, 2 * H + uq)) : z4;
+        o.go[q] = ok ? ld4(at(gp, 3 * H + uq)) : z4;
+        o.c4[q] = ok ? ld4(at(cc, uq)) : z4; o.cp4[q] = (ok && cpp) ? ld4(at(cpp, uq)) : z4; o.dh4[q] = ok ? ld4(dho + uq) : z4;
       }
       return o;
     };
@@ -586,8 +606,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
       const int u = u0 + uh * 32 + c * 8;
       const bool ok = rok && u < H && !first;
       Dc d;
-      d.v[0] = ok ? ld4(dcs + u) : z4;
-      d.v[1] = ok ? ld4(dcs + u + 4) : z4;
+      d.v[0] = ok ? ld4(at(dcs, u)) : z4;
+      d.v[1] = ok ? ld4(at(dcs, u + 4)) : z4;
       return d;
     };
     Ops cur = load_ops(0);
@@ -632,11 +652,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_bwd_kernel(const __gr
               dk[i] = dct * fv[i];
             }
             const int uq = u + 4 * q;
-            st4(gp + uq, make_float4(di[0], di[1], di[2], di[3]));
-            st4(gp + H + uq, make_float4(df[0], df[1], df[2], df[3]));
-            st4(gp + 2 * H + uq, make_float4(dg[0], dg[1], dg[2], dg[3]));
-            st4(gp + 3 * H + uq, make_float4(dO[0], dO[1], dO[2], dO[3]));
-            st4(dcs + uq, make_float4(dk[0], dk[1], dk[2], dk[3]));
+            st4(const_cast<float*>(at(gp, uq)), make_float4(di[0], di[1], di[2], di[3]));
+            st4(const_cast<float*>(at(gp, H + uq)), make_float4(df[0], df[1], df[2], df[3]));
+            st4(const_cast<float*>(at(gp, 2 * H + uq)), make_float4(dg[0], dg[1], dg[2], dg[3]));
+            st4(const_cast<float*>(at(gp, 3 * H + uq)), make_float4(dO[0], dO[1], dO[2], dO[3]));
+            st4(const_cast<float*>(at(dcs, uq)), make_float4(dk[0], dk[1], dk[2], dk[3]));
           }
         }
         cur = nxt;
@@ -694,9 +714,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int
                : "memory");
 }
 
-// STORE = 1: grad-carrying pass (row-major gate buffer overwritten with the activated gates, c stored) - BPTT and the
-// weight-gradient GEMMs read that buffer as a K-major matrix.  CHUNK = 1 (no-grad passes: sampling, the critic phase's
-// generations): the gate buffer is private scratch in the chunked order the input-projection GEMM wrote for this kernel.
+// STORE = 1: grad-carrying pass (the gate buffer is overwritten with the activated gates, c is stored).  CHUNK = 1: the gate
+// buffer (and c) in the chunked order [t][tile][columns / 4][128 rows][4 floats] the input-projection GEMM wrote for this kernel
+// - every epilogue access is a coalesced 16-byte access; BPTT (gemm_tc_lstm_bwd_kernel<1>) reads a k-slab of it as one
+// contiguous 16 KB block in UMMA core-matrix order.  CHUNK = 0: row-major [t][b][columns] (kept for A/B measurements).
 template <int STORE, int CHUNK>
 __global__ void __launch_bounds__(P_THREADS, 1) lstm128_tc_fwd_kernel(const __grid_constant__ PersistParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -878,7 +899,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) lstm128_tc_fwd_kernel(const __gr
     for (int step = 0; step < T && live; ++step) {
       const int t = dir ? T - 1 - step : step;
       float* gp_next = step + 1 < T ? gate_ptr(dir ? t - 1 : t + 1) : gp;
-      float* cout = STORE ? p.cseq + (int64_t)dir * TB * PH + ((int64_t)t * p.B + r) * PH : nullptr;
+      // c of this thread's row at t: row-major [2][T][B][H], or chunked [2][T][tiles][H / 4][128][4] with the gate buffer
+      float* cout = !STORE ? nullptr
+                    : CHUNK ? p.cseq + ((((int64_t)dir * T + t) * tiles + blockIdx.x) * (PH / 4) * 128 + rl) * 4
+                            : p.cseq + (int64_t)dir * TB * PH + ((int64_t)t * p.B + r) * PH;
       uint8_t* hb = s_h + (step & 1) * P_HBUF + rl * 128;  // this row inside each k-slab of the tile being produced
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -933,12 +957,24 @@ __global__ void __launch_bounds__(P_THREADS, 1) lstm128_tc_fwd_kernel(const __gr
           *reinterpret_cast<float4*>(slab + (((ch + 1) ^ (rl & 7)) << 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
         if (STORE && rok) {
-          st4(cout + u, make_float4(creg[q][0], creg[q][1], creg[q][2], creg[q][3]));
-          st4(cout + u + 4, make_float4(creg[q][4], creg[q][5], creg[q][6], creg[q][7]));
+          if (CHUNK) {
+            float* cq = cout + (int64_t)(u >> 2) * 512;
+            st4(cq, make_float4(creg[q][0], creg[q][1], creg[q][2], creg[q][3]));
+            st4(cq + 512, make_float4(creg[q][4], creg[q][5], creg[q][6], creg[q][7]));
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            st4(gp + g * PH + u, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
-            st4(gp + g * PH + u + 4, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+            for (int g = 0; g < 4; ++g) {
+              float* gq = gp + (int64_t)((g * PH + u) >> 2) * 512;
+              st4(gq, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
+              st4(gq + 512, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+            }
+          } else {
+            st4(cout + u, make_float4(creg[q][0], creg[q][1], creg[q][2], creg[q][3]));
+            st4(cout + u + 4, make_float4(creg[q][4], creg[q][5], creg[q][6], creg[q][7]));
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              st4(gp + g * PH + u, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
+              st4(gp + g * PH + u + 4, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+            }
           }
         }
         if ((q & 3) == 3) {
@@ -1201,7 +1237,6 @@ bool lstm128_persist_rowmajor() { return lstm128_mode() >= 2; }
 int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
                             float* cseq, int T, int64_t B, int store, int chunked, cudaStream_t st) {
   constexpr int H = gtc::PH;
-  if (store && chunked) return wgg_fail(ctx, WGG_EINVAL, "lstm128_persist_forward: the stashing pass keeps the row-major gate buffer%s");
   gtc::PersistParams prm;
   memset(&prm, 0, sizeof(prm));
   for (int d = 0; d < 2; ++d)
@@ -1215,7 +1250,8 @@ int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t
   prm.l2pf = l2pf_env >= 0 ? l2pf_env : (2 * cdiv64(B, gtc::SBM) <= 64 ? 1 : 0);
   constexpr size_t smem = (size_t)2 * gtc::P_HBUF + gtc::P_NST * gtc::P_WST + 128 + 16 + 1024;
   void (*kernel)(const gtc::PersistParams) =
-      store ? gtc::lstm128_tc_fwd_kernel<1, 0> : chunked ? gtc::lstm128_tc_fwd_kernel<0, 1> : gtc::lstm128_tc_fwd_kernel<0, 0>;
+      store ? (chunked ? gtc::lstm128_tc_fwd_kernel<1, 1> : gtc::lstm128_tc_fwd_kernel<1, 0>)
+            : (chunked ? gtc::lstm128_tc_fwd_kernel<0, 1> : gtc::lstm128_tc_fwd_kernel<0, 0>);
   if (!wgg_smem_ok(ctx, kernel, smem))
     return wgg_fail(ctx, WGG_ECUDA, "lstm128_tc_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(B, gtc::SBM), 2);
@@ -1227,34 +1263,35 @@ int lstm128_persist_forward(wgg_ctx* ctx, float* gates, const float* lp, int64_t
   return WGG_OK;
 }
 
-// scratch: dcs [2][B][H] | W_hh^T images [2][H][4H]
-int64_t lstm_step_tc_bwd_scratch_floats(int H, int64_t B) { return 2 * B * (int64_t)H + 8 * (int64_t)H * H + 64; }
+// scratch: dcs [2][B padded to tiles][H] | W_hh^T images [2][H][4H]
+int64_t lstm_step_tc_bwd_scratch_floats(int H, int64_t B) { return 2 * ((B + 127) / 128 * 128) * (int64_t)H + 8 * (int64_t)H * H + 64; }
 
 int lstm_step_tc_backward(wgg_ctx* ctx, int H, float* gates, const float* cseq, const float* lp, int64_t dir_stride,
-                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, cudaStream_t st) {
+                          int64_t off_whh, const float* dh_out, float* scratch, int T, int64_t B, int chunked, cudaStream_t st) {
   float* dcs = scratch;
-  float* wt = scratch + ((2 * B * (int64_t)H + 3) & ~(int64_t)3);  // keep the image 16-byte aligned
+  float* wt = scratch + ((2 * ((B + 127) / 128 * 128) * (int64_t)H + 3) & ~(int64_t)3);  // keep the image 16-byte aligned
   if (reinterpret_cast<uintptr_t>(wt) & 15) wt += 4 - ((reinterpret_cast<uintptr_t>(wt) & 15) >> 2);
   WGG_TRY(transpose_image_launch(ctx, lp + off_whh, dir_stride, wt, 4 * H, H, 2, st));
   const int64_t TB = (int64_t)T * B;
   gtc::StepBwdParams prm;
   memset(&prm, 0, sizeof(prm));
   for (int d = 0; d < 2; ++d) {
-    if (!gtc::make_map_time(&prm.a[d], gates + d * TB * 4 * H, 4 * H, B, T, 4 * H) ||
+    if ((!chunked && !gtc::make_map_time(&prm.a[d], gates + d * TB * 4 * H, 4 * H, B, T, 4 * H)) ||
         !gtc::make_map_rows(&prm.b[d], wt + (int64_t)d * 4 * H * H, H, 4 * H, 4 * H, gtc::SUN))
       return wgg_fail(ctx, WGG_ECUDA, "lstm_step_tc_backward: cuTensorMapEncodeTiled failed%s");
   }
   prm.gates = gates; prm.cseq = cseq; prm.dh_out = dh_out; prm.dcs = dcs;
   prm.T = T; prm.B = (int)B; prm.H = H; prm.gerr = ctx->async_err;
   constexpr size_t smem = (size_t)gtc::WNST * (gtc::SA_BYTES + gtc::WB_BYTES) + 128 + 16 + 1024;
-  if (!wgg_smem_ok(ctx, gtc::gemm_tc_lstm_bwd_kernel, smem))
+  void (*kernel)(const gtc::StepBwdParams) = chunked ? gtc::gemm_tc_lstm_bwd_kernel<1> : gtc::gemm_tc_lstm_bwd_kernel<0>;
+  if (!wgg_smem_ok(ctx, kernel, smem))
     return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_bwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);
   for (int step = T - 1; step >= 0; --step) {
     prm.step = step;
     ProfScope prof(ctx, "gemm_tc_lstm_bwd_kernel", st, step < T - 1 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
                    4.0 * 2 * ((double)B * 4 * H * (step < T - 1 ? 3 : 2) + 5.0 * B * H), "gemm_tc_lstm_bwd_kernel");
-    WGG_TRY(gtc::launch_step(ctx, gtc::gemm_tc_lstm_bwd_kernel, grid, smem, st, prm, "gemm_tc_lstm_bwd_kernel"));
+    WGG_TRY(gtc::launch_step(ctx, kernel, grid, smem, st, prm, "gemm_tc_lstm_bwd_kernel"));
   }
   return WGG_OK;
 }

@@ -471,14 +471,16 @@ bool rec_has_persistent_kernel(int H) { return H == 8 || H == 16 || H == 32 || H
 int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
   if (rec_has_persistent_kernel(H)) return 0;
   // backward: dh_rec | dc, or (fused tcgen05 step kernels) dc | the W_hh^T images
-  return backward ? 4 * B * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * B * (int64_t)H;
+  // (the carried dc of the chunked BPTT is padded to whole 128-gesture tiles)
+  return backward ? 4 * ((B + 127) / 128 * 128) * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * B * (int64_t)H;
 }
 
 // K-major operand images of the tcgen05 weight / input-gradient GEMMs of the step-by-step path (backward only):
-// da^T [2][4H][T B] | two ping-pong h^T / input^T buffers [2H][T B] | W_ih^T [2][maxI][4H]  (+ alignment slack)
+// da^T [2][4H][T B] | two ping-pong h^T / input^T buffers [2H][T B] | W_ih^T [2][maxI][4H] | row-major copy of da
+// [2][T B][4H] (chunked stash only: the input-gradient GEMM and the bias sums read it)  (+ alignment slack)
 int64_t wgrad_tc_scratch_floats(int H, int64_t TB, int64_t maxI) {
   if (rec_has_persistent_kernel(H)) return 0;
-  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + 16;
+  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + TB * 8 * H + 16;
 }
 
 int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
@@ -517,7 +519,7 @@ int rec_bwd_generic(wgg_ctx* ctx, int H, float* gates, const float* cseq, const 
   const int64_t TB = (int64_t)T * B;
   const int H4 = 4 * H;
   if (lstm_step_tc_usable(ctx, H, gates, dh_out, lp, off_whh, dir_stride))
-    return lstm_step_tc_backward(ctx, H, gates, cseq, lp, dir_stride, off_whh, dh_out, scratch, T, B, st);
+    return lstm_step_tc_backward(ctx, H, gates, cseq, lp, dir_stride, off_whh, dh_out, scratch, T, B, 0, st);
   float* dhrec = scratch;
   float* dcs = scratch + 2 * B * H;
   for (int step = T - 1; step >= 0; --step) {
@@ -572,6 +574,7 @@ inline int ew_grid(int64_t n) {
 }
 
 struct StashView {
+  float* zb;  // scaled regime: per-gesture latent term of the layer-0 projection
   float* x0;
   float* hseq[WGG_MAX_HIDDEN_LAYERS];
   float* gates[WGG_MAX_HIDDEN_LAYERS];
@@ -584,18 +587,55 @@ int64_t fwd_gate_floats(const GenLayout& g, int64_t B) {
   return (int64_t)g.T * (rec_has_persistent_kernel(g.H) ? B : pad128(B)) * 8 * g.H;
 }
 
+// Stash of a grad-carrying forward: x0 | hseq[l] | gates[l] | cseq[l] (| zb).  In the scaled regime the gate and c buffers
+// are padded to whole 128-gesture tiles (the chunked order of the persistent H = 128 kernels needs whole tiles; the row-major
+// order simply leaves the tail unused) and the per-gesture latent term of the layer-0 projection (zb) lives here too.
 int64_t stash_floats(const GenLayout& g, int64_t B) {
   const int64_t TB = (int64_t)g.T * B;
-  return TB * (g.I0 + (int64_t)g.L * 12 * g.H);
+  if (rec_has_persistent_kernel(g.H)) return TB * (g.I0 + (int64_t)g.L * 12 * g.H);
+  const int64_t TBp = (int64_t)g.T * pad128(B);
+  return TB * (g.I0 + (int64_t)g.L * 2 * g.H) + TBp * (int64_t)g.L * 10 * g.H + 8 * pad128(B) * (int64_t)g.H + 16;
 }
 
 void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
   const int64_t TB = (int64_t)g.T * B;
+  const int64_t TBg = rec_has_persistent_kernel(g.H) ? TB : (int64_t)g.T * pad128(B);
   v->x0 = s;
   s += TB * g.I0;
   for (int l = 0; l < g.L; ++l) { v->hseq[l] = s; s += TB * 2 * g.H; }
-  for (int l = 0; l < g.L; ++l) { v->gates[l] = s; s += TB * 8 * g.H; }
-  for (int l = 0; l < g.L; ++l) { v->cseq[l] = s; s += TB * 2 * g.H; }
+  for (int l = 0; l < g.L; ++l) { v->gates[l] = s; s += TBg * 8 * g.H; }
+  for (int l = 0; l < g.L; ++l) { v->cseq[l] = s; s += TBg * 2 * g.H; }
+  if (reinterpret_cast<uintptr_t>(s) & 15) s += 4 - ((reinterpret_cast<uintptr_t>(s) & 15) >> 2);
+  v->zb = s;
+}
+
+// [dir][t][tile][columns / 4][128][4] (chunked da, TF32-rounded by BPTT) -> daT [dir][column][T B] (K-major image for the weight
+// gradients) and da_rm [dir][T B][columns] (row-major copy for the input-gradient GEMM and the bias sums).
+// block = (t * tiles + tile, group of 32 columns, dir); 256 threads; both outputs written in 128-byte runs.
+__global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict__ dac, float* __restrict__ daT,
+                                                         float* __restrict__ da_rm, int T, int64_t B, int C4) {
+  __shared__ float tile[128][33];
+  const int tiles = (int)((B + 127) / 128);
+  const int t = blockIdx.x / tiles, tl = blockIdx.x % tiles, cg = blockIdx.y, d = blockIdx.z;
+  const int64_t TB = (int64_t)T * B;
+  const float* src = dac + ((((int64_t)d * T + t) * tiles + tl) * (C4 / 4) + cg * 8) * 512;
+  for (int i = threadIdx.x; i < 8 * 128; i += 256) {  // 8 chunks x 128 rows of 16 bytes, contiguous
+    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)i * 4);
+    const int ch = i >> 7, r = i & 127;
+    tile[r][4 * ch] = v.x; tile[r][4 * ch + 1] = v.y; tile[r][4 * ch + 2] = v.z; tile[r][4 * ch + 3] = v.w;
+  }
+  __syncthreads();
+  const int64_t b0 = (int64_t)tl * 128;
+  const int nrows = B - b0 < 128 ? (int)(B - b0) : 128;
+  const int64_t m0 = (int64_t)t * B + b0;
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {  // daT: column-major runs of 128 rows
+    const int c = i >> 7, r = i & 127;
+    if (r < nrows) daT[((int64_t)d * C4 + cg * 32 + c) * TB + m0 + r] = tile[r][c];
+  }
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {  // da_rm: rows of 32 columns
+    const int r = i >> 5, c = i & 31;
+    if (r < nrows) da_rm[((int64_t)d * TB + m0 + r) * C4 + cg * 32 + c] = tile[r][c];
+  }
 }
 
 }  // namespace
@@ -633,6 +673,40 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
          wgrad_tc_scratch_floats(g.H, TB, maxI);
 }
 
+namespace {
+// input projection of layer l: gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d] (both directions batched); chunked = the gate
+// buffer in the order of the persistent H = 128 kernels
+GemmP xproj_gemm(const GenLayout& g, int64_t B, int l, const float* in, const float* lp, float* gates, bool chunked) {
+  const int64_t TB = (int64_t)g.T * B;
+  const int I = g.in_dim(l);
+  GemmP p;
+  p.tag = "gemm_kernel/lstm_xproj";
+  p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
+  p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
+  p.C = gates; p.scm = 4 * g.H; p.scn = 1;
+  p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
+  p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
+  if (chunked) { p.out_chunk = 1; p.chunk_B = B; p.bsC = (int64_t)g.T * pad128(B) * 4 * g.H; }
+  return p;
+}
+
+// Does layer l run on the chunked gate buffer (persistent H = 128 kernels)?  The answer depends only on the context's math
+// mode, the configuration, the batch size and the alignment of the buffers - the backward pass re-derives the forward's
+// answer for a stash from the same call.
+bool layer_chunked(wgg_ctx* ctx, const GenLayout& g, int64_t B, int l, const float* in, const float* lp, float* gates,
+                   const float* hout, const float* zb) {
+  if (!zb || (reinterpret_cast<uintptr_t>(zb) & 15) || g.Z > 64 || g.pd > 4) return false;
+  if (!lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l])) return false;
+  if (l == 0) return true;
+  return gemm_tc_usable(ctx, xproj_gemm(g, B, l, in, lp, gates, true));
+}
+// WGG_LSTM128_STASH_CHUNK=0: grad-carrying passes keep the row-major stash and the per-timestep kernels (A/B measurements)
+bool stash_chunk_enabled() {
+  static const bool on = [] { const char* e = getenv("WGG_LSTM128_STASH_CHUNK"); return !(e && e[0] == '0'); }();
+  return on;
+}
+}  // namespace
+
 extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, const float* params, const float* proto,
                                      const float* z, int64_t B, float* out, float* stash, float* ws,
                                      int64_t ws_floats, void* stream) {
@@ -667,7 +741,10 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
   }
   // scaled regime: layer 0's input projection without materialising x0 (the stash still gets x0: the backward reads it)
   float* zb = nullptr;
-  if (!rec_has_persistent_kernel(g.H) && g.pd <= 4 && ws) {
+  if (!rec_has_persistent_kernel(g.H) && g.pd <= 4 && stash) {
+    zb = sv.zb;  // part of the stash: the backward pass must be able to re-derive the layout decision without the workspace
+    if ((reinterpret_cast<uintptr_t>(zb) | reinterpret_cast<uintptr_t>(sv.gates[0])) & 15) zb = nullptr;
+  } else if (!rec_has_persistent_kernel(g.H) && g.pd <= 4 && ws) {
     const int64_t base = TB * (g.I0 + 4 * g.H) + fwd_gate_floats(g, B) + rec_generic_scratch_floats(g.H, B, 0);
     float* q = ws + base;
     if (reinterpret_cast<uintptr_t>(q) & 15) q += 4 - ((reinterpret_cast<uintptr_t>(q) & 15) >> 2);
@@ -687,21 +764,10 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     float* gates = stash ? sv.gates[l] : gates_ws;
     float* cseq = stash ? sv.cseq[l] : nullptr;
     hout = stash ? sv.hseq[l] : hbuf[l & 1];
-    // no-grad pass at H = 128 (tensor-core modes): the persistent recurrence reads the gate buffer in chunked order
-    bool chunked = !stash && zb && g.Z <= 64 && lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l]);
-    GemmP p;  // gates[d] = in * W_ih[d]^T + b_ih[d] + b_hh[d]   (both directions batched)
-    p.tag = "gemm_kernel/lstm_xproj";
-    p.A = in; p.M = TB; p.K = I; p.sam = I; p.sak = 1;
-    p.B = lp; p.N = 4 * g.H; p.sbk = 1; p.sbn = I;
-    p.C = gates; p.scm = 4 * g.H; p.scn = 1;
-    p.nbatch = 2; p.bsA = 0; p.bsB = g.dir_stride[l]; p.bsC = TB * 4 * g.H; p.bsBias = g.dir_stride[l];
-    p.bias = lp + g.off_bih[l]; p.bias2 = lp + g.off_bhh[l];
-    if (chunked && l > 0) {
-      GemmP pc = p;
-      pc.out_chunk = 1; pc.chunk_B = B; pc.bsC = (int64_t)g.T * tiles * 128 * 4 * g.H;
-      if (gemm_tc_usable(ctx, pc)) p = pc;
-      else chunked = false;
-    }
+    // H = 128 in the tensor-core modes: the persistent recurrence on the chunked gate buffer (no-grad passes, and - with c
+    // and the activated gates stored in the same order - the grad-carrying pass)
+    const bool chunked = (!stash || stash_chunk_enabled()) && layer_chunked(ctx, g, B, l, in, lp, gates, hout, zb);
+    const GemmP p = xproj_gemm(g, B, l, in, lp, gates, chunked && l > 0);
     if (l == 0 && zb && chunked) {
       dim3 gz((unsigned)tiles, 2);
       zb_chunk_kernel<<<gz, 128, 0, st>>>(z, lp, g.dir_stride[l], g.off_bih[l], g.off_bhh[l], zb, B, g.Z, g.pd, I, 4 * g.H);
@@ -731,7 +797,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
       WGG_TRY(gemm_launch(ctx, p, st));
     }
     if (chunked) {
-      WGG_TRY(lstm128_persist_forward(ctx, gates, lp, g.dir_stride[l], g.off_whh[l], hout, nullptr, g.T, B, 0, 1, st));
+      WGG_TRY(lstm128_persist_forward(ctx, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, g.T, B, stash ? 1 : 0, 1, st));
       in = hout;
       continue;
     }
@@ -777,7 +843,14 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   if (reinterpret_cast<uintptr_t>(daT) & 15) daT += 4 - ((reinterpret_cast<uintptr_t>(daT) & 15) >> 2);
   float* hT[2] = {daT + TB * 2 * H4, daT + TB * 2 * H4 + TB * 2 * H};  // [2H][T B] each
   float* wihT = hT[1] + TB * 2 * H;                                    // [2][I][4H]
+  float* da_rm = wihT + 2 * maxI * H4;                                 // [2][T B][4H] (chunked stash only)
+  if (reinterpret_cast<uintptr_t>(da_rm) & 15) da_rm += 4 - ((reinterpret_cast<uintptr_t>(da_rm) & 15) >> 2);
   int hcur = 0;                                                        // hT[hcur] = transposed output of the current layer
+  float* zb_stash = nullptr;
+  if (!tcp && !rec_has_persistent_kernel(H) && g.pd <= 4) {
+    zb_stash = sv.zb;
+    if ((reinterpret_cast<uintptr_t>(zb_stash) | reinterpret_cast<uintptr_t>(sv.gates[0])) & 15) zb_stash = nullptr;
+  }
 
   if (tcp) {
     // head and LSTM stack backward run entirely on the tcgen05 path (fused head, BPTT, dx and dW/db kernels)
@@ -810,11 +883,22 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     float* dlp = dparams + g.layer_off[l];
     float* da = sv.gates[l];
     const float* in = l == 0 ? sv.x0 : sv.hseq[l - 1];
-    WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, st));
+    // the forward's layout decision for this layer, re-derived (same context mode, same buffers)
+    const bool ch = stash_chunk_enabled() && layer_chunked(ctx, g, B, l, in, lp, da, sv.hseq[l], zb_stash);
+    if (ch) WGG_TRY(lstm_step_tc_backward(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, 1, st));
+    else WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, st));
     const bool tc_ih = wtc && I >= 128 && (I & 3) == 0;   // layer 0 (I0 = C + Z columns) stays on the mma.sync engine
     const bool tc_hh = wtc && H >= 128 && g.T > 1;
+    if (ch) {
+      // chunked da -> K-major image (weight gradients) + row-major copy (input gradient, bias sums, layer-0 weight gradient)
+      dim3 ug((unsigned)(g.T * (pad128(B) / 128)), (unsigned)(H4 / 32), 2);
+      ProfScope prof(ctx, "transpose_tf32_kernel", st, 0.0, 12.0 * (double)TB * H4 * 2, "unchunk_da_kernel");
+      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, g.T, B, H4);
+      WGG_CHECK_LAUNCH(ctx, "unchunk_da_kernel");
+      da = da_rm;
+    }
     if (tc_ih || tc_hh) {
-      WGG_TRY(transpose_tf32_launch(ctx, da, H4, TB * H4, daT, TB, TB * H4, TB, H4, 2, st));
+      if (!ch) WGG_TRY(transpose_tf32_launch(ctx, da, H4, TB * H4, daT, TB, TB * H4, TB, H4, 2, st));
       if (l == g.L - 1 && tc_hh) WGG_TRY(transpose_tf32_launch(ctx, sv.hseq[l], 2 * H, 0, hT[hcur], TB, 0, TB, 2 * H, 1, st));
       if (tc_ih) WGG_TRY(transpose_tf32_launch(ctx, in, I, 0, hT[hcur ^ 1], TB, 0, TB, I, 1, st));
     }
