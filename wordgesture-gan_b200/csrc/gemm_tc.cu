@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
 // CTA = 128 gestures x 64 hidden units x direction; the epilogue overwrites the activated gates of step t with da (the
 // next launch's A operand and the operand of the weight-gradient GEMMs).  The first launch (step T - 1) has K = 0.
 // ---------------------------------------------------------------------------------------------
-constexpr int WNST = 4;
+constexpr int WNST = 4;  // (7 stages measured slower: 19.1 vs 17.2 ms of BPTT per H = 128 step)
 constexpr int WB_BYTES = SUN * BK * 4;  // 8 KB
 
 struct StepBwdParams {

@@ -130,33 +130,92 @@ __global__ void __launch_bounds__(128) zb_chunk_kernel(const float* __restrict__
   }
 }
 
+// block = (tile of 128 gestures, direction, group of 16 gate columns); thread = gesture.  The 16 columns' prototype weights
+// and latent terms stay in registers for all T timesteps; the tile's prototype points go through shared memory 32 timesteps
+// at a time (coalesced reads of each gesture's contiguous (t, c) run); every store is a coalesced 16-byte store.
+constexpr int XP_TS = 32;  // timesteps staged per pass
 __global__ void __launch_bounds__(128) xproj0_chunk_kernel(const float* __restrict__ proto, const float* __restrict__ zbc,
                                                            const float* __restrict__ w, int64_t dir_stride,
                                                            float* __restrict__ gates, int T, int64_t B, int C, int pd, int I0,
                                                            int H4) {
-  extern __shared__ float4 s_w3[];  // [H4]: the pd (<= 4) prototype columns of W_ih[d][n]
-  const int tile = blockIdx.x, d = blockIdx.y, rl = threadIdx.x, tiles = gridDim.x;
-  for (int n = threadIdx.x; n < H4; n += 128) {
-    const float* wr = w + d * dir_stride + (int64_t)n * I0;
-    s_w3[n] = make_float4(__ldg(wr), pd > 1 ? __ldg(wr + 1) : 0.f, pd > 2 ? __ldg(wr + 2) : 0.f, pd > 3 ? __ldg(wr + 3) : 0.f);
-  }
-  __syncthreads();
+  extern __shared__ float s_p[];  // [128 rows][XP_TS * C + 1]
+  const int tile = blockIdx.x, d = blockIdx.y, cg = blockIdx.z, rl = threadIdx.x, tiles = gridDim.x;
+  const int ld = XP_TS * C + 1;
   const int64_t b = (int64_t)tile * 128 + rl;
-  if (b >= B) return;
-  const float* zb = zbc + (((int64_t)d * tiles + tile) * (H4 / 4) * 128 + rl) * 4;
-  for (int t = blockIdx.z; t < T; t += gridDim.z) {
-    const float* pp = proto + (b * T + t) * C;
-    const float x0 = __ldg(pp), x1 = pd > 1 ? __ldg(pp + 1) : 0.f, x2 = pd > 2 ? __ldg(pp + 2) : 0.f, x3 = pd > 3 ? __ldg(pp + 3) : 0.f;
-    float* g = gates + ((((int64_t)d * T + t) * tiles + tile) * (H4 / 4) * 128 + rl) * 4;
-#pragma unroll 4
-    for (int n4 = 0; n4 < H4 / 4; ++n4) {
-      float4 o = *reinterpret_cast<const float4*>(zb + (int64_t)n4 * 512);
-      const float4 w0 = s_w3[4 * n4], w1 = s_w3[4 * n4 + 1], w2 = s_w3[4 * n4 + 2], w3 = s_w3[4 * n4 + 3];
-      o.x += x0 * w0.x + x1 * w0.y + x2 * w0.z + x3 * w0.w;
-      o.y += x0 * w1.x + x1 * w1.y + x2 * w1.z + x3 * w1.w;
-      o.z += x0 * w2.x + x1 * w2.y + x2 * w2.z + x3 * w2.w;
-      o.w += x0 * w3.x + x1 * w3.y + x2 * w3.z + x3 * w3.w;
-      *reinterpret_cast<float4*>(g + (int64_t)n4 * 512) = o;
+  const int64_t b0 = (int64_t)tile * 128;
+  const int nrows = B - b0 < 128 ? (int)(B - b0) : 128;
+  float wv[16][3], zv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float* wr = w + d * dir_stride + (int64_t)(cg * 16 + j) * I0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wv[j][c] = c < pd ? __ldg(wr + c) : 0.f;
+  }
+  const float* zb = zbc + ((((int64_t)d * tiles + tile) * (H4 / 4) + cg * 4) * 128 + rl) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(zb + (int64_t)q * 512);
+    zv[4 * q] = v.x; zv[4 * q + 1] = v.y; zv[4 * q + 2] = v.z; zv[4 * q + 3] = v.w;
+  }
+  for (int t0 = 0; t0 < T; t0 += XP_TS) {
+    const int nt = T - t0 < XP_TS ? T - t0 : XP_TS;
+    __syncthreads();
+    // rows of nt * C contiguous floats: consecutive threads read consecutive floats of one row
+    for (int i = threadIdx.x; i < nrows * nt * C; i += 128) {
+      const int r = i / (nt * C), k = i % (nt * C);
+      s_p[r * ld + k] = __ldg(proto + ((b0 + r) * T + t0) * C + k);
+    }
+    __syncthreads();
+    if (b < B) {
+      for (int tt = 0; tt < nt; ++tt) {
+        const float* pp = s_p + rl * ld + tt * C;
+        const float x0 = pp[0], x1 = pd > 1 ? pp[1] : 0.f, x2 = pd > 2 ? pp[2] : 0.f;
+        float* g = gates + (((((int64_t)d * T + t0 + tt) * tiles + tile) * (H4 / 4) + cg * 4) * 128 + rl) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o;
+          o.x = zv[4 * q] + x0 * wv[4 * q][0] + x1 * wv[4 * q][1] + x2 * wv[4 * q][2];
+          o.y = zv[4 * q + 1] + x0 * wv[4 * q + 1][0] + x1 * wv[4 * q + 1][1] + x2 * wv[4 * q + 1][2];
+          o.z = zv[4 * q + 2] + x0 * wv[4 * q + 2][0] + x1 * wv[4 * q + 2][1] + x2 * wv[4 * q + 2][2];
+          o.w = zv[4 * q + 3] + x0 * wv[4 * q + 3][0] + x1 * wv[4 * q + 3][1] + x2 * wv[4 * q + 3][2];
+          *reinterpret_cast<float4*>(g + (int64_t)q * 512) = o;
+        }
+      }
+    }
+  }
+}
+
+// Output head of the scaled path: out[b][t][c] = tanh(h[t][b][:] . Wo[c] + bo[c])  (models.py:161-163; fp32).  One warp per
+// (t, b) row: a coalesced read of the 2H hidden values, Wo in shared memory, warp-shuffle reduction - a pass over hseq at
+// memory speed instead of T batched N = 3 GEMMs.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ wo,
+                                                       const float* __restrict__ bo, float* __restrict__ out, int T, int64_t B,
+                                                       int K, int C) {
+  extern __shared__ float s_wo[];  // [C][K]
+  for (int i = threadIdx.x; i < C * K; i += 256) s_wo[i] = __ldg(wo + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t nrows = (int64_t)T * B;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < nrows; row += warps) {
+    const float* hr = h + row * K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 4 * lane; k < K; k += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(hr + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < C) {
+          const float4 wv = *reinterpret_cast<const float4*>(s_wo + c * K + k);
+          acc[c] += x.x * wv.x + x.y * wv.y + x.z * wv.z + x.w * wv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane < C) {
+      const float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      const int64_t t = row / B, b = row % B;
+      out[(b * T + t) * C + lane] = tanhf(v + __ldg(bo + lane));
     }
   }
 }
@@ -695,7 +754,7 @@ GemmP xproj_gemm(const GenLayout& g, int64_t B, int l, const float* in, const fl
 // answer for a stash from the same call.
 bool layer_chunked(wgg_ctx* ctx, const GenLayout& g, int64_t B, int l, const float* in, const float* lp, float* gates,
                    const float* hout, const float* zb) {
-  if (!zb || (reinterpret_cast<uintptr_t>(zb) & 15) || g.Z > 64 || g.pd > 4) return false;
+  if (!zb || (reinterpret_cast<uintptr_t>(zb) & 15) || g.Z > 64 || g.pd > 3) return false;
   if (!lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l])) return false;
   if (l == 0) return true;
   return gemm_tc_usable(ctx, xproj_gemm(g, B, l, in, lp, gates, true));
@@ -772,12 +831,12 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
       dim3 gz((unsigned)tiles, 2);
       zb_chunk_kernel<<<gz, 128, 0, st>>>(z, lp, g.dir_stride[l], g.off_bih[l], g.off_bhh[l], zb, B, g.Z, g.pd, I, 4 * g.H);
       WGG_CHECK_LAUNCH(ctx, "zb_chunk_kernel");
-      int zs = (int)(4 * (int64_t)ctx->sm_count / (2 * tiles) + 1);
-      if (zs > g.T) zs = g.T;
-      dim3 grid((unsigned)tiles, 2, (unsigned)zs);
+      dim3 grid((unsigned)tiles, 2, (unsigned)(4 * g.H / 16));
       ProfScope prof(ctx, "xproj0_kernel", st, 2.0 * TB * 8.0 * g.H * g.pd, 4.0 * TB * 8.0 * g.H, "xproj0_kernel");
-      xproj0_chunk_kernel<<<grid, 128, (size_t)4 * g.H * sizeof(float4), st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C,
-                                                                                g.pd, I, 4 * g.H);
+      const size_t xsm = (size_t)128 * (XP_TS * g.C + 1) * sizeof(float);
+      if (!wgg_smem_ok(ctx, xproj0_chunk_kernel, xsm))
+        return wgg_fail(ctx, WGG_ECUDA, "xproj0_chunk_kernel: cannot reserve shared memory%s");
+      xproj0_chunk_kernel<<<grid, 128, xsm, st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C, g.pd, I, 4 * g.H);
       WGG_CHECK_LAUNCH(ctx, "xproj0_chunk_kernel");
     } else if (l == 0 && zb) {
       GemmP q;  // zb[d] (B x 4H) = z * W_ih[d][:, pd:]^T + b_ih[d] + b_hh[d]     (fp32)
@@ -803,6 +862,16 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     }
     WGG_TRY(rec_fwd_launch(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, rec_scratch, g.T, B, stash ? 1 : 0, st));
     in = hout;
+  }
+  if (!rec_has_persistent_kernel(g.H) && g.C <= 4 && (2 * g.H) % 4 == 0 && (reinterpret_cast<uintptr_t>(hout) & 15) == 0 &&
+      (size_t)g.C * 2 * g.H * sizeof(float) <= 48 * 1024) {
+    int64_t blocks = cdiv64(TB, 8);
+    if (blocks > 16 * (int64_t)ctx->sm_count) blocks = 16 * (int64_t)ctx->sm_count;
+    ProfScope prof(ctx, "head_fwd_kernel", st, 2.0 * TB * 2.0 * g.H * g.C, 4.0 * TB * (2.0 * g.H + g.C), "head_fwd_kernel");
+    head_fwd_kernel<<<(unsigned)blocks, 256, (size_t)g.C * 2 * g.H * sizeof(float), st>>>(hout, params + g.off_wo, params + g.off_bo,
+                                                                                         out, g.T, B, 2 * g.H, g.C);
+    WGG_CHECK_LAUNCH(ctx, "head_fwd_kernel");
+    return WGG_OK;
   }
   GemmP p;  // out[b][t][:] = tanh(h[t][b][:] * Wo^T + bo), batched over t to transpose (t,b)->(b,t)
   p.tag = "gemm_kernel/head_fwd";
