@@ -161,8 +161,9 @@ int gemm_tc_launch(wgg_ctx* ctx, const GemmP& p, cudaStream_t st);
 // fused per-timestep kernels of the scaled recurrence (tcgen05 recurrent product + LSTM cell in the epilogue, gemm_tc.cu)
 bool lstm_step_tc_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
                          int64_t dir_stride);
+// chunked = 1: gate buffer / c in the chunked order [..][tile][columns / 4][128][4] (see gemm_tc.cu)
 int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
-                         float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st);
+                         float* cseq, float* cstate, int T, int64_t B, int store, int chunked, cudaStream_t st);
 // persistent recurrence for gen_hidden_dim = 128 (one launch per layer; gemm_tc.cu)
 bool lstm128_persist_usable(const wgg_ctx* ctx, int H, const float* gates, const float* hseq, const float* lp, int64_t off_whh,
                             int64_t dir_stride);

@@ -275,7 +275,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
-template <int SNST>
+// CHUNK = 1: gate buffer, c (sequence or carried state) in the chunked order [..][tile][columns / 4][128 rows][4 floats] - the
+// epilogue's 16-byte accesses are then coalesced (lane = gesture) instead of one 128-byte line per lane.
+template <int SNST, int CHUNK>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __grid_constant__ StepFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -354,14 +356,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
     const int row = m0 + quarter * 32 + lane;
     const bool rok = row < p.B;
     const int64_t TB = (int64_t)p.T * p.B;
-    float* gp = p.gates + (((int64_t)dir * p.T + t) * p.B + (rok ? row : 0)) * 4 * H;
-    float* hp = p.hseq + ((int64_t)t * p.B + (rok ? row : 0)) * 2 * H + dir * H;
-    const float* cprev = nullptr;
-    if (p.step > 0)
-      cprev = p.store ? p.cseq + (int64_t)dir * TB * H + ((int64_t)tp * p.B + (rok ? row : 0)) * H
-                      : p.cstate + ((int64_t)dir * p.B + (rok ? row : 0)) * H;
-    float* cout = p.store ? p.cseq + (int64_t)dir * TB * H + ((int64_t)t * p.B + (rok ? row : 0)) * H
-                          : p.cstate + ((int64_t)dir * p.B + (rok ? row : 0)) * H;
+    const int rl = quarter * 32 + lane;
+    const int tiles = (p.B + SBM - 1) / SBM;
+    const int64_t rr0 = rok ? row : 0;
+    // CHUNK: the 4 columns [n, n + 4) of this row inside a [columns / 4][128][4] block: block + (n >> 2) * 512 + rl * 4
+    auto at = [&](float* base, int n) -> float* { return CHUNK ? base + (int64_t)(n >> 2) * 512 : base + n; };
+    float* gp = CHUNK ? p.gates + ((((int64_t)dir * p.T + t) * tiles + blockIdx.y) * (int64_t)(4 * H) * SBM + rl * 4)
+                      : p.gates + (((int64_t)dir * p.T + t) * p.B + rr0) * 4 * H;
+    float* hp = p.hseq + ((int64_t)t * p.B + rr0) * 2 * H + dir * H;
+    auto cptr = [&](int tt) -> float* {  // c of this row: stored sequence (tt = timestep) or the carried state
+      if (p.store)
+        return CHUNK ? p.cseq + ((((int64_t)dir * p.T + tt) * tiles + blockIdx.y) * (H / 4) * SBM + rl) * 4
+                     : p.cseq + (int64_t)dir * TB * H + ((int64_t)tt * p.B + rr0) * H;
+      return CHUNK ? p.cstate + (((int64_t)dir * tiles + blockIdx.y) * (H / 4) * SBM + rl) * 4 : p.cstate + ((int64_t)dir * p.B + rr0) * H;
+    };
+    float* cprev = p.step > 0 ? cptr(tp) : nullptr;
+    float* cout = cptr(t);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // four chunks of 8 hidden units per thread (two adjacent 16-byte accesses = one full 32-byte sector per row and gate); a
     // chunk's operands (the four pre-activations, c_prev: ten 16-byte loads) are requested two chunks ahead of their use,
@@ -374,15 +384,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
       const bool ok = rok && u < H;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        pre[slot][g][0] = ok ? ld4(gp + g * H + u) : z4;
-        pre[slot][g][1] = ok ? ld4(gp + g * H + u + 4) : z4;
+        pre[slot][g][0] = ok ? ld4(at(gp, g * H + u)) : z4;
+        pre[slot][g][1] = ok ? ld4(at(gp, g * H + u + 4)) : z4;
       }
     };
     auto load_c = [&](int c, int slot) {
       const int u = u0 + uh * 32 + c * 8;
       const bool ok = rok && u < H && cprev;
-      cp[slot][0] = ok ? ld4(cprev + u) : z4;
-      cp[slot][1] = ok ? ld4(cprev + u + 4) : z4;
+      cp[slot][0] = ok ? ld4(at(cprev, u)) : z4;
+      cp[slot][1] = ok ? ld4(at(cprev, u + 4)) : z4;
     };
     load_pre(0, 0);
     load_pre(1, 1);
@@ -437,13 +447,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
           }
           st4(hp + u, make_float4(hv[0], hv[1], hv[2], hv[3]));
           st4(hp + u + 4, make_float4(hv[4], hv[5], hv[6], hv[7]));
-          st4(cout + u, make_float4(cv[0], cv[1], cv[2], cv[3]));
-          st4(cout + u + 4, make_float4(cv[4], cv[5], cv[6], cv[7]));
+          st4(at(cout, u), make_float4(cv[0], cv[1], cv[2], cv[3]));
+          st4(at(cout, u + 4), make_float4(cv[4], cv[5], cv[6], cv[7]));
           if (p.store) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              st4(gp + g * H + u, make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
-              st4(gp + g * H + u + 4, make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
+              st4(at(gp, g * H + u), make_float4(a[g][0], a[g][1], a[g][2], a[g][3]));
+              st4(at(gp, g * H + u + 4), make_float4(a[g][4], a[g][5], a[g][6], a[g][7]));
             }
           }
         }
@@ -1193,7 +1203,7 @@ bool lstm_step_tc_usable(const wgg_ctx* ctx, int H, const float* gates, const fl
 }
 
 int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
-                         float* cseq, float* cstate, int T, int64_t B, int store, cudaStream_t st) {
+                         float* cseq, float* cstate, int T, int64_t B, int store, int chunked, cudaStream_t st) {
   gtc::StepFwdParams prm;
   memset(&prm, 0, sizeof(prm));
   for (int d = 0; d < 2; ++d) {
@@ -1205,7 +1215,9 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
   prm.T = T; prm.B = (int)B; prm.H = H; prm.store = store; prm.gerr = ctx->async_err;
   static const int nst = [] { const char* e = getenv("WGG_STEP_NST"); const int v = e ? atoi(e) : 3; return v == 2 || v == 4 ? v : 3; }();
   const size_t smem = (size_t)nst * (gtc::SA_BYTES + gtc::SB_BYTES) + 128 + 16 + 1024;
-  void (*kernel)(const gtc::StepFwdParams) = nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4> : gtc::gemm_tc_lstm_fwd_kernel<3>;
+  void (*kernel)(const gtc::StepFwdParams) =
+      chunked ? (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 1> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 1> : gtc::gemm_tc_lstm_fwd_kernel<3, 1>)
+              : (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 0> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 0> : gtc::gemm_tc_lstm_fwd_kernel<3, 0>);
   if (!wgg_smem_ok(ctx, kernel, smem))
     return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_fwd_kernel: cannot reserve shared memory%s");
   dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);

@@ -531,7 +531,7 @@ int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
   if (rec_has_persistent_kernel(H)) return 0;
   // backward: dh_rec | dc, or (fused tcgen05 step kernels) dc | the W_hh^T images
   // (the carried dc of the chunked BPTT is padded to whole 128-gesture tiles)
-  return backward ? 4 * ((B + 127) / 128 * 128) * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * B * (int64_t)H;
+  return backward ? 4 * ((B + 127) / 128 * 128) * (int64_t)H + 8 * (int64_t)H * H + 64 : 2 * ((B + 127) / 128 * 128) * (int64_t)H;
 }
 
 // K-major operand images of the tcgen05 weight / input-gradient GEMMs of the step-by-step path (backward only):
@@ -551,7 +551,7 @@ int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t 
   if (lstm128_persist_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride) && lstm128_persist_rowmajor())
     return lstm128_persist_forward(ctx, gates, lp, dir_stride, off_whh, hseq, cseq, T, B, store, 0, st);
   if (lstm_step_tc_usable(ctx, H, gates, hseq, lp, off_whh, dir_stride))
-    return lstm_step_tc_forward(ctx, H, gates, lp, dir_stride, off_whh, hseq, cseq, cstate, T, B, store, st);
+    return lstm_step_tc_forward(ctx, H, gates, lp, dir_stride, off_whh, hseq, cseq, cstate, T, B, store, 0, st);
   for (int step = 0; step < T; ++step) {
     if (step > 0) {
       // direction 0 consumes h at t - 1 and writes gates at t = step; direction 1 consumes h at t + 1, writes t = T-1-step
@@ -673,7 +673,8 @@ void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
 // block = (t * tiles + tile, group of 32 columns, dir); 256 threads; both outputs written in 128-byte runs.
 __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict__ dac, float* __restrict__ daT,
                                                          float* __restrict__ da_rm, int T, int64_t B, int C4) {
-  __shared__ float tile[128][33];
+  __shared__ float tile[128][33];                   // [row][column]: source of the row-major copy
+  __shared__ __align__(16) float tileT[32][132];    // [column][row]: source of the K-major image
   const int tiles = (int)((B + 127) / 128);
   const int t = blockIdx.x / tiles, tl = blockIdx.x % tiles, cg = blockIdx.y, d = blockIdx.z;
   const int64_t TB = (int64_t)T * B;
@@ -682,18 +683,30 @@ __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict
     const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)i * 4);
     const int ch = i >> 7, r = i & 127;
     tile[r][4 * ch] = v.x; tile[r][4 * ch + 1] = v.y; tile[r][4 * ch + 2] = v.z; tile[r][4 * ch + 3] = v.w;
+    tileT[4 * ch][r] = v.x; tileT[4 * ch + 1][r] = v.y; tileT[4 * ch + 2][r] = v.z; tileT[4 * ch + 3][r] = v.w;
   }
   __syncthreads();
   const int64_t b0 = (int64_t)tl * 128;
   const int nrows = B - b0 < 128 ? (int)(B - b0) : 128;
   const int64_t m0 = (int64_t)t * B + b0;
-  for (int i = threadIdx.x; i < 32 * 128; i += 256) {  // daT: column-major runs of 128 rows
-    const int c = i >> 7, r = i & 127;
-    if (r < nrows) daT[((int64_t)d * C4 + cg * 32 + c) * TB + m0 + r] = tile[r][c];
+  if ((B & 3) == 0) {  // 16-byte stores (T B and the tile offsets are multiples of 4)
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {  // daT: column-major runs of 128 rows, 4 rows per store
+      const int c = i >> 5, r = (i & 31) * 4;
+      if (r < nrows)
+        *reinterpret_cast<float4*>(daT + ((int64_t)d * C4 + cg * 32 + c) * TB + m0 + r) =
+            *reinterpret_cast<const float4*>(&tileT[c][r]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+      const int c = i >> 7, r = i & 127;
+      if (r < nrows) daT[((int64_t)d * C4 + cg * 32 + c) * TB + m0 + r] = tileT[c][r];
+    }
   }
-  for (int i = threadIdx.x; i < 32 * 128; i += 256) {  // da_rm: rows of 32 columns
-    const int r = i >> 5, c = i & 31;
-    if (r < nrows) da_rm[((int64_t)d * TB + m0 + r) * C4 + cg * 32 + c] = tile[r][c];
+  for (int i = threadIdx.x; i < 8 * 128; i += 256) {  // da_rm: rows of 32 columns, 4 columns per store
+    const int r = i >> 3, c = (i & 7) * 4;
+    if (r < nrows)
+      *reinterpret_cast<float4*>(da_rm + ((int64_t)d * TB + m0 + r) * C4 + cg * 32 + c) =
+          make_float4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);
   }
 }
 
@@ -729,7 +742,7 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   // dpre | dh | dx | split-K partials | column-sum scratch | (tcgen05 path: its own backward workspace)
   return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2) +
          generator_tc_bwd_workspace_floats(cfg, B) + rec_generic_scratch_floats(g.H, B, 1) +
-         wgrad_tc_scratch_floats(g.H, TB, maxI);
+         wgrad_tc_scratch_floats(g.H, TB, maxI) + 32;  // + alignment slack of the sub-buffers
 }
 
 namespace {
@@ -749,13 +762,15 @@ GemmP xproj_gemm(const GenLayout& g, int64_t B, int l, const float* in, const fl
   return p;
 }
 
-// Does layer l run on the chunked gate buffer (persistent H = 128 kernels)?  The answer depends only on the context's math
+// Does layer l run on the chunked gate buffer (scaled regime, tensor-core modes: the persistent H = 128 kernel or the chunked
+// variants of the per-timestep kernels)?  The answer depends only on the context's math
 // mode, the configuration, the batch size and the alignment of the buffers - the backward pass re-derives the forward's
 // answer for a stash from the same call.
 bool layer_chunked(wgg_ctx* ctx, const GenLayout& g, int64_t B, int l, const float* in, const float* lp, float* gates,
                    const float* hout, const float* zb) {
-  if (!zb || (reinterpret_cast<uintptr_t>(zb) & 15) || g.Z > 64 || g.pd > 3) return false;
-  if (!lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l])) return false;
+  static const bool on = [] { const char* e = getenv("WGG_SCALED_CHUNK"); return !(e && e[0] == '0'); }();
+  if (!on || !zb || (reinterpret_cast<uintptr_t>(zb) & 15) || g.Z > 64 || g.pd > 3 || (g.H & 7)) return false;
+  if (!lstm_step_tc_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l])) return false;
   if (l == 0) return true;
   return gemm_tc_usable(ctx, xproj_gemm(g, B, l, in, lp, gates, true));
 }
@@ -856,7 +871,11 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
       WGG_TRY(gemm_launch(ctx, p, st));
     }
     if (chunked) {
-      WGG_TRY(lstm128_persist_forward(ctx, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, g.T, B, stash ? 1 : 0, 1, st));
+      if (lstm128_persist_usable(ctx, g.H, gates, hout, lp, g.off_whh[l], g.dir_stride[l]))
+        WGG_TRY(lstm128_persist_forward(ctx, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, g.T, B, stash ? 1 : 0, 1, st));
+      else
+        WGG_TRY(lstm_step_tc_forward(ctx, g.H, gates, lp, g.dir_stride[l], g.off_whh[l], hout, cseq, rec_scratch, g.T, B,
+                                     stash ? 1 : 0, 1, st));
       in = hout;
       continue;
     }
@@ -899,13 +918,15 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   const bool tcp = ctx->math_mode >= 1 && generator_tc_supported(cfg);
   StashView sv;
   if (!tcp) stash_view(g, B, stash, &sv);
+  // every sub-buffer starts on a 16-byte boundary (the kernels of the chunked path make 16-byte accesses to dh and the scratch)
+  auto a4 = [](int64_t n) { return (n + 3) & ~(int64_t)3; };
   float* dpre = ws;
-  float* dh = dpre + TB * g.C;
-  float* dx = dh + TB * maxI;
-  float* part = dx + TB * maxI;
-  float* csws = part + gemm_splitk_ws_floats(H4, maxI, 2);
-  float* tcws = csws + colsum_ws_floats(H4, 2);
-  float* rec_scratch = tcws + generator_tc_bwd_workspace_floats(cfg, B);  // dh_rec | dc of the step-by-step recurrence
+  float* dh = dpre + a4(TB * g.C);
+  float* dx = dh + a4(TB * maxI);
+  float* part = dx + a4(TB * maxI);
+  float* csws = part + a4(gemm_splitk_ws_floats(H4, maxI, 2));
+  float* tcws = csws + a4(colsum_ws_floats(H4, 2));
+  float* rec_scratch = tcws + a4(generator_tc_bwd_workspace_floats(cfg, B));  // dh_rec | dc of the step-by-step recurrence
   // scaled regime, tensor-core modes: weight / input gradients as K-major tcgen05 GEMMs over transposed operand images
   const bool wtc = !tcp && !rec_has_persistent_kernel(H) && lstm_wgrad_tc_usable(ctx, H, B, g.T);
   float* daT = rec_scratch + rec_generic_scratch_floats(H, B, 1);
