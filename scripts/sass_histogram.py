@@ -14,12 +14,13 @@ for line in sass.splitlines():
         kern = re.sub(r"^void ", "", re.sub(r"\(.*", "", kern))
         hist[kern] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m and kern:
         hist[kern][m.group(1)] += 1
-KEY = ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "UTMALDG", "SYNCS", "MUFU", "HMMA", "FFMA", "LDGSTS")
+KEY = ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "MUFU", "HMMA", "FFMA", "LDGSTS")
 print("# SASS opcode histogram of libwgg_sm100.so (sm_100a), `cuobjdump -sass`\n")
 print("UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld (TMEM load), UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (bulk async copy),")
+print("UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA with a tensor map),")
 print("SYNCS = mbarrier ops, HMMA = mma.sync (the 3xTF32 / generic-shape engine), LDGSTS = cp.async.  Kernels without any")
 print("tensor-core or async-copy instruction are listed at the end with their instruction count only.\n")
 print("| kernel | instr | " + " | ".join(KEY) + " |")

@@ -771,13 +771,11 @@ int conv_tc_fwd_launch(wgg_ctx* ctx, const float* in, const float* wimg, const f
   const int WCS = (N / 8) * 128;
   const size_t smem = (size_t)((Kchunks * WCS + 1023) / 1024) * 1024 + ctc::NST * (size_t)CinC * ctc::CS + 64 * 4 + (2 * ctc::NST + 2) * 8 + 16;
   const bool multi = a.halves > 1;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[multi]) {
-    const cudaError_t e = multi ? cudaFuncSetAttribute(ctc::conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(ctc::conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return wgg_fail(ctx, WGG_ECUDA, "conv_tc_fwd_kernel: cannot reserve shared memory%s");
-    configured[multi] = smem;
-  }
+  // raise the kernel's dynamic shared memory limit once per context (= per device) to the opt-in maximum: the layers of a
+  // model need different amounts
+  if (smem > 227 * 1024 || !(multi ? wgg_smem_ok(ctx, ctc::conv_tc_fwd_kernel<true>, 227 * 1024)
+                                    : wgg_smem_ok(ctx, ctc::conv_tc_fwd_kernel<false>, 227 * 1024)))
+    return wgg_fail(ctx, WGG_ECUDA, "conv_tc_fwd_kernel: cannot reserve shared memory%s");
   const double flops = 2.0 * (double)B * T * N * (double)(taps * CinC * 4);
   ProfScope prof(ctx, "conv_tc_fwd_kernel", st, flops, (double)B * T * 4.0 * (CinC * 4 + N), tag);
   if (multi) ctc::conv_tc_fwd_kernel<true><<<conv_tc_grid(ctx, B * a.halves), ctc::NTHREADS, smem, st>>>(a);
