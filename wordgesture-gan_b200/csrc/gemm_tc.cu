@@ -277,7 +277,25 @@ __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_ca
 
 // CHUNK = 1: gate buffer, c (sequence or carried state) in the chunked order [..][tile][columns / 4][128 rows][4 floats] - the
 // epilogue's 16-byte accesses are then coalesced (lane = gesture) instead of one 128-byte line per lane.
-template <int SNST, int CHUNK>
+// CL = 2: the two CTAs of a cluster work on neighbouring row tiles of the same (unit block, direction) and therefore need the
+// same weight slabs: each fetches half of every slab (two of the four gate boxes) and multicasts it into both CTAs' rings, so a
+// CTA streams A + B / 2 instead of A + B through L2 (the kernel is bound by that stream: 48 KB per k-slab and CTA).  A ring
+// stage is refilled only after BOTH CTAs' MMAs have released it (tcgen05.commit multicast onto both EMPTY barriers).
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int SNST, int CHUNK, int CL>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __grid_constant__ StepFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
   auto EMPTY = [&](int s) { return bar0 + 8u * (SNST + s); };
   const uint32_t DONE = bar0 + 8u * (2 * SNST);
   if (tid == 0) {
-    for (int s = 0; s < SNST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < SNST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), CL); }
     mbar_init(DONE, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -307,8 +325,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  uint32_t crank = 0;
+  if (CL > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    cluster_sync_all();  // the peer's barriers exist before anything of ours can reach them
+  }
   const uint32_t tmem_base = *s_tmem;
   const int KT = p.step > 0 ? (H + BK - 1) / BK : 0;
+  // weight boxes of one ring stage: alone, all four gates; in a pair, gates {2 rank, 2 rank + 1} multicast to both CTAs
+  auto load_b = [&](int s, int it) {
+    if (CL > 1) {
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = 2 * (int)crank + gg;
+        tma_load_2d_mc(smem_u32(s_b + s * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(s), (uint16_t)0x3);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        tma_load_2d(smem_u32(s_b + s * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(s));
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -316,9 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
       const int npre = KT < SNST ? KT : SNST;
       for (int it = 0; it < npre; ++it) {
         mbar_expect_tx(FULL(it), SA_BYTES + SB_BYTES);
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          tma_load_2d(smem_u32(s_b + it * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(it));
+        load_b(it, it);
       }
       pdl_wait();
       pdl_launch_dependents();
@@ -328,9 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
         if (!mbar_wait(EMPTY(s), (uint32_t)(((it / SNST) & 1) ^ 1), s_abort, p.gerr, 74)) break;
         mbar_expect_tx(FULL(s), SA_BYTES + SB_BYTES);
         tma_load_3d(smem_u32(s_a + s * SA_BYTES), &p.a[dir], it * BK, m0, tp, FULL(s));
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          tma_load_2d(smem_u32(s_b + s * SB_BYTES + g * SBOX_BYTES), &p.b[dir], it * BK, g * H + u0, FULL(s));
+        load_b(s, it);
       }
     }
   } else if (warp == 1) {
@@ -345,7 +378,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks)
           mma_tf32_ss(tmem_base, desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32), idesc, (it | ks) ? 1u : 0u);
-        mma_commit(EMPTY(s));
+        if (CL > 1) mma_commit_mc(EMPTY(s), (uint16_t)0x3);
+        else mma_commit(EMPTY(s));
       }
       __syncwarp();
     }
@@ -462,6 +496,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_lstm_fwd_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -1177,15 +1212,25 @@ bool make_map_time(CUtensorMap* m, const float* base, int64_t K, int64_t B, int6
 // Launch of one timestep kernel with programmatic stream serialisation (the kernels call griddepcontrol.wait before they
 // touch anything the previous launch wrote); WGG_PDL=0 falls back to ordinary stream order.
 template <class P>
-int launch_step(wgg_ctx* ctx, void (*kernel)(const P), dim3 grid, size_t smem, cudaStream_t st, const P& prm, const char* name) {
+int launch_step(wgg_ctx* ctx, void (*kernel)(const P), dim3 grid, size_t smem, cudaStream_t st, const P& prm, const char* name,
+                int cluster_y = 1) {
   static const bool pdl = [] { const char* e = getenv("WGG_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_y > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = (unsigned)cluster_y; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kernel, prm);
   return wgg_check_launch(ctx, name);
 }
@@ -1215,18 +1260,23 @@ int lstm_step_tc_forward(wgg_ctx* ctx, int H, float* gates, const float* lp, int
   prm.T = T; prm.B = (int)B; prm.H = H; prm.store = store; prm.gerr = ctx->async_err;
   static const int nst = [] { const char* e = getenv("WGG_STEP_NST"); const int v = e ? atoi(e) : 3; return v == 2 || v == 4 ? v : 3; }();
   const size_t smem = (size_t)nst * (gtc::SA_BYTES + gtc::SB_BYTES) + 128 + 16 + 1024;
+  // WGG_STEP_CLUSTER=2: pairs of row tiles share the weight slabs by TMA multicast (3-stage ring, at least two row tiles)
+  static const int cl_env = [] { const char* e = getenv("WGG_STEP_CLUSTER"); return e ? atoi(e) : 1; }();
+  const int cl = (cl_env == 2 && nst == 3 && cdiv64(B, gtc::SBM) >= 2) ? 2 : 1;
   void (*kernel)(const gtc::StepFwdParams) =
-      chunked ? (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 1> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 1> : gtc::gemm_tc_lstm_fwd_kernel<3, 1>)
-              : (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 0> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 0> : gtc::gemm_tc_lstm_fwd_kernel<3, 0>);
+      cl == 2 ? (chunked ? gtc::gemm_tc_lstm_fwd_kernel<3, 1, 2> : gtc::gemm_tc_lstm_fwd_kernel<3, 0, 2>)
+      : chunked ? (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 1, 1> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 1, 1> : gtc::gemm_tc_lstm_fwd_kernel<3, 1, 1>)
+                : (nst == 2 ? gtc::gemm_tc_lstm_fwd_kernel<2, 0, 1> : nst == 4 ? gtc::gemm_tc_lstm_fwd_kernel<4, 0, 1> : gtc::gemm_tc_lstm_fwd_kernel<3, 0, 1>);
   if (!wgg_smem_ok(ctx, kernel, smem))
     return wgg_fail(ctx, WGG_ECUDA, "gemm_tc_lstm_fwd_kernel: cannot reserve shared memory%s");
-  dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)cdiv64(B, gtc::SBM), 2);
+  // row tiles padded to whole clusters: the extra CTA fetches its share of the weights, multiplies zero-filled rows, stores nothing
+  dim3 grid((unsigned)cdiv64(H, gtc::SUN), (unsigned)(cdiv64(cdiv64(B, gtc::SBM), cl) * cl), 2);
   for (int step = 0; step < T; ++step) {
     prm.step = step;
     ProfScope prof(ctx, "gemm_tc_lstm_fwd_kernel", st, step > 0 ? 2.0 * B * 4.0 * H * H * 2 : 0.0,
                    4.0 * 2 * ((double)B * (step > 0 ? H : 0) + (double)B * 4 * H * (store ? 2 : 1) + 3.0 * B * H),
                    "gemm_tc_lstm_fwd_kernel");
-    WGG_TRY(gtc::launch_step(ctx, kernel, grid, smem, st, prm, "gemm_tc_lstm_fwd_kernel"));
+    WGG_TRY(gtc::launch_step(ctx, kernel, grid, smem, st, prm, "gemm_tc_lstm_fwd_kernel", cl));
   }
   return WGG_OK;
 }
