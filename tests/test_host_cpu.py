@@ -63,6 +63,29 @@ def test_flat_layout_sizes_agree_with_c(kw):
         (3 if mc.prototype_has_time else 2) + mc.latent_dim + 12 * mc.gen_hidden_dim * mc.gen_num_layers)
 
 
+@pytest.mark.parametrize("H,T,L", [(128, 256, 4), (96, 64, 3), (512, 256, 2)])
+def test_scaled_regime_buffer_sizes(H, T, L):
+    """Scaled regime (BASELINE configs[3]; csrc/lstm.cu stash_floats / wgg_generator_workspace_floats): the stash holds x0 and
+    hseq at the true batch, the gate / c buffers padded to whole 128-gesture tiles (chunked order of the tcgen05 recurrence
+    kernels) and the per-gesture latent term of the layer-0 projection; the sizes are host-side functions of (config, batch)
+    alone, grow with the batch and cover the row-major layout as well."""
+    mc = wgg.ModelConfig(gen_hidden_dim=H, seq_length=T, gen_num_layers=L)
+    lib, cfg = _lib.lib(), _lib.c_cfg(mc)
+    I0 = (3 if mc.prototype_has_time else 2) + mc.latent_dim
+    prev = (0, 0, 0)
+    for B in (1, 5, 128, 129, 1024):
+        Bp = (B + 127) // 128 * 128
+        stash = lib.wgg_generator_stash_floats(cfg, B)
+        assert stash >= T * B * (I0 + 2 * H * L) + T * Bp * 10 * H * L + 8 * Bp * H
+        assert stash >= T * B * (I0 + 12 * H * L)                      # the row-major layout fits too
+        fwd, bwd = lib.wgg_generator_workspace_floats(cfg, B, 0), lib.wgg_generator_workspace_floats(cfg, B, 1)
+        assert fwd >= T * B * (I0 + 4 * H) + T * Bp * 8 * H + 8 * Bp * H  # x0, two hseq, padded gate buffer, latent term
+        assert bwd >= T * B * (3 + 2 * 2 * H) + T * B * (8 * H + 4 * H + 8 * H)  # dpre/dh/dx + daT, hT x2, da row-major copy
+        assert (stash, fwd, bwd) > prev or B == 1
+        assert stash >= prev[0] and fwd >= prev[1] and bwd >= prev[2]
+        prev = (stash, fwd, bwd)
+
+
 def test_state_dict_contract_default():
     """Keys / shapes / order listed in SURVEY.md section 8b (measured on the reference)."""
     G = wgg.Generator()
