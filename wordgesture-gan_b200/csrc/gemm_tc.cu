@@ -8,13 +8,19 @@
 //   * one elected thread issues the MMAs (K-major SWIZZLE_128B shared-memory descriptors, K advanced by 32 bytes inside
 //     the swizzle atom), tcgen05.commit releases the stage;
 //   * eight epilogue warps (two per TMEM lane quarter, one per 128-column half) read the accumulators with tcgen05.ld and
-//     write C rows (bias - staged once in shared memory - add, or read-modify-write).
+//     write C rows (bias - staged once in shared memory - add, or read-modify-write), or - GemmP::out_chunk - the gate buffer
+//     in the chunked order [t][tile of 128 gestures][columns / 4][128 rows][4 floats] of the recurrence kernels;
+//   * split-K (the weight gradients: K = T * B): blockIdx.z also enumerates k ranges, each writing its own dense partial
+//     slice, reduced in fixed order.  Weight / input gradients reach this "NT" form through K-major TF32 images of their
+//     operands (transpose_tf32_kernel; unchunk_da_kernel in lstm.cu).
 // TF32 operands are 4 bytes each, so the tile has to be this large for the tensor pipe not to starve on L2 bandwidth.
-// Operand values are taken as they are (the tensor core reads the upper 19 bits of each fp32: truncation).
+// Operand values are taken as they are (the tensor core reads the upper 19 bits of each fp32: truncation); the producers of
+// h, da and the transposed images round to nearest.
 //
-// The same pipeline carries the per-timestep recurrence of the scaled regime with the LSTM cell fused into the epilogue
-// (gemm_tc_lstm_fwd_kernel / gemm_tc_lstm_bwd_kernel below): one launch per timestep and layer instead of a GEMM that
-// read-modify-writes the gate buffer followed by a cell kernel.
+// The same pipeline carries the recurrence of the scaled regime with the LSTM cell fused into the epilogue:
+//   * gemm_tc_lstm_fwd_kernel / gemm_tc_lstm_bwd_kernel: one launch per timestep and layer (any hidden size), programmatic
+//     dependent launch between consecutive steps;
+//   * lstm128_tc_fwd_kernel: persistent over all timesteps for gen_hidden_dim = 128 (h tile and cell state stay on the SM).
 #include <cuda.h>
 
 #include "tc_common.cuh"
