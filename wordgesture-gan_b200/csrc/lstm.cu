@@ -537,9 +537,12 @@ int64_t rec_generic_scratch_floats(int H, int64_t B, int backward) {
 // K-major operand images of the tcgen05 weight / input-gradient GEMMs of the step-by-step path (backward only):
 // da^T [2][4H][T B] | two ping-pong h^T / input^T buffers [2H][T B] | W_ih^T [2][maxI][4H] | row-major copy of da
 // [2][T B][4H] (chunked stash only: the input-gradient GEMM and the bias sums read it)  (+ alignment slack)
-int64_t wgrad_tc_scratch_floats(int H, int64_t TB, int64_t maxI) {
+int64_t wgrad_tc_scratch_floats(int H, int T, int64_t B, int64_t maxI) {
   if (rec_has_persistent_kernel(H)) return 0;
-  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + TB * 8 * H + 16;
+  const int64_t TB = (int64_t)T * B;
+  const int64_t nblk = (int64_t)T * ((B + 127) / 128);  // (t, tile) blocks of the chunked layout
+  // + first-stage bias-gradient partials [2][T * tiles][4H] written by unchunk_da_kernel
+  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + TB * 8 * H + 2 * nblk * 4 * H + 32;
 }
 
 int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
@@ -646,6 +649,32 @@ int64_t fwd_gate_floats(const GenLayout& g, int64_t B) {
   return (int64_t)g.T * (rec_has_persistent_kernel(g.H) ? B : pad128(B)) * 8 * g.H;
 }
 
+// second stage of the bias gradients: out[d][col] (+)= sum over the S blocks of colpart[d][s][col], the same into out2.
+// block = 32 columns x 8 interleaved segments of the S partials (8 independent loads in flight per thread), fixed order.
+__global__ void __launch_bounds__(256) colpart_reduce_kernel(const float* __restrict__ colpart, int S, int C4, float* __restrict__ out,
+                                                             float* __restrict__ out2, int64_t bsOut) {
+  __shared__ float part[8][32];
+  const int c = threadIdx.x & 31, seg = threadIdx.x >> 5, d = blockIdx.y;
+  const int col = blockIdx.x * 32 + c;
+  const float* p = colpart + (int64_t)d * S * C4 + col;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int s = seg;
+  for (; s + 56 < S; s += 64) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += p[(int64_t)(s + 8 * j) * C4];
+  }
+  for (; s < S; s += 8) acc[0] += p[(int64_t)s * C4];
+  part[seg][c] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (seg == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][c];
+    out[(int64_t)d * bsOut + col] += tot;
+    if (out2) out2[(int64_t)d * bsOut + col] += tot;
+  }
+}
+
 // Stash of a grad-carrying forward: x0 | hseq[l] | gates[l] | cseq[l] (| zb).  In the scaled regime the gate and c buffers
 // are padded to whole 128-gesture tiles (the chunked order of the persistent H = 128 kernels needs whole tiles; the row-major
 // order simply leaves the tail unused) and the per-gesture latent term of the layer-0 projection (zb) lives here too.
@@ -671,8 +700,11 @@ void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
 // [dir][t][tile][columns / 4][128][4] (chunked da, TF32-rounded by BPTT) -> daT [dir][column][T B] (K-major image for the weight
 // gradients) and da_rm [dir][T B][columns] (row-major copy for the input-gradient GEMM and the bias sums).
 // block = (t * tiles + tile, group of 32 columns, dir); 256 threads; both outputs written in 128-byte runs.
+// colpart [dir][t * tiles + tile][columns]: the block's column sums over its (valid) rows - first stage of the bias
+// gradients db_ih = db_hh = sum over (t, b) of da, reduced in fixed order by reduce_partials afterwards.
 __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict__ dac, float* __restrict__ daT,
-                                                         float* __restrict__ da_rm, int T, int64_t B, int C4) {
+                                                         float* __restrict__ da_rm, float* __restrict__ colpart, int T, int64_t B,
+                                                         int C4) {
   __shared__ float tile[128][33];                   // [row][column]: source of the row-major copy
   __shared__ __align__(16) float tileT[32][132];    // [column][row]: source of the K-major image
   const int tiles = (int)((B + 127) / 128);
@@ -708,6 +740,24 @@ __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict
       *reinterpret_cast<float4*>(da_rm + ((int64_t)d * TB + m0 + r) * C4 + cg * 32 + c) =
           make_float4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);
   }
+  {  // column sums: thread = (column, segment of 16 rows); the eight segment sums are combined in fixed order
+    const int c = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    float sum = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = seg * 16 + rr;
+      if (r < nrows) sum += tile[r][c];
+    }
+    __syncthreads();           // every read of tileT above is done: reuse its first rows as scratch
+    tileT[seg][c] = sum;
+    __syncthreads();
+    if (seg == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += tileT[k][c];
+      colpart[((int64_t)d * gridDim.x + blockIdx.x) * C4 + cg * 32 + c] = tot;
+    }
+  }
 }
 
 }  // namespace
@@ -742,7 +792,7 @@ extern "C" int64_t wgg_generator_workspace_floats(const wgg_model_cfg* cfg, int6
   // dpre | dh | dx | split-K partials | column-sum scratch | (tcgen05 path: its own backward workspace)
   return TB * (g.C + 2 * maxI) + gemm_splitk_ws_floats(4 * g.H, maxI, 2) + colsum_ws_floats(4 * g.H, 2) +
          generator_tc_bwd_workspace_floats(cfg, B) + rec_generic_scratch_floats(g.H, B, 1) +
-         wgrad_tc_scratch_floats(g.H, TB, maxI) + 32;  // + alignment slack of the sub-buffers
+         wgrad_tc_scratch_floats(g.H, g.T, B, maxI) + 32;  // + alignment slack of the sub-buffers
 }
 
 namespace {
@@ -935,6 +985,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
   float* wihT = hT[1] + TB * 2 * H;                                    // [2][I][4H]
   float* da_rm = wihT + 2 * maxI * H4;                                 // [2][T B][4H] (chunked stash only)
   if (reinterpret_cast<uintptr_t>(da_rm) & 15) da_rm += 4 - ((reinterpret_cast<uintptr_t>(da_rm) & 15) >> 2);
+  float* colpart = da_rm + TB * 2 * H4;                                // [2][T * tiles][4H] bias-gradient partials
   int hcur = 0;                                                        // hT[hcur] = transposed output of the current layer
   float* zb_stash = nullptr;
   if (!tcp && !rec_has_persistent_kernel(H) && g.pd <= 4) {
@@ -983,7 +1034,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       // chunked da -> K-major image (weight gradients) + row-major copy (input gradient, bias sums, layer-0 weight gradient)
       dim3 ug((unsigned)(g.T * (pad128(B) / 128)), (unsigned)(H4 / 32), 2);
       ProfScope prof(ctx, "transpose_tf32_kernel", st, 0.0, 12.0 * (double)TB * H4 * 2, "unchunk_da_kernel");
-      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, g.T, B, H4);
+      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, colpart, g.T, B, H4);
       WGG_CHECK_LAUNCH(ctx, "unchunk_da_kernel");
       da = da_rm;
     }
@@ -1033,9 +1084,14 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       WGG_TRY(gemm_launch(ctx, p, st));
     }
     if (tc_ih) hcur ^= 1;  // the input's image is the next (lower) layer's output image
-    // db_ih[d] = db_hh[d] += column sums of da[d]
-    WGG_TRY(colsum_launch(ctx, da, TB, H4, H4, 2, TB * H4, dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1,
-                          csws, st));
+    // db_ih[d] = db_hh[d] += column sums of da[d] (chunked: second stage over the partials of the unchunk pass)
+    if (ch) {
+      colpart_reduce_kernel<<<dim3((unsigned)(H4 / 32), 2), 256, 0, st>>>(colpart, (int)(g.T * (pad128(B) / 128)), H4,
+                                                                       dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l]);
+      WGG_CHECK_LAUNCH(ctx, "colpart_reduce_kernel");
+    } else
+      WGG_TRY(colsum_launch(ctx, da, TB, H4, H4, 2, TB * H4, dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1,
+                            csws, st));
     if (l > 0 || dz) {
       const bool tc_dx = wtc && I >= 128 && (I & 3) == 0;
       if (tc_dx) WGG_TRY(transpose_image_launch(ctx, lp, g.dir_stride[l], wihT, H4, I, 2, st));  // W_ih^T [d][I][4H]
