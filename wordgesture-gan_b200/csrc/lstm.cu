@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) zb_chunk_kernel(const float* __restrict__
   for (int k = 0; k < 64; ++k) zr[k] = (k < Z && b < B) ? __ldg(z + b * Z + k) : 0.f;
   const float* wd = w + d * dir_stride;
   float* out = zbc + (((int64_t)d * gridDim.x + tile) * (H4 / 4) * 128 + rl) * 4;
-  for (int n4 = 0; n4 < H4 / 4; ++n4) {
+  for (int n4 = blockIdx.z; n4 < H4 / 4; n4 += gridDim.z) {  // column groups spread over blockIdx.z: enough blocks to fill the SMs
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -893,7 +893,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
     const bool chunked = (!stash || stash_chunk_enabled()) && layer_chunked(ctx, g, B, l, in, lp, gates, hout, zb);
     const GemmP p = xproj_gemm(g, B, l, in, lp, gates, chunked && l > 0);
     if (l == 0 && zb && chunked) {
-      dim3 gz((unsigned)tiles, 2);
+      dim3 gz((unsigned)tiles, 2, 16);
       zb_chunk_kernel<<<gz, 128, 0, st>>>(z, lp, g.dir_stride[l], g.off_bih[l], g.off_bhh[l], zb, B, g.Z, g.pd, I, 4 * g.H);
       WGG_CHECK_LAUNCH(ctx, "zb_chunk_kernel");
       dim3 grid((unsigned)tiles, 2, (unsigned)(4 * g.H / 16));
