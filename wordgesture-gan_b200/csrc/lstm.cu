@@ -541,8 +541,8 @@ int64_t wgrad_tc_scratch_floats(int H, int T, int64_t B, int64_t maxI) {
   if (rec_has_persistent_kernel(H)) return 0;
   const int64_t TB = (int64_t)T * B;
   const int64_t nblk = (int64_t)T * ((B + 127) / 128);  // (t, tile) blocks of the chunked layout
-  // + first-stage bias-gradient partials [2][T * tiles][4H] written by unchunk_da_kernel
-  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + TB * 8 * H + 2 * nblk * 4 * H + 32;
+  // + first-stage partials [planes][2][T * tiles][4H] written by unchunk_da_kernel (bias sums; layer 0: + 3 prototype planes)
+  return TB * 8 * H + 2 * TB * 2 * H + 2 * maxI * 4 * H + TB * 8 * H + 4 * 2 * nblk * 4 * H + 32;  // 4 planes (layer 0)
 }
 
 int rec_fwd_generic(wgg_ctx* ctx, int H, float* gates, const float* lp, int64_t dir_stride, int64_t off_whh, float* hseq,
@@ -652,7 +652,7 @@ int64_t fwd_gate_floats(const GenLayout& g, int64_t B) {
 // second stage of the bias gradients: out[d][col] (+)= sum over the S blocks of colpart[d][s][col], the same into out2.
 // block = 32 columns x 8 interleaved segments of the S partials (8 independent loads in flight per thread), fixed order.
 __global__ void __launch_bounds__(256) colpart_reduce_kernel(const float* __restrict__ colpart, int S, int C4, float* __restrict__ out,
-                                                             float* __restrict__ out2, int64_t bsOut) {
+                                                             float* __restrict__ out2, int64_t bsOut, int64_t ostride) {
   __shared__ float part[8][32];
   const int c = threadIdx.x & 31, seg = threadIdx.x >> 5, d = blockIdx.y;
   const int col = blockIdx.x * 32 + c;
@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(256) colpart_reduce_kernel(const float* __rest
     float tot = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += part[k][c];
-    out[(int64_t)d * bsOut + col] += tot;
-    if (out2) out2[(int64_t)d * bsOut + col] += tot;
+    out[(int64_t)d * bsOut + col * ostride] += tot;
+    if (out2) out2[(int64_t)d * bsOut + col * ostride] += tot;
   }
 }
 
@@ -702,11 +702,15 @@ void stash_view(const GenLayout& g, int64_t B, float* s, StashView* v) {
 // block = (t * tiles + tile, group of 32 columns, dir); 256 threads; both outputs written in 128-byte runs.
 // colpart [dir][t * tiles + tile][columns]: the block's column sums over its (valid) rows - first stage of the bias
 // gradients db_ih = db_hh = sum over (t, b) of da, reduced in fixed order by reduce_partials afterwards.
+// Layer 0 (x0 != nullptr: the stashed [T][B][I0] input, whose first pd columns are the prototype point): three more planes
+// colpart[1 + k] = sum over the rows of da * prototype column k - first stage of dW_ih[:, k], k < pd <= 3 (the latent columns of
+// dW_ih come from the time-summed da, sum_t_chunk_kernel: x0's latent part does not depend on t).  Plane stride 2 * blocks * C4.
 __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict__ dac, float* __restrict__ daT,
                                                          float* __restrict__ da_rm, float* __restrict__ colpart, int T, int64_t B,
-                                                         int C4) {
+                                                         int C4, const float* __restrict__ x0, int I0, int pd) {
   __shared__ float tile[128][33];                   // [row][column]: source of the row-major copy
   __shared__ __align__(16) float tileT[32][132];    // [column][row]: source of the K-major image
+  __shared__ float ps[128][3];                      // layer 0: the rows' prototype point at this timestep
   const int tiles = (int)((B + 127) / 128);
   const int t = blockIdx.x / tiles, tl = blockIdx.x % tiles, cg = blockIdx.y, d = blockIdx.z;
   const int64_t TB = (int64_t)T * B;
@@ -717,10 +721,15 @@ __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict
     tile[r][4 * ch] = v.x; tile[r][4 * ch + 1] = v.y; tile[r][4 * ch + 2] = v.z; tile[r][4 * ch + 3] = v.w;
     tileT[4 * ch][r] = v.x; tileT[4 * ch + 1][r] = v.y; tileT[4 * ch + 2][r] = v.z; tileT[4 * ch + 3][r] = v.w;
   }
-  __syncthreads();
   const int64_t b0 = (int64_t)tl * 128;
   const int nrows = B - b0 < 128 ? (int)(B - b0) : 128;
   const int64_t m0 = (int64_t)t * B + b0;
+  if (x0)
+    for (int i = threadIdx.x; i < 128 * 3; i += 256) {
+      const int r = i / 3, k = i % 3;
+      ps[r][k] = (r < nrows && k < pd) ? __ldg(x0 + (m0 + r) * I0 + k) : 0.f;
+    }
+  __syncthreads();
   if ((B & 3) == 0) {  // 16-byte stores (T B and the tile offsets are multiples of 4)
     for (int i = threadIdx.x; i < 32 * 32; i += 256) {  // daT: column-major runs of 128 rows, 4 rows per store
       const int c = i >> 5, r = (i & 31) * 4;
@@ -742,22 +751,52 @@ __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict
   }
   {  // column sums: thread = (column, segment of 16 rows); the eight segment sums are combined in fixed order
     const int c = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    float sum = 0.f;
+    float sum = 0.f, sp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) {
       const int r = seg * 16 + rr;
-      if (r < nrows) sum += tile[r][c];
+      if (r < nrows) {
+        const float v = tile[r][c];
+        sum += v;
+        if (x0) { sp[0] += v * ps[r][0]; sp[1] += v * ps[r][1]; sp[2] += v * ps[r][2]; }
+      }
     }
     __syncthreads();           // every read of tileT above is done: reuse its first rows as scratch
     tileT[seg][c] = sum;
+    if (x0) { tileT[8 + seg][c] = sp[0]; tileT[16 + seg][c] = sp[1]; tileT[24 + seg][c] = sp[2]; }
     __syncthreads();
-    if (seg == 0) {
+    const int planes = x0 ? 4 : 1;
+    if (seg < planes) {        // warp `seg` combines plane `seg` in fixed order
       float tot = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) tot += tileT[k][c];
-      colpart[((int64_t)d * gridDim.x + blockIdx.x) * C4 + cg * 32 + c] = tot;
+      for (int k = 0; k < 8; ++k) tot += tileT[8 * seg + k][c];
+      colpart[(((int64_t)seg * 2 + d) * gridDim.x + blockIdx.x) * C4 + cg * 32 + c] = tot;
     }
   }
+}
+
+// S[d][b][col] = sum over t of da[d][t][b][col] (chunked da -> row-major S): the latent columns of layer 0's input and the
+// latent-code gradient only see the time-summed da (x0's latent part is the same at every timestep).
+// block = 128 gestures of one tile x one 4-column chunk; coalesced 16-byte loads.
+__global__ void __launch_bounds__(128) sum_t_chunk_kernel(const float* __restrict__ dac, float* __restrict__ S, int T, int64_t B,
+                                                          int C4) {
+  const int tl = blockIdx.x, q = blockIdx.y, d = blockIdx.z, rl = threadIdx.x, tiles = gridDim.x;
+  const int64_t tstride = (int64_t)tiles * (C4 / 4) * 512;
+  const float* p = dac + (((int64_t)d * T * tiles + tl) * (C4 / 4) + q) * 512 + rl * 4;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int t = 0;
+  for (; t + 1 < T; t += 2) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)t * tstride);
+    const float4 v1 = *reinterpret_cast<const float4*>(p + (int64_t)(t + 1) * tstride);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+  }
+  if (t < T) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p + (int64_t)t * tstride);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+  }
+  const int64_t b = (int64_t)tl * 128 + rl;
+  if (b < B) *reinterpret_cast<float4*>(S + ((int64_t)d * B + b) * C4 + 4 * q) = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
 }
 
 }  // namespace
@@ -1030,12 +1069,20 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     else WGG_TRY(rec_bwd_launch(ctx, H, da, sv.cseq[l], lp, g.dir_stride[l], g.off_whh[l], dh, rec_scratch, g.T, B, st));
     const bool tc_ih = wtc && I >= 128 && (I & 3) == 0;   // layer 0 (I0 = C + Z columns) stays on the mma.sync engine
     const bool tc_hh = wtc && H >= 128 && g.T > 1;
+    // Layer 0 on the chunked stash: its input x0 = [prototype(t, b) | z(b)] makes dW_ih and dz cheap - the prototype columns are
+    // pd weighted column sums of da (second planes of the unchunk pass), the latent columns and dz only need the time-summed da
+    // (K = B instead of K = T B) - instead of two K = T B / N = 35 contractions on the mma.sync engine.
+    const bool l0_fused = ch && l == 0 && g.pd <= 3 && g.T >= 4;
     if (ch) {
       // chunked da -> K-major image (weight gradients) + row-major copy (input gradient, bias sums, layer-0 weight gradient)
       dim3 ug((unsigned)(g.T * (pad128(B) / 128)), (unsigned)(H4 / 32), 2);
       ProfScope prof(ctx, "transpose_tf32_kernel", st, 0.0, 12.0 * (double)TB * H4 * 2, "unchunk_da_kernel");
-      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, colpart, g.T, B, H4);
+      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, colpart, g.T, B, H4, l0_fused ? sv.x0 : nullptr, g.I0, g.pd);
       WGG_CHECK_LAUNCH(ctx, "unchunk_da_kernel");
+      if (l0_fused) {  // time-summed da (row-major [2][B][4H]) into the free dx buffer
+        sum_t_chunk_kernel<<<dim3((unsigned)(pad128(B) / 128), (unsigned)(H4 / 4), 2), 128, 0, st>>>(da, dx, g.T, B, H4);
+        WGG_CHECK_LAUNCH(ctx, "sum_t_chunk_kernel");
+      }
       da = da_rm;
     }
     if (tc_ih || tc_hh) {
@@ -1051,6 +1098,20 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       p.C = dlp; p.scm = I; p.scn = 1; p.accumulate = 1;
       p.nbatch = 2; p.bsA = TB * H4; p.bsB = 0; p.bsC = g.dir_stride[l];
       p.splitk = 2; p.partial = part;  // > 1: the tcgen05 engine chooses its own split count
+      WGG_TRY(gemm_launch(ctx, p, st));
+    } else if (l0_fused) {
+      const int nblk = (int)(g.T * (pad128(B) / 128));
+      for (int k = 0; k < g.pd; ++k) {  // dW_ih[d][:, k] += second stage over plane 1 + k
+        colpart_reduce_kernel<<<dim3((unsigned)(H4 / 32), 2), 256, 0, st>>>(colpart + (int64_t)(1 + k) * 2 * nblk * H4, nblk, H4,
+                                                                         dlp + k, nullptr, g.dir_stride[l], I);
+        WGG_CHECK_LAUNCH(ctx, "colpart_reduce_kernel");
+      }
+      GemmP p;  // dW_ih[d][:, pd:] (4H x Z) += S[d]^T (4H x B) * z (B x Z);  z = the latent columns of x0 at t = 0
+      p.tag = "gemm_kernel/lstm_dWih0_z";
+      p.A = dx; p.M = H4; p.K = B; p.sam = 1; p.sak = H4;
+      p.B = sv.x0 + g.pd; p.N = g.Z; p.sbk = I; p.sbn = 1;
+      p.C = dlp + g.pd; p.scm = I; p.scn = 1; p.accumulate = 1; p.force_fp32 = 1;
+      p.nbatch = 2; p.bsA = B * H4; p.bsB = 0; p.bsC = g.dir_stride[l];
       WGG_TRY(gemm_launch(ctx, p, st));
     } else {
       GemmP p;  // dW_ih[d] (4H x I) += da[d]^T * in
@@ -1087,11 +1148,24 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     // db_ih[d] = db_hh[d] += column sums of da[d] (chunked: second stage over the partials of the unchunk pass)
     if (ch) {
       colpart_reduce_kernel<<<dim3((unsigned)(H4 / 32), 2), 256, 0, st>>>(colpart, (int)(g.T * (pad128(B) / 128)), H4,
-                                                                       dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l]);
+                                                                       dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1);
       WGG_CHECK_LAUNCH(ctx, "colpart_reduce_kernel");
     } else
       WGG_TRY(colsum_launch(ctx, da, TB, H4, H4, 2, TB * H4, dlp + g.off_bih[l], dlp + g.off_bhh[l], g.dir_stride[l], 1,
                             csws, st));
+    if (l0_fused) {
+      if (dz) {
+        for (int d = 0; d < 2; ++d) {
+          GemmP p;  // dz (B x Z) (+)= S[d] (B x 4H) * W_ih[d][:, pd:]
+          p.tag = "gemm_kernel/lstm_dz";
+          p.A = dx + (int64_t)d * B * H4; p.M = B; p.K = H4; p.sam = H4; p.sak = 1;
+          p.B = lp + d * g.dir_stride[l] + g.pd; p.N = g.Z; p.sbk = I; p.sbn = 1;
+          p.C = dz; p.scm = g.Z; p.scn = 1; p.accumulate = d; p.force_fp32 = 1;
+          WGG_TRY(gemm_launch(ctx, p, st));
+        }
+      }
+      return WGG_OK;  // layer 0 was the last layer of the loop; dz is complete
+    }
     if (l > 0 || dz) {
       const bool tc_dx = wtc && I >= 128 && (I & 3) == 0;
       if (tc_dx) WGG_TRY(transpose_image_launch(ctx, lp, g.dir_stride[l], wihT, H4, I, 2, st));  // W_ih^T [d][I][4H]
