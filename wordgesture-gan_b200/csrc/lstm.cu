@@ -675,6 +675,103 @@ __global__ void __launch_bounds__(256) colpart_reduce_kernel(const float* __rest
   }
 }
 
+// Output head backward of the scaled path in one pass over hseq (models.py:161-163):
+//   dpre[r][k] = dy (1 - y^2);  dh[r][:] = dpre[r] . Wo;  dWo[k][:] += sum_r dpre[r][k] h[r][:];  dbo[k] += sum_r dpre[r][k]
+// block: slabs of 64 (t, b) rows; thread = (4-column group of the 2H hidden columns, row phase); per-block partial sums of
+// dWo / dbo go to `part` ([blocks][C * K2 + 4]) and are reduced in fixed order by head_bwd_reduce_kernel.
+constexpr int HB_ROWS = 64;
+__global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                             const float* __restrict__ hL, const float* __restrict__ wo,
+                                                             float* __restrict__ dh, float* __restrict__ part, int T, int64_t B,
+                                                             int K2, int C) {
+  extern __shared__ float s_hb[];           // Wo [C][K2] | dpre [HB_ROWS][4] | partial combine [phases][C * K2]
+  float* s_wo = s_hb;
+  float* s_dp = s_wo + C * K2;
+  float* s_pc = s_dp + HB_ROWS * 4;
+  const int ncg = K2 / 4;                   // column groups
+  const int phases = 256 / ncg > 0 ? 256 / ncg : 1;  // row phases (threads beyond phases * ncg idle in the column loop)
+  const int cg = threadIdx.x % ncg, ph = threadIdx.x / ncg;
+  const bool colthread = ph < phases;
+  for (int i = threadIdx.x; i < C * K2; i += 256) s_wo[i] = __ldg(wo + i);
+  float4 accw[4];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) accw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t nrows = (int64_t)T * B;
+  for (int64_t r0 = (int64_t)blockIdx.x * HB_ROWS; r0 < nrows; r0 += (int64_t)gridDim.x * HB_ROWS) {
+    __syncthreads();
+    if (threadIdx.x < HB_ROWS * 4) {
+      const int rr = threadIdx.x >> 2, k = threadIdx.x & 3;
+      const int64_t r = r0 + rr;
+      float v = 0.f;
+      if (r < nrows && k < C) {
+        const int64_t t = r / B, b = r % B;
+        const int64_t src = (b * T + t) * C + k;
+        const float yy = __ldg(y + src);
+        v = __ldg(dy + src) * (1.f - yy * yy);
+      }
+      s_dp[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (colthread) {
+      for (int rr = ph; rr < HB_ROWS; rr += phases) {
+        const int64_t r = r0 + rr;
+        if (r >= nrows) break;
+        const float4 h4 = *reinterpret_cast<const float4*>(hL + r * K2 + 4 * cg);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < C) {
+            const float d = s_dp[rr * 4 + k];
+            const float4 w = *reinterpret_cast<const float4*>(s_wo + k * K2 + 4 * cg);
+            o.x += d * w.x; o.y += d * w.y; o.z += d * w.z; o.w += d * w.w;
+            accw[k].x += d * h4.x; accw[k].y += d * h4.y; accw[k].z += d * h4.z; accw[k].w += d * h4.w;
+            if (cg == 0) accb[k] += d;
+          }
+        }
+        *reinterpret_cast<float4*>(dh + r * K2 + 4 * cg) = o;
+      }
+    }
+  }
+  // combine the row phases in fixed order, one partial row per block
+  __syncthreads();
+  if (colthread)
+    for (int k = 0; k < C; ++k) *reinterpret_cast<float4*>(s_pc + ((int64_t)ph * C + k) * K2 + 4 * cg) = accw[k];
+  __shared__ float s_b[64][4];
+  if (colthread && cg == 0)
+    for (int k = 0; k < 4; ++k) s_b[ph][k] = accb[k];
+  __syncthreads();
+  float* prow = part + (int64_t)blockIdx.x * (C * K2 + 4);
+  for (int i = threadIdx.x; i < C * K2; i += 256) {
+    float tot = 0.f;
+    for (int q = 0; q < phases; ++q) tot += s_pc[(int64_t)q * C * K2 + i];
+    prow[i] = tot;
+  }
+  if (threadIdx.x < 4) {
+    float tot = 0.f;
+    for (int q = 0; q < phases; ++q) tot += s_b[q][threadIdx.x];
+    prow[C * K2 + threadIdx.x] = tot;
+  }
+}
+
+// dWo (C x K2, contiguous) += sum over the blocks' partials; dbo (C) likewise
+__global__ void __launch_bounds__(256) head_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int K2, int C,
+                                                              float* __restrict__ dwo, float* __restrict__ dbo) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int n = C * K2 + 4, nw = C * K2;
+  if (i >= n || (i >= nw && i - nw >= C)) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int s = 0;
+  for (; s + 3 < nblocks; s += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += part[(int64_t)(s + j) * n + i];
+  }
+  for (; s < nblocks; ++s) acc[0] += part[(int64_t)s * n + i];
+  const float tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  if (i < nw) dwo[i] += tot;
+  else dbo[i - nw] += tot;
+}
+
 // Stash of a grad-carrying forward: x0 | hseq[l] | gates[l] | cseq[l] (| zb).  In the scaled regime the gate and c buffers
 // are padded to whole 128-gesture tiles (the chunked order of the persistent H = 128 kernels needs whole tiles; the row-major
 // order simply leaves the tail unused) and the per-gesture latent term of the layer-0 projection (zb) lives here too.
@@ -743,7 +840,7 @@ __global__ void __launch_bounds__(256) unchunk_da_kernel(const float* __restrict
       if (r < nrows) daT[((int64_t)d * C4 + cg * 32 + c) * TB + m0 + r] = tileT[c][r];
     }
   }
-  for (int i = threadIdx.x; i < 8 * 128; i += 256) {  // da_rm: rows of 32 columns, 4 columns per store
+  for (int i = threadIdx.x; da_rm && i < 8 * 128; i += 256) {  // da_rm: rows of 32 columns, 4 columns per store
     const int r = i >> 3, c = (i & 7) * 4;
     if (r < nrows)
       *reinterpret_cast<float4*>(da_rm + ((int64_t)d * TB + m0 + r) * C4 + cg * 32 + c) =
@@ -938,7 +1035,7 @@ extern "C" int wgg_generator_forward(wgg_ctx* ctx, const wgg_model_cfg* cfg, con
       dim3 grid((unsigned)tiles, 2, (unsigned)(4 * g.H / 16));
       ProfScope prof(ctx, "xproj0_kernel", st, 2.0 * TB * 8.0 * g.H * g.pd, 4.0 * TB * 8.0 * g.H, "xproj0_kernel");
       const size_t xsm = (size_t)128 * (XP_TS * g.C + 1) * sizeof(float);
-      if (!wgg_smem_ok(ctx, xproj0_chunk_kernel, xsm))
+      if (xsm > 200 * 1024 || !wgg_smem_ok(ctx, xproj0_chunk_kernel, 200 * 1024))
         return wgg_fail(ctx, WGG_ECUDA, "xproj0_chunk_kernel: cannot reserve shared memory%s");
       xproj0_chunk_kernel<<<grid, 128, xsm, st>>>(proto, zb, lp, g.dir_stride[l], gates, g.T, B, g.C, g.pd, I, 4 * g.H);
       WGG_CHECK_LAUNCH(ctx, "xproj0_chunk_kernel");
@@ -1038,9 +1135,29 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
                                         g.off_bhh, B, stash, out, dout, g.off_wo, g.off_bo, dz, tcws,
                                         generator_tc_bwd_workspace_floats(cfg, B), st);
   }
+  const float* hL = sv.hseq[g.L - 1];
+  const int K2 = 2 * H;
+  const int hb_ncg = K2 / 4, hb_ph = 256 / hb_ncg > 0 ? 256 / hb_ncg : 1;
+  const size_t hb_smem = ((size_t)g.C * K2 + HB_ROWS * 4 + (size_t)hb_ph * g.C * K2) * sizeof(float);
+  // scaled path: the whole head backward in one pass over hseq (the partial rows fit the split-K scratch)
+  int64_t hb_blocks = cdiv64(TB, HB_ROWS);
+  if (hb_blocks > 4 * (int64_t)ctx->sm_count) hb_blocks = 4 * (int64_t)ctx->sm_count;
+  if (!rec_has_persistent_kernel(H) && g.C <= 4 && (K2 & 3) == 0 && hb_ncg <= 256 && hb_smem <= 200 * 1024 &&
+      hb_blocks * (g.C * K2 + 4) <= gemm_splitk_ws_floats(H4, maxI, 2) &&
+      ((reinterpret_cast<uintptr_t>(hL) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(part)) & 15) == 0) {
+    if (!wgg_smem_ok(ctx, head_bwd_fused_kernel, 200 * 1024))  // once per context: the limit must cover every hidden size
+      return wgg_fail(ctx, WGG_ECUDA, "head_bwd_fused_kernel: cannot reserve shared memory%s");
+    {
+      ProfScope prof(ctx, "head_bwd_fused_kernel", st, 4.0 * TB * K2 * g.C, 8.0 * TB * K2, "head_bwd_fused_kernel");
+      head_bwd_fused_kernel<<<(unsigned)hb_blocks, 256, hb_smem, st>>>(out, dout, hL, params + g.off_wo, dh, part, g.T, B, K2, g.C);
+      WGG_CHECK_LAUNCH(ctx, "head_bwd_fused_kernel");
+    }
+    head_bwd_reduce_kernel<<<(unsigned)cdiv64(g.C * K2 + 4, 256), 256, 0, st>>>(part, (int)hb_blocks, K2, g.C,
+                                                                               dparams + g.off_wo, dparams + g.off_bo);
+    WGG_CHECK_LAUNCH(ctx, "head_bwd_reduce_kernel");
+  } else {
   head_bwd_kernel<<<ew_grid(TB * g.C), 256, 0, st>>>(out, dout, dpre, g.T, B, g.C);
   WGG_CHECK_LAUNCH(ctx, "head_bwd_kernel");
-  const float* hL = sv.hseq[g.L - 1];
   {
     GemmP p;  // dWo (C x 2H) += dpre^T * hL
     p.tag = "gemm_kernel/head_wgrad";
@@ -1056,6 +1173,7 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
     q.B = params + g.off_wo; q.N = 2 * H; q.sbk = 2 * H; q.sbn = 1;
     q.C = dh; q.scm = 2 * H; q.scn = 1; q.force_fp32 = 1;
     WGG_TRY(gemm_launch(ctx, q, st));
+  }
   }
   for (int l = g.L - 1; l >= 0; --l) {
     const int I = g.in_dim(l);
@@ -1077,7 +1195,9 @@ extern "C" int wgg_generator_backward(wgg_ctx* ctx, const wgg_model_cfg* cfg, co
       // chunked da -> K-major image (weight gradients) + row-major copy (input gradient, bias sums, layer-0 weight gradient)
       dim3 ug((unsigned)(g.T * (pad128(B) / 128)), (unsigned)(H4 / 32), 2);
       ProfScope prof(ctx, "transpose_tf32_kernel", st, 0.0, 12.0 * (double)TB * H4 * 2, "unchunk_da_kernel");
-      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, da_rm, colpart, g.T, B, H4, l0_fused ? sv.x0 : nullptr, g.I0, g.pd);
+      // (layer 0 with every consumer of the row-major copy gone - fused dW_ih / dz, tcgen05 dW_hh - does not write it)
+      unchunk_da_kernel<<<ug, 256, 0, st>>>(da, daT, (l0_fused && tc_hh) ? nullptr : da_rm, colpart, g.T, B, H4,
+                                            l0_fused ? sv.x0 : nullptr, g.I0, g.pd);
       WGG_CHECK_LAUNCH(ctx, "unchunk_da_kernel");
       if (l0_fused) {  // time-summed da (row-major [2][B][4H]) into the free dx buffer
         sum_t_chunk_kernel<<<dim3((unsigned)(pad128(B) / 128), (unsigned)(H4 / 4), 2), 128, 0, st>>>(da, dx, g.T, B, H4);
